@@ -1,0 +1,1232 @@
+// hdk_amg_setup.cu -- BoomerAMG setup on the device (north-star item 4):
+// strength of connection, PMIS coarsening, extended+i interpolation with truncation,
+// R = P^T, Galerkin RAP with hash accumulators, l1 norms, dense coarsest inverse.
+// Stands in for HYPRE_BoomerAMGSetup (reference trigger src/internal/solver.c:296,
+// src/internal/precon.c:107; options src/internal/amg.c:863-1035).
+//
+// Parity contract: integer results (S, C/F splitting, sparsity of P and of every coarse
+// operator, including the storage order inside rows) are bit-identical to the CPU oracle
+// (oracle/amg_setup.c), and so are the floating-point values, because every row is
+// accumulated by one thread in the oracle's order with separately rounded multiply/add.
+#include "hdk_amg.cuh"
+#include <cub/cub.cuh>
+#include <algorithm>
+#include <math.h>
+
+namespace hdk {
+
+#define C_PT 1
+#define F_PT -1
+#define SF_PT -3
+
+static const int64_t SCRATCH_BUDGET = (int64_t)1 << 30; // hash slots per chunk (4-8 GB)
+
+// =====================================================================================
+// small utilities
+// =====================================================================================
+__global__ void k_cast_i64(const int *in, int64_t *out, int n)
+{
+   int i = blockIdx.x * blockDim.x + threadIdx.x;
+   if (i < n) out[i] = (int64_t)in[i];
+}
+
+static int exclusive_scan_i64(const int *in, int64_t *out, int n)
+{
+   k_cast_i64<<<cdiv(n, 256), 256, 0, g.stream>>>(in, out, n);
+   HDK_LAUNCH_CHECK();
+   size_t bytes = 0;
+   HDK_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, bytes, out, out, n, g.stream));
+   char *tmp;
+   HDK_TRY(dalloc(&tmp, bytes));
+   HDK_CUDA(cub::DeviceScan::ExclusiveSum(tmp, bytes, out, out, n, g.stream));
+   g.launches++;
+   dfree(tmp);
+   return HDK_OK;
+}
+
+__global__ void k_chunk_bounds(const int64_t *off, int n, int64_t budget, int nchunks, int *bounds)
+{
+   int c = blockIdx.x * blockDim.x + threadIdx.x;
+   if (c > nchunks) return;
+   if (c == nchunks) { bounds[c] = n; return; }
+   int64_t target = (int64_t)c * budget;
+   int lo = 0, hi = n;
+   while (lo < hi) { int mid = (lo + hi) >> 1; if (off[mid] >= target) hi = mid; else lo = mid + 1; }
+   bounds[c] = lo;
+}
+
+// rows [bounds[c], bounds[c+1]) use at most `maxsz` scratch slots
+static int plan_chunks(const int64_t *off_d, int n, std::vector<int> &bounds, int64_t &maxsz)
+{
+   int64_t total = 0;
+   HDK_CUDA(cudaMemcpyAsync(&total, off_d + n, sizeof(int64_t), cudaMemcpyDeviceToHost, g.stream));
+   HDK_CUDA(cudaStreamSynchronize(g.stream));
+   if (total <= SCRATCH_BUDGET) { bounds = {0, n}; maxsz = total; return HDK_OK; }
+   int  nch = (int)((total + SCRATCH_BUDGET - 1) / SCRATCH_BUDGET);
+   int *bd;
+   HDK_TRY(dalloc(&bd, (size_t)nch + 1));
+   k_chunk_bounds<<<cdiv(nch + 1, 128), 128, 0, g.stream>>>(off_d, n, SCRATCH_BUDGET, nch, bd);
+   HDK_LAUNCH_CHECK();
+   bounds.resize((size_t)nch + 1);
+   HDK_CUDA(cudaMemcpyAsync(bounds.data(), bd, sizeof(int) * ((size_t)nch + 1), cudaMemcpyDeviceToHost, g.stream));
+   HDK_CUDA(cudaStreamSynchronize(g.stream));
+   dfree(bd);
+   bounds.erase(std::unique(bounds.begin(), bounds.end()), bounds.end());
+   maxsz = 0;
+   for (size_t c = 0; c + 1 < bounds.size(); c++)
+   {
+      int64_t o[2];
+      HDK_CUDA(cudaMemcpyAsync(&o[0], off_d + bounds[c], sizeof(int64_t), cudaMemcpyDeviceToHost, g.stream));
+      HDK_CUDA(cudaMemcpyAsync(&o[1], off_d + bounds[c + 1], sizeof(int64_t), cudaMemcpyDeviceToHost, g.stream));
+      HDK_CUDA(cudaStreamSynchronize(g.stream));
+      if (o[1] - o[0] > maxsz) maxsz = o[1] - o[0];
+   }
+   return HDK_OK;
+}
+
+__device__ __forceinline__ int pow2ceil(int v)
+{
+   if (v < 4) return 4;
+   return 1 << (32 - __clz(v - 1));
+}
+
+// open-addressing tables living in global scratch, one per row, keys initialised to -1
+__device__ __forceinline__ unsigned hslot(int key, int cap) { return ((unsigned)key * 2654435761u) >> (__clz(cap) + 1); }
+
+__device__ __forceinline__ bool hset_insert(int *keys, int cap, int key)
+{
+   unsigned h = hslot(key, cap), mask = (unsigned)cap - 1;
+   while (true)
+   {
+      int k = keys[h];
+      if (k == key) return false;
+      if (k == -1) { keys[h] = key; return true; }
+      h = (h + 1) & mask;
+   }
+}
+__device__ __forceinline__ int hmap_find(const int2 *tab, int cap, int key)
+{
+   unsigned h = hslot(key, cap), mask = (unsigned)cap - 1;
+   while (true)
+   {
+      int2 e = tab[h];
+      if (e.x == key) return e.y;
+      if (e.x == -1) return -1;
+      h = (h + 1) & mask;
+   }
+}
+// returns the stored value if present, else stores `val` and returns -1
+__device__ __forceinline__ int hmap_insert(int2 *tab, int cap, int key, int val)
+{
+   unsigned h = hslot(key, cap), mask = (unsigned)cap - 1;
+   while (true)
+   {
+      int2 e = tab[h];
+      if (e.x == key) return e.y;
+      if (e.x == -1) { tab[h] = make_int2(key, val); return -1; }
+      h = (h + 1) & mask;
+   }
+}
+
+// =====================================================================================
+// strength of connection (hypre_BoomerAMGCreateS)
+// =====================================================================================
+struct RowS { double diag, thr; bool weak_all; };
+
+__device__ __forceinline__ RowS row_strength(const int *rp, const double *val, const int *orp, const double *oval,
+                                             int i, double theta, double mrs)
+{
+   RowS   r;
+   int    b = rp[i], e = rp[i + 1];
+   double diag = val[b], row_scale = 0.0, row_sum = diag;
+   for (int k = b + 1; k < e; k++)
+   {
+      double v = val[k];
+      if (diag < 0) row_scale = row_scale > v ? row_scale : v;
+      else row_scale = row_scale < v ? row_scale : v;
+      row_sum = __dadd_rn(row_sum, v);
+   }
+   if (orp)
+      for (int k = orp[i]; k < orp[i + 1]; k++)
+      {
+         double v = oval[k];
+         if (diag < 0) row_scale = row_scale > v ? row_scale : v;
+         else row_scale = row_scale < v ? row_scale : v;
+         row_sum = __dadd_rn(row_sum, v);
+      }
+   r.diag     = diag;
+   r.thr      = __dmul_rn(theta, row_scale);
+   r.weak_all = (fabs(row_sum) > __dmul_rn(fabs(diag), mrs)) && (mrs < 1.0);
+   return r;
+}
+
+template <bool FILL>
+__global__ void k_strength(const int *rp, const int *col, const double *val, const int *orp, const double *oval,
+                           int n, double theta, double mrs, int *cnt, const int *srp, int *scol)
+{
+   int i = blockIdx.x * blockDim.x + threadIdx.x;
+   if (i > n) return;
+   if (i == n) { if (!FILL) cnt[n] = 0; return; }
+   int b = rp[i], e = rp[i + 1], c = 0;
+   int p = FILL ? srp[i] : 0;
+   if (e > b)
+   {
+      RowS r = row_strength(rp, val, orp, oval, i, theta, mrs);
+      if (!r.weak_all)
+         for (int k = b + 1; k < e; k++)
+         {
+            double v      = val[k];
+            bool   strong = (r.diag < 0) ? !(v <= r.thr) : !(v >= r.thr);
+            if (strong) { if (FILL) scol[p++] = col[k]; else c++; }
+         }
+   }
+   if (!FILL) cnt[i] = c;
+}
+
+static int build_strength(const hdk_csr_s &A, double theta, double mrs, DevCSR &S)
+{
+   const DevCSR &D = A.diag;
+   int           n = D.nrows;
+   const int    *orp = A.offd.nnz > 0 ? A.offd.rowptr : nullptr;
+   const double *ov  = A.offd.nnz > 0 ? A.offd.val : nullptr;
+   int *cnt, *srp;
+   HDK_TRY(dalloc(&cnt, (size_t)n + 1));
+   HDK_TRY(dalloc(&srp, (size_t)n + 1));
+   k_strength<false><<<cdiv(n + 1, 256), 256, 0, g.stream>>>(D.rowptr, D.col, D.val, orp, ov, n, theta, mrs, cnt, nullptr, nullptr);
+   HDK_LAUNCH_CHECK();
+   HDK_TRY(exclusive_scan_int(cnt, srp, n + 1));
+   int nnzS = 0;
+   HDK_CUDA(cudaMemcpyAsync(&nnzS, srp + n, sizeof(int), cudaMemcpyDeviceToHost, g.stream));
+   HDK_CUDA(cudaStreamSynchronize(g.stream));
+   dfree(cnt);
+   S = DevCSR();
+   S.nrows = n; S.ncols = n; S.nnz = nnzS; S.rowptr = srp; S.owns = true;
+   HDK_TRY(dalloc(&S.col, (size_t)nnzS + 8));
+   k_strength<true><<<cdiv(n + 1, 256), 256, 0, g.stream>>>(D.rowptr, D.col, D.val, orp, ov, n, theta, mrs, nullptr, srp, S.col);
+   HDK_LAUNCH_CHECK();
+   return HDK_OK;
+}
+
+// =====================================================================================
+// PMIS (hypre_BoomerAMGCoarsenPMIS + hypre_BoomerAMGIndepSet), measures from the
+// Park-Miller stream of hypre_Rand() reached by skip-ahead: seed_k = seed0 * 16807^k mod (2^31-1)
+// =====================================================================================
+__device__ __forceinline__ uint32_t mulmod31(uint32_t a, uint32_t b)
+{
+   const uint64_t M = 2147483647ull;
+   uint64_t p = (uint64_t)a * b;
+   uint64_t r = (p & M) + (p >> 31);
+   r          = (r & M) + (r >> 31);
+   if (r >= M) r -= M;
+   return (uint32_t)r;
+}
+
+__global__ void k_count_cols(const int *col, int nnz, int *cnt)
+{
+   int k = blockIdx.x * blockDim.x + threadIdx.x;
+   if (k < nnz) atomicAdd(cnt + col[k], 1);
+}
+
+__global__ void k_measure(const int *cnt, int n, uint32_t seed0, int64_t goff, double *measure)
+{
+   int i = blockIdx.x * blockDim.x + threadIdx.x;
+   if (i >= n) return;
+   uint64_t e = (uint64_t)(goff + i) + 1; // number of hypre_Rand() calls up to and including row i
+   uint32_t base = 16807u, acc = seed0;
+   while (e)
+   {
+      if (e & 1) acc = mulmod31(acc, base);
+      base = mulmod31(base, base);
+      e >>= 1;
+   }
+   measure[i] = __dadd_rn((double)cnt[i], __ddiv_rn((double)acc, 2147483647.0));
+}
+
+__global__ void k_pmis_init(const int *srp, int n, int *cf, double *measure)
+{
+   int i = blockIdx.x * blockDim.x + threadIdx.x;
+   if (i >= n) return;
+   if (srp[i + 1] == srp[i]) { cf[i] = SF_PT; measure[i] = 0.0; }
+   else cf[i] = 0;
+}
+
+__global__ void k_pmis_mark(int n, int *cf, const double *measure)
+{
+   int i = blockIdx.x * blockDim.x + threadIdx.x;
+   if (i < n && cf[i] == 0 && measure[i] > 1.0) cf[i] = 1;
+}
+
+__global__ void k_pmis_elim(const int *srp, const int *scol, int n, int *cf, const double *measure)
+{
+   int i = blockIdx.x * blockDim.x + threadIdx.x;
+   if (i >= n) return;
+   double mi = measure[i];
+   if (!(mi > 1.0)) return;
+   for (int k = srp[i]; k < srp[i + 1]; k++)
+   {
+      int    j  = scol[k];
+      double mj = measure[j];
+      if (mj > 1.0)
+      {
+         if (mi > mj) cf[j] = 0;
+         else if (mj > mi) cf[i] = 0;
+      }
+   }
+}
+
+__global__ void k_pmis_set(const int *srp, const int *scol, int n, int *cf, double *measure, int *remaining)
+{
+   int  i = blockIdx.x * blockDim.x + threadIdx.x;
+   bool undecided = false;
+   if (i < n)
+   {
+      double mi = measure[i];
+      if (mi > 0.0) // still in the graph
+      {
+         int c = cf[i];
+         if (mi < 1.0) c = F_PT;
+         if (c > 0) c = C_PT;
+         else
+            for (int k = srp[i]; k < srp[i + 1]; k++)
+               if (cf[scol[k]] > 0) { c = F_PT; break; }
+         cf[i] = c;
+         if (c != 0) measure[i] = 0.0; else undecided = true;
+      }
+   }
+   int cnt = __syncthreads_count(undecided);
+   if (threadIdx.x == 0 && cnt) atomicAdd(remaining, cnt);
+}
+
+static int run_pmis(const DevCSR &S, int seed, int64_t goff, int *cf, double *measure, double *measure_keep, int *iters_out)
+{
+   int  n = S.nrows;
+   int *cnt;
+   HDK_TRY(dalloc(&cnt, (size_t)n + 1));
+   HDK_CUDA(cudaMemsetAsync(cnt, 0, sizeof(int) * ((size_t)n + 1), g.stream));
+   if (S.nnz > 0) { k_count_cols<<<cdiv(S.nnz, 256), 256, 0, g.stream>>>(S.col, S.nnz, cnt); HDK_LAUNCH_CHECK(); }
+   uint32_t s0 = seed < 1 ? 1u : (seed >= 2147483647 ? 2147483646u : (uint32_t)seed);
+   k_measure<<<cdiv(n, 256), 256, 0, g.stream>>>(cnt, n, s0, goff, measure);
+   HDK_LAUNCH_CHECK();
+   dfree(cnt);
+   if (measure_keep) HDK_CUDA(cudaMemcpyAsync(measure_keep, measure, sizeof(double) * (size_t)n, cudaMemcpyDeviceToDevice, g.stream));
+   k_pmis_init<<<cdiv(n, 256), 256, 0, g.stream>>>(S.rowptr, n, cf, measure);
+   HDK_LAUNCH_CHECK();
+   int *rem = reinterpret_cast<int *>(g.dscal + S_TMP2);
+   int  iters = 0, hrem = 1;
+   while (hrem > 0 && iters < 1000)
+   {
+      HDK_CUDA(cudaMemsetAsync(rem, 0, sizeof(int), g.stream));
+      k_pmis_mark<<<cdiv(n, 256), 256, 0, g.stream>>>(n, cf, measure);
+      HDK_LAUNCH_CHECK();
+      k_pmis_elim<<<cdiv(n, 256), 256, 0, g.stream>>>(S.rowptr, S.col, n, cf, measure);
+      HDK_LAUNCH_CHECK();
+      k_pmis_set<<<cdiv(n, 256), 256, 0, g.stream>>>(S.rowptr, S.col, n, cf, measure, rem);
+      HDK_LAUNCH_CHECK();
+      HDK_CUDA(cudaMemcpyAsync(&hrem, rem, sizeof(int), cudaMemcpyDeviceToHost, g.stream));
+      HDK_CUDA(cudaStreamSynchronize(g.stream));
+      iters++;
+   }
+   if (iters_out) *iters_out = iters;
+   return HDK_OK;
+}
+
+__global__ void k_cf_flag(const int *cf, int n, int *flag)
+{
+   int i = blockIdx.x * blockDim.x + threadIdx.x;
+   if (i > n) return;
+   flag[i] = (i < n && cf[i] > 0) ? 1 : 0;
+}
+
+// =====================================================================================
+// extended+i interpolation (hypre_BoomerAMGBuildExtPIInterp) + truncation
+// (hypre_BoomerAMGInterpTruncation with hypre_qsort2abs): one thread per row
+// =====================================================================================
+__global__ void k_interp_cap(const int *srp, const int *scol, const int *cf, int n, int *cap)
+{
+   int i = blockIdx.x * blockDim.x + threadIdx.x;
+   if (i > n) return;
+   int c = 0;
+   if (i < n && cf[i] < 0 && cf[i] != SF_PT)
+   {
+      int ub = 0;
+      for (int k = srp[i]; k < srp[i + 1]; k++)
+      {
+         int j = scol[k];
+         if (cf[j] > 0) ub++;
+         else if (cf[j] != SF_PT) ub += srp[j + 1] - srp[j];
+      }
+      c = pow2ceil(2 * ub);
+   }
+   cap[i] = c;
+}
+
+__global__ void k_interp_count(const int *srp, const int *scol, const int *cf, int row0, int row1,
+                               const int64_t *off, int *keys, int max_elmts, int *cnt, int *rowlen)
+{
+   int i = row0 + blockIdx.x * blockDim.x + threadIdx.x;
+   if (i >= row1) return;
+   int c = 0;
+   if (cf[i] > 0) c = 1;
+   else if (cf[i] != SF_PT)
+   {
+      int *tab = keys + (off[i] - off[row0]);
+      int  cap = (int)(off[i + 1] - off[i]);
+      for (int k = srp[i]; k < srp[i + 1]; k++)
+      {
+         int i1 = scol[k];
+         if (cf[i1] > 0) { if (hset_insert(tab, cap, i1)) c++; }
+         else if (cf[i1] != SF_PT)
+            for (int kk = srp[i1]; kk < srp[i1 + 1]; kk++)
+            {
+               int k1 = scol[kk];
+               if (cf[k1] > 0 && hset_insert(tab, cap, k1)) c++;
+            }
+      }
+   }
+   cnt[i]    = c;
+   rowlen[i] = (max_elmts > 0 && c > max_elmts) ? max_elmts : c;
+}
+
+__global__ void k_interp_cap2(const int *srp, const int *cf, const int *cnt, int n, int *cap2)
+{
+   int i = blockIdx.x * blockDim.x + threadIdx.x;
+   if (i > n) return;
+   int c = 0;
+   if (i < n && cf[i] < 0 && cf[i] != SF_PT) c = pow2ceil(2 * (cnt[i] + (srp[i + 1] - srp[i])));
+   cap2[i] = c;
+}
+
+__device__ __forceinline__ void swap2(int *v, double *w, int i, int j)
+{
+   int t = v[i]; v[i] = v[j]; v[j] = t;
+   double d = w[i]; w[i] = w[j]; w[j] = d;
+}
+
+// hypre_qsort2abs without recursion: the partition of every sub-range is independent of the
+// order sub-ranges are visited in, so an explicit stack gives the identical arrangement.
+__device__ void qsort2abs_dev(int *v, double *w, int n)
+{
+   int stl[40], str[40], sp = 0;
+   stl[0] = 0; str[0] = n - 1; sp = 1;
+   while (sp > 0)
+   {
+      sp--;
+      int left = stl[sp], right = str[sp];
+      while (left < right)
+      {
+         swap2(v, w, left, (left + right) / 2);
+         int last = left;
+         for (int i = left + 1; i <= right; i++)
+            if (fabs(w[i]) > fabs(w[left])) swap2(v, w, ++last, i);
+         swap2(v, w, left, last);
+         // recurse on the smaller part first (bounded stack), loop on the other
+         int l1 = left, r1 = last - 1, l2 = last + 1, r2 = right;
+         if (r1 - l1 < r2 - l2)
+         {
+            if (l2 < r2) { stl[sp] = l2; str[sp] = r2; sp++; }
+            left = l1; right = r1;
+         }
+         else
+         {
+            if (l1 < r1) { stl[sp] = l1; str[sp] = r1; sp++; }
+            left = l2; right = r2;
+         }
+      }
+   }
+}
+
+__global__ void k_interp_fill(const int *arp, const int *acol, const double *aval, const int *srp, const int *scol,
+                              const int *cf, const int *f2c, int row0, int row1, const int *cnt,
+                              const int64_t *hoff, int2 *htab, const int64_t *loff, int *lcol, double *lval,
+                              int max_elmts, const int *prp, int *pcol, double *pval)
+{
+   int i = row0 + blockIdx.x * blockDim.x + threadIdx.x;
+   if (i >= row1) return;
+   int p0 = prp[i];
+   if (cf[i] > 0) { pcol[p0] = f2c[i]; pval[p0] = 1.0; return; }
+   if (cf[i] == SF_PT) return;
+   int2   *tab = htab + (hoff[i] - hoff[row0]);
+   int     cap = (int)(hoff[i + 1] - hoff[i]);
+   int    *lc  = lcol + (loff[i] - loff[row0]);
+   double *lv  = lval + (loff[i] - loff[row0]);
+   int     nC  = 0;
+   // discovery of C-hat_i in hypre's order; strong F neighbours are tagged with -2
+   for (int k = srp[i]; k < srp[i + 1]; k++)
+   {
+      int i1 = scol[k];
+      if (cf[i1] > 0)
+      {
+         if (hmap_insert(tab, cap, i1, nC) == -1) { lc[nC] = i1; lv[nC] = 0.0; nC++; }
+      }
+      else if (cf[i1] != SF_PT)
+      {
+         hmap_insert(tab, cap, i1, -2);
+         for (int kk = srp[i1]; kk < srp[i1 + 1]; kk++)
+         {
+            int k1 = scol[kk];
+            if (cf[k1] > 0 && hmap_insert(tab, cap, k1, nC) == -1) { lc[nC] = k1; lv[nC] = 0.0; nC++; }
+         }
+      }
+   }
+   double diagonal = aval[arp[i]];
+   for (int jj = arp[i] + 1; jj < arp[i + 1]; jj++)
+   {
+      int    i1 = acol[jj];
+      double a  = aval[jj];
+      int    m  = hmap_find(tab, cap, i1);
+      if (m >= 0) lv[m] = __dadd_rn(lv[m], a);
+      else if (m == -2)
+      {
+         double sum = 0.0;
+         double sgn = aval[arp[i1]] < 0 ? -1.0 : 1.0;
+         for (int j1 = arp[i1] + 1; j1 < arp[i1 + 1]; j1++)
+         {
+            int    i2 = acol[j1];
+            double v  = aval[j1];
+            if (sgn * v < 0 && (i2 == i || hmap_find(tab, cap, i2) >= 0)) sum = __dadd_rn(sum, v);
+         }
+         if (sum != 0.0)
+         {
+            double distribute = __ddiv_rn(a, sum);
+            for (int j1 = arp[i1] + 1; j1 < arp[i1 + 1]; j1++)
+            {
+               int    i2 = acol[j1];
+               double v  = aval[j1];
+               if (sgn * v < 0)
+               {
+                  int m2 = hmap_find(tab, cap, i2);
+                  if (m2 >= 0) lv[m2] = __dadd_rn(lv[m2], __dmul_rn(distribute, v));
+                  if (i2 == i) diagonal = __dadd_rn(diagonal, __dmul_rn(distribute, v));
+               }
+            }
+         }
+         else diagonal = __dadd_rn(diagonal, a);
+      }
+      else if (cf[i1] != SF_PT) diagonal = __dadd_rn(diagonal, a);
+   }
+   if (diagonal != 0.0)
+   {
+      double nd = -diagonal;
+      for (int k = 0; k < nC; k++) lv[k] = __ddiv_rn(lv[k], nd);
+   }
+   int len = nC;
+   if (max_elmts > 0 && nC > max_elmts)
+   {
+      double row_sum = 0.0, scale = 0.0;
+      for (int k = 0; k < nC; k++) row_sum = __dadd_rn(row_sum, lv[k]);
+      qsort2abs_dev(lc, lv, nC);
+      for (int k = 0; k < max_elmts; k++) scale = __dadd_rn(scale, lv[k]);
+      if (scale != 0.0 && scale != row_sum)
+      {
+         scale = __ddiv_rn(row_sum, scale);
+         for (int k = 0; k < max_elmts; k++) lv[k] = __dmul_rn(lv[k], scale);
+      }
+      len = max_elmts;
+   }
+   for (int k = 0; k < len; k++) { pcol[p0 + k] = f2c[lc[k]]; pval[p0 + k] = lv[k]; }
+}
+
+__global__ void k_cf_reset_sf(int *cf, int n)
+{
+   int i = blockIdx.x * blockDim.x + threadIdx.x;
+   if (i < n && cf[i] == SF_PT) cf[i] = F_PT;
+}
+
+static int build_interp(const DevCSR &A, const DevCSR &S, int *cf, const int *f2c, int nc, int max_elmts, DevCSR &P)
+{
+   int  n = A.nrows;
+   int *cap, *cnt, *rowlen, *prp;
+   int64_t *off;
+   HDK_TRY(dalloc(&cap, (size_t)n + 1));
+   HDK_TRY(dalloc(&cnt, (size_t)n + 1));
+   HDK_TRY(dalloc(&rowlen, (size_t)n + 1));
+   HDK_TRY(dalloc(&prp, (size_t)n + 1));
+   HDK_TRY(dalloc(&off, (size_t)n + 1));
+   // pass 1: |C-hat_i| with hash sets sized from an upper bound, chunked to bound scratch
+   k_interp_cap<<<cdiv(n + 1, 256), 256, 0, g.stream>>>(S.rowptr, S.col, cf, n, cap);
+   HDK_LAUNCH_CHECK();
+   HDK_TRY(exclusive_scan_i64(cap, off, n + 1));
+   std::vector<int> bounds;
+   int64_t          maxsz;
+   HDK_TRY(plan_chunks(off, n, bounds, maxsz));
+   {
+      int *keys;
+      HDK_TRY(dalloc(&keys, (size_t)maxsz + 4));
+      for (size_t c = 0; c + 1 < bounds.size(); c++)
+      {
+         int r0 = bounds[c], r1 = bounds[c + 1];
+         if (r1 <= r0) continue;
+         HDK_CUDA(cudaMemsetAsync(keys, 0xFF, sizeof(int) * ((size_t)maxsz + 4), g.stream));
+         k_interp_count<<<cdiv(r1 - r0, 128), 128, 0, g.stream>>>(S.rowptr, S.col, cf, r0, r1, off, keys, max_elmts, cnt, rowlen);
+         HDK_LAUNCH_CHECK();
+      }
+      dfree(keys);
+   }
+   HDK_CUDA(cudaMemsetAsync(rowlen + n, 0, sizeof(int), g.stream));
+   HDK_CUDA(cudaMemsetAsync(cnt + n, 0, sizeof(int), g.stream));
+   HDK_TRY(exclusive_scan_int(rowlen, prp, n + 1));
+   int nnzP = 0;
+   HDK_CUDA(cudaMemcpyAsync(&nnzP, prp + n, sizeof(int), cudaMemcpyDeviceToHost, g.stream));
+   HDK_CUDA(cudaStreamSynchronize(g.stream));
+   P = DevCSR();
+   P.nrows = n; P.ncols = nc; P.nnz = nnzP; P.rowptr = prp; P.owns = true;
+   HDK_TRY(dalloc(&P.col, (size_t)nnzP + 8));
+   HDK_TRY(dalloc(&P.val, (size_t)nnzP + 8));
+   HDK_CUDA(cudaMemsetAsync(P.col + nnzP, 0, sizeof(int) * 8, g.stream));
+   HDK_CUDA(cudaMemsetAsync(P.val + nnzP, 0, sizeof(double) * 8, g.stream));
+   // pass 2: weights.  hash maps sized from the exact counts, candidate lists in scratch
+   int64_t *loff;
+   HDK_TRY(dalloc(&loff, (size_t)n + 1));
+   k_interp_cap2<<<cdiv(n + 1, 256), 256, 0, g.stream>>>(S.rowptr, cf, cnt, n, cap);
+   HDK_LAUNCH_CHECK();
+   HDK_TRY(exclusive_scan_i64(cap, off, n + 1));
+   HDK_TRY(exclusive_scan_i64(cnt, loff, n + 1));
+   HDK_TRY(plan_chunks(off, n, bounds, maxsz));
+   {
+      int64_t maxl = 0;
+      for (size_t c = 0; c + 1 < bounds.size(); c++)
+      {
+         int64_t o[2];
+         HDK_CUDA(cudaMemcpyAsync(&o[0], loff + bounds[c], sizeof(int64_t), cudaMemcpyDeviceToHost, g.stream));
+         HDK_CUDA(cudaMemcpyAsync(&o[1], loff + bounds[c + 1], sizeof(int64_t), cudaMemcpyDeviceToHost, g.stream));
+         HDK_CUDA(cudaStreamSynchronize(g.stream));
+         if (o[1] - o[0] > maxl) maxl = o[1] - o[0];
+      }
+      int2   *htab;
+      int    *lcol;
+      double *lval;
+      HDK_TRY(dalloc(&htab, (size_t)maxsz + 4));
+      HDK_TRY(dalloc(&lcol, (size_t)maxl + 4));
+      HDK_TRY(dalloc(&lval, (size_t)maxl + 4));
+      for (size_t c = 0; c + 1 < bounds.size(); c++)
+      {
+         int r0 = bounds[c], r1 = bounds[c + 1];
+         if (r1 <= r0) continue;
+         HDK_CUDA(cudaMemsetAsync(htab, 0xFF, sizeof(int2) * ((size_t)maxsz + 4), g.stream));
+         k_interp_fill<<<cdiv(r1 - r0, 128), 128, 0, g.stream>>>(A.rowptr, A.col, A.val, S.rowptr, S.col, cf, f2c, r0, r1,
+                                                                cnt, off, htab, loff, lcol, lval, max_elmts, prp, P.col, P.val);
+         HDK_LAUNCH_CHECK();
+      }
+      dfree(htab); dfree(lcol); dfree(lval);
+   }
+   k_cf_reset_sf<<<cdiv(n, 256), 256, 0, g.stream>>>(cf, n);
+   HDK_LAUNCH_CHECK();
+   dfree(cap); dfree(cnt); dfree(rowlen); dfree(off); dfree(loff);
+   return HDK_OK;
+}
+
+// =====================================================================================
+// R = P^T (hypre_CSRMatrixTranspose order: ascending fine row inside each coarse row)
+// =====================================================================================
+__global__ void k_expand_rows(const int *rp, int n, int *rowid)
+{
+   int i = blockIdx.x * blockDim.x + threadIdx.x;
+   if (i >= n) return;
+   for (int k = rp[i]; k < rp[i + 1]; k++) rowid[k] = i;
+}
+__global__ void k_iota(int *v, int n)
+{
+   int i = blockIdx.x * blockDim.x + threadIdx.x;
+   if (i < n) v[i] = i;
+}
+__global__ void k_transpose_fill(const int *perm, const int *rowid, const double *val, int nnz, int *tcol, double *tval)
+{
+   int k = blockIdx.x * blockDim.x + threadIdx.x;
+   if (k >= nnz) return;
+   int s = perm[k];
+   tcol[k] = rowid[s];
+   if (val) tval[k] = val[s];
+}
+__global__ void k_rowptr_from_sorted(const int *keys, int nnz, int nrows, int *rp)
+{
+   int r = blockIdx.x * blockDim.x + threadIdx.x;
+   if (r > nrows) return;
+   int lo = 0, hi = nnz; // first k with keys[k] >= r
+   while (lo < hi) { int mid = (lo + hi) >> 1; if (keys[mid] >= r) hi = mid; else lo = mid + 1; }
+   rp[r] = lo;
+}
+
+static int csr_transpose(const DevCSR &A, DevCSR &T)
+{
+   int nnz = A.nnz;
+   HDK_TRY(csr_alloc(T, A.ncols, A.nrows, nnz, A.val != nullptr));
+   if (nnz == 0) { HDK_CUDA(cudaMemsetAsync(T.rowptr, 0, sizeof(int) * ((size_t)T.nrows + 1), g.stream)); return HDK_OK; }
+   int *rowid, *idx, *keys_out, *perm;
+   HDK_TRY(dalloc(&rowid, (size_t)nnz));
+   HDK_TRY(dalloc(&idx, (size_t)nnz));
+   HDK_TRY(dalloc(&keys_out, (size_t)nnz));
+   HDK_TRY(dalloc(&perm, (size_t)nnz));
+   k_expand_rows<<<cdiv(A.nrows, 256), 256, 0, g.stream>>>(A.rowptr, A.nrows, rowid);
+   HDK_LAUNCH_CHECK();
+   k_iota<<<cdiv(nnz, 256), 256, 0, g.stream>>>(idx, nnz);
+   HDK_LAUNCH_CHECK();
+   int bits = 1;
+   while ((1LL << bits) < (long long)A.ncols + 1 && bits < 31) bits++;
+   size_t bytes = 0;
+   HDK_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, bytes, A.col, keys_out, idx, perm, nnz, 0, bits, g.stream));
+   char *tmp;
+   HDK_TRY(dalloc(&tmp, bytes));
+   HDK_CUDA(cub::DeviceRadixSort::SortPairs(tmp, bytes, A.col, keys_out, idx, perm, nnz, 0, bits, g.stream)); // stable
+   g.launches++;
+   k_transpose_fill<<<cdiv(nnz, 256), 256, 0, g.stream>>>(perm, rowid, A.val, nnz, T.col, T.val);
+   HDK_LAUNCH_CHECK();
+   k_rowptr_from_sorted<<<cdiv(T.nrows + 1, 256), 256, 0, g.stream>>>(keys_out, nnz, T.nrows, T.rowptr);
+   HDK_LAUNCH_CHECK();
+   dfree(tmp); dfree(rowid); dfree(idx); dfree(keys_out); dfree(perm);
+   return HDK_OK;
+}
+
+// =====================================================================================
+// Galerkin product (hypre_BoomerAMGBuildCoarseOperatorKT order): one thread per coarse row,
+// hash accumulators in scratch; row = diagonal first, then columns in discovery order of
+// (i1 in R_ic) x (i2 in A_i1) x (i3 in P_i2); value = sum (r*a)*p in that order.
+// =====================================================================================
+__global__ void k_rap_q(const int *arp, const int *acol, const int *prp, int n, int *q)
+{
+   int i = blockIdx.x * blockDim.x + threadIdx.x;
+   if (i >= n) return;
+   int s = 0;
+   for (int k = arp[i]; k < arp[i + 1]; k++) { int j = acol[k]; s += prp[j + 1] - prp[j]; }
+   q[i] = s;
+}
+__global__ void k_rap_cap(const int *rrp, const int *rcol, const int *q, int nc, int *cap)
+{
+   int ic = blockIdx.x * blockDim.x + threadIdx.x;
+   if (ic > nc) return;
+   if (ic == nc) { cap[ic] = 0; return; }
+   long long ub = 1;
+   for (int k = rrp[ic]; k < rrp[ic + 1]; k++) ub += q[rcol[k]];
+   if (ub > nc) ub = nc;
+   cap[ic] = pow2ceil((int)(2 * ub));
+}
+__global__ void k_rap_count(const int *rrp, const int *rcol, const int *arp, const int *acol, const int *prp,
+                            const int *pcol, int row0, int row1, const int64_t *off, int *keys, int *cnt)
+{
+   int ic = row0 + blockIdx.x * blockDim.x + threadIdx.x;
+   if (ic >= row1) return;
+   int *tab = keys + (off[ic] - off[row0]);
+   int  cap = (int)(off[ic + 1] - off[ic]);
+   int  c   = 1;
+   hset_insert(tab, cap, ic);
+   for (int j1 = rrp[ic]; j1 < rrp[ic + 1]; j1++)
+   {
+      int i1 = rcol[j1];
+      for (int j2 = arp[i1]; j2 < arp[i1 + 1]; j2++)
+      {
+         int i2 = acol[j2];
+         for (int j3 = prp[i2]; j3 < prp[i2 + 1]; j3++)
+            if (hset_insert(tab, cap, pcol[j3])) c++;
+      }
+   }
+   cnt[ic] = c;
+}
+__global__ void k_rap_cap2(const int *cnt, int nc, int *cap2)
+{
+   int ic = blockIdx.x * blockDim.x + threadIdx.x;
+   if (ic > nc) return;
+   cap2[ic] = ic < nc ? pow2ceil(2 * cnt[ic]) : 0;
+}
+__global__ void k_rap_fill(const int *rrp, const int *rcol, const double *rval, const int *arp, const int *acol,
+                           const double *aval, const int *prp, const int *pcol, const double *pval, int row0,
+                           int row1, const int64_t *off, int2 *htab, const int *crp, int *ccol, double *cval)
+{
+   int ic = row0 + blockIdx.x * blockDim.x + threadIdx.x;
+   if (ic >= row1) return;
+   int2 *tab = htab + (off[ic] - off[row0]);
+   int   cap = (int)(off[ic + 1] - off[ic]);
+   int   b = crp[ic], c = b;
+   hmap_insert(tab, cap, ic, c);
+   ccol[c] = ic; cval[c] = 0.0; c++;
+   for (int j1 = rrp[ic]; j1 < rrp[ic + 1]; j1++)
+   {
+      int    i1 = rcol[j1];
+      double r  = rval[j1];
+      for (int j2 = arp[i1]; j2 < arp[i1 + 1]; j2++)
+      {
+         int    i2 = acol[j2];
+         double ra = __dmul_rn(r, aval[j2]);
+         for (int j3 = prp[i2]; j3 < prp[i2 + 1]; j3++)
+         {
+            int    i3  = pcol[j3];
+            double rap = __dmul_rn(ra, pval[j3]);
+            int    m   = hmap_insert(tab, cap, i3, c);
+            if (m == -1) { ccol[c] = i3; cval[c] = rap; c++; }
+            else cval[m] = __dadd_rn(cval[m], rap);
+         }
+      }
+   }
+}
+
+static int build_rap(const DevCSR &R, const DevCSR &A, const DevCSR &P, DevCSR &C)
+{
+   int nc = R.nrows, n = A.nrows;
+   int *q, *cap, *cnt, *crp;
+   int64_t *off;
+   HDK_TRY(dalloc(&q, (size_t)n + 1));
+   HDK_TRY(dalloc(&cap, (size_t)nc + 1));
+   HDK_TRY(dalloc(&cnt, (size_t)nc + 1));
+   HDK_TRY(dalloc(&crp, (size_t)nc + 1));
+   HDK_TRY(dalloc(&off, (size_t)nc + 1));
+   k_rap_q<<<cdiv(n, 256), 256, 0, g.stream>>>(A.rowptr, A.col, P.rowptr, n, q);
+   HDK_LAUNCH_CHECK();
+   k_rap_cap<<<cdiv(nc + 1, 256), 256, 0, g.stream>>>(R.rowptr, R.col, q, nc, cap);
+   HDK_LAUNCH_CHECK();
+   HDK_TRY(exclusive_scan_i64(cap, off, nc + 1));
+   std::vector<int> bounds;
+   int64_t          maxsz;
+   HDK_TRY(plan_chunks(off, nc, bounds, maxsz));
+   {
+      int *keys;
+      HDK_TRY(dalloc(&keys, (size_t)maxsz + 4));
+      for (size_t c = 0; c + 1 < bounds.size(); c++)
+      {
+         int r0 = bounds[c], r1 = bounds[c + 1];
+         if (r1 <= r0) continue;
+         HDK_CUDA(cudaMemsetAsync(keys, 0xFF, sizeof(int) * ((size_t)maxsz + 4), g.stream));
+         k_rap_count<<<cdiv(r1 - r0, 128), 128, 0, g.stream>>>(R.rowptr, R.col, A.rowptr, A.col, P.rowptr, P.col, r0, r1, off, keys, cnt);
+         HDK_LAUNCH_CHECK();
+      }
+      dfree(keys);
+   }
+   HDK_CUDA(cudaMemsetAsync(cnt + nc, 0, sizeof(int), g.stream));
+   HDK_TRY(exclusive_scan_int(cnt, crp, nc + 1));
+   int nnzC = 0;
+   HDK_CUDA(cudaMemcpyAsync(&nnzC, crp + nc, sizeof(int), cudaMemcpyDeviceToHost, g.stream));
+   HDK_CUDA(cudaStreamSynchronize(g.stream));
+   C = DevCSR();
+   C.nrows = nc; C.ncols = nc; C.nnz = nnzC; C.rowptr = crp; C.owns = true;
+   HDK_TRY(dalloc(&C.col, (size_t)nnzC + 8));
+   HDK_TRY(dalloc(&C.val, (size_t)nnzC + 8));
+   HDK_CUDA(cudaMemsetAsync(C.col + nnzC, 0, sizeof(int) * 8, g.stream));
+   HDK_CUDA(cudaMemsetAsync(C.val + nnzC, 0, sizeof(double) * 8, g.stream));
+   k_rap_cap2<<<cdiv(nc + 1, 256), 256, 0, g.stream>>>(cnt, nc, cap);
+   HDK_LAUNCH_CHECK();
+   HDK_TRY(exclusive_scan_i64(cap, off, nc + 1));
+   HDK_TRY(plan_chunks(off, nc, bounds, maxsz));
+   {
+      int2 *htab;
+      HDK_TRY(dalloc(&htab, (size_t)maxsz + 4));
+      for (size_t c = 0; c + 1 < bounds.size(); c++)
+      {
+         int r0 = bounds[c], r1 = bounds[c + 1];
+         if (r1 <= r0) continue;
+         HDK_CUDA(cudaMemsetAsync(htab, 0xFF, sizeof(int2) * ((size_t)maxsz + 4), g.stream));
+         k_rap_fill<<<cdiv(r1 - r0, 128), 128, 0, g.stream>>>(R.rowptr, R.col, R.val, A.rowptr, A.col, A.val, P.rowptr, P.col,
+                                                             P.val, r0, r1, off, htab, crp, C.col, C.val);
+         HDK_LAUNCH_CHECK();
+      }
+      dfree(htab);
+   }
+   dfree(q); dfree(cap); dfree(cnt); dfree(off);
+   return HDK_OK;
+}
+
+// =====================================================================================
+// l1 norms (hypre_ParCSRComputeL1Norms): option 1 full row l1 norm (relax 18);
+// option 4 truncated l1 = |a_ii| + 0.5*sum_offd|a_ij| (relax 8/13/14); option 5 diagonal
+// =====================================================================================
+__global__ void k_l1(const int *rp, const double *val, const int *orp, const double *oval, int n, int option, double *l1)
+{
+   int i = blockIdx.x * blockDim.x + threadIdx.x;
+   if (i >= n) return;
+   int    b = rp[i], e = rp[i + 1];
+   double d = e > b ? val[b] : 0.0, v;
+   if (option == 1)
+   {
+      v = 0.0;
+      for (int k = b; k < e; k++) v = __dadd_rn(v, fabs(val[k]));
+      if (orp) for (int k = orp[i]; k < orp[i + 1]; k++) v = __dadd_rn(v, fabs(oval[k]));
+      if (d < 0) v = -v;
+   }
+   else if (option == 4)
+   {
+      double od = 0.0;
+      if (orp) for (int k = orp[i]; k < orp[i + 1]; k++) od = __dadd_rn(od, fabs(oval[k]));
+      v = __dadd_rn(fabs(d), __dmul_rn(0.5, od));
+      if (v <= (4.0 / 3.0) * fabs(d)) v = fabs(d);
+      if (d < 0) v = -v;
+   }
+   else v = d;
+   l1[i] = v;
+}
+
+static int relax_l1_option(int type)
+{
+   if (type == 18) return 1;
+   if (type == 8 || type == 13 || type == 14) return 4;
+   return 5;
+}
+
+static int build_l1(const hdk_csr_s &A, int option, double **out)
+{
+   int n = A.diag.nrows;
+   HDK_TRY(dalloc(out, (size_t)n + 8));
+   const int    *orp = A.offd.nnz > 0 ? A.offd.rowptr : nullptr;
+   const double *ov  = A.offd.nnz > 0 ? A.offd.val : nullptr;
+   k_l1<<<cdiv(n, 256), 256, 0, g.stream>>>(A.diag.rowptr, A.diag.val, orp, ov, n, option, *out);
+   HDK_LAUNCH_CHECK();
+   return HDK_OK;
+}
+
+// strict lower triangle (two-stage Gauss-Seidel)
+template <bool FILL>
+__global__ void k_lower(const int *rp, const int *col, const double *val, int n, int *cnt, const int *lrp, int *lcol, double *lval)
+{
+   int i = blockIdx.x * blockDim.x + threadIdx.x;
+   if (i > n) return;
+   if (i == n) { if (!FILL) cnt[n] = 0; return; }
+   int c = 0, p = FILL ? lrp[i] : 0;
+   for (int k = rp[i]; k < rp[i + 1]; k++)
+      if (col[k] < i) { if (FILL) { lcol[p] = col[k]; lval[p] = val[k]; p++; } else c++; }
+   if (!FILL) cnt[i] = c;
+}
+
+static int build_lower(const DevCSR &A, DevCSR &L)
+{
+   int  n = A.nrows;
+   int *cnt, *lrp;
+   HDK_TRY(dalloc(&cnt, (size_t)n + 1));
+   HDK_TRY(dalloc(&lrp, (size_t)n + 1));
+   k_lower<false><<<cdiv(n + 1, 256), 256, 0, g.stream>>>(A.rowptr, A.col, A.val, n, cnt, nullptr, nullptr, nullptr);
+   HDK_LAUNCH_CHECK();
+   HDK_TRY(exclusive_scan_int(cnt, lrp, n + 1));
+   int nnz = 0;
+   HDK_CUDA(cudaMemcpyAsync(&nnz, lrp + n, sizeof(int), cudaMemcpyDeviceToHost, g.stream));
+   HDK_CUDA(cudaStreamSynchronize(g.stream));
+   dfree(cnt);
+   HDK_TRY(csr_alloc(L, n, n, nnz));
+   dfree(L.rowptr); L.rowptr = lrp;
+   k_lower<true><<<cdiv(n + 1, 256), 256, 0, g.stream>>>(A.rowptr, A.col, A.val, n, nullptr, lrp, L.col, L.val);
+   HDK_LAUNCH_CHECK();
+   return csr_analyze(L);
+}
+
+// =====================================================================================
+// coarsest level: dense inverse by Gauss-Jordan with partial pivoting, one CTA
+// =====================================================================================
+__global__ void k_dense_fill(const int *rp, const int *col, const double *val, int n, double *M /* n x 2n */)
+{
+   int i = blockIdx.x * blockDim.x + threadIdx.x;
+   if (i >= n) return;
+   for (int k = rp[i]; k < rp[i + 1]; k++) M[(size_t)i * 2 * n + col[k]] += val[k];
+   M[(size_t)i * 2 * n + n + i] = 1.0;
+}
+
+__global__ void __launch_bounds__(1024) k_gauss_jordan(double *M, int n, double *inv)
+{
+   __shared__ double sval[32];
+   __shared__ int    sidx[32];
+   __shared__ int    piv;
+   __shared__ double pivval;
+   const int tid = threadIdx.x, nt = blockDim.x, w = 2 * n;
+   for (int k = 0; k < n; k++)
+   {
+      // pivot search in column k
+      double best = -1.0; int bi = k;
+      for (int r = k + tid; r < n; r += nt) { double v = fabs(M[(size_t)r * w + k]); if (v > best) { best = v; bi = r; } }
+      for (int o = 16; o > 0; o >>= 1)
+      {
+         double ov = __shfl_down_sync(0xffffffffu, best, o); int oi = __shfl_down_sync(0xffffffffu, bi, o);
+         if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+      }
+      if ((tid & 31) == 0) { sval[tid >> 5] = best; sidx[tid >> 5] = bi; }
+      __syncthreads();
+      if (tid == 0)
+      {
+         double b = sval[0]; int i2 = sidx[0];
+         for (int q = 1; q < (nt + 31) / 32; q++) if (sval[q] > b || (sval[q] == b && sidx[q] < i2)) { b = sval[q]; i2 = sidx[q]; }
+         piv = i2; pivval = M[(size_t)i2 * w + k];
+      }
+      __syncthreads();
+      int    pr = piv;
+      double pv = pivval;
+      if (pv != 0.0)
+      {
+         if (pr != k)
+            for (int j = tid; j < w; j += nt) { double t = M[(size_t)k * w + j]; M[(size_t)k * w + j] = M[(size_t)pr * w + j]; M[(size_t)pr * w + j] = t; }
+         __syncthreads();
+         for (int j = tid; j < w; j += nt) M[(size_t)k * w + j] /= pv;
+         __syncthreads();
+         // eliminate column k from every other row
+         for (int idx = tid; idx < n * w; idx += nt)
+         {
+            int r = idx / w, j = idx - r * w;
+            if (r != k && j != k)
+            {
+               double f = M[(size_t)r * w + k];
+               if (f != 0.0) M[(size_t)r * w + j] -= f * M[(size_t)k * w + j];
+            }
+         }
+         __syncthreads();
+         for (int r = tid; r < n; r += nt) if (r != k) M[(size_t)r * w + k] = 0.0;
+      }
+      __syncthreads();
+   }
+   for (int idx = tid; idx < n * n; idx += nt) { int r = idx / n, j = idx - r * n; inv[idx] = M[(size_t)r * w + n + j]; }
+}
+
+static int build_dense_inverse(const DevCSR &A, double **inv)
+{
+   int     n = A.nrows;
+   double *M;
+   HDK_TRY(dalloc(&M, (size_t)n * 2 * n + 8));
+   HDK_TRY(dalloc(inv, (size_t)n * n + 8));
+   HDK_CUDA(cudaMemsetAsync(M, 0, sizeof(double) * ((size_t)n * 2 * n), g.stream));
+   k_dense_fill<<<cdiv(n, 128), 128, 0, g.stream>>>(A.rowptr, A.col, A.val, n, M);
+   HDK_LAUNCH_CHECK();
+   k_gauss_jordan<<<1, 1024, 0, g.stream>>>(M, n, *inv);
+   HDK_LAUNCH_CHECK();
+   dfree(M);
+   return HDK_OK;
+}
+
+// wrap a rank-local DevCSR as a ParCSR object with an empty offd block
+static hdk_csr_s *wrap_local(DevCSR &D, int64_t grows)
+{
+   hdk_csr_s *A  = new hdk_csr_s();
+   A->row_start  = 0; A->row_end = (int64_t)D.nrows - 1; A->global_rows = grows; A->global_nnz = D.nnz;
+   A->diag       = D;
+   D             = DevCSR();
+   return A;
+}
+
+static void destroy_local(hdk_csr_s *A)
+{
+   if (!A) return;
+   csr_free(A->diag); csr_free(A->offd);
+   dfree(A->halo.col_map); dfree(A->halo.send_idx); dfree(A->halo.send_buf); dfree(A->halo.x_halo);
+   delete A;
+}
+
+} // namespace hdk
+
+using namespace hdk;
+
+extern "C" {
+
+void hdk_amg_default_params(hdk_amg_params *p)
+{
+   /* GPU-build defaults of the reference: src/internal/amg.c:120-238 under HYPRE_USING_GPU */
+   p->coarsen_type = 8; p->strong_th = 0.25; p->max_row_sum = 0.9;
+   p->max_coarse_size = 64; p->min_coarse_size = 0; p->max_levels = 25;
+   p->interp_type = 6; p->max_nnz_row = 4; p->trunc_factor = 0.0;
+   p->relax_down = 18; p->relax_up = 18; p->relax_coarse = 9;
+   p->sweeps_down = p->sweeps_up = p->sweeps_coarse = 1;
+   p->relax_weight = p->outer_weight = 1.0;
+   p->rand_seed = 2747; p->keep_transpose = 1; p->print_level = 0;
+}
+
+int hdk_amg_destroy(hdk_amg *M)
+{
+   if (!M) return HDK_OK;
+   if (g.inited)
+   {
+      for (auto &L : M->lev)
+      {
+         if (L.owns_A) destroy_local(L.A);
+         destroy_local(L.P); destroy_local(L.R);
+         csr_free(L.S); csr_free(L.L);
+         dfree(L.cf); dfree(L.measure);
+         if (L.l1_up != L.l1_down) dfree(L.l1_up);
+         dfree(L.l1_down);
+         dfree(L.u); dfree(L.f); dfree(L.t);
+      }
+      dfree(M->ge_inv);
+   }
+   delete M;
+   return HDK_OK;
+}
+
+int hdk_amg_setup(const hdk_csr *A0, const hdk_amg_params *prm, hdk_amg **out)
+{
+   HDK_TRY(require_init());
+   if (!A0 || !prm || !out) return set_error(HDK_ERR_INVALID, "hdk_amg_setup: null argument");
+   if (prm->interp_type != 6) return set_error(HDK_ERR_UNSUPPORTED, "interpolation type %d: only extended+i (6) has a device kernel", prm->interp_type);
+   if (prm->trunc_factor != 0.0) return set_error(HDK_ERR_UNSUPPORTED, "interpolation trunc_factor != 0 is not supported on the device path");
+   hdk_amg_s *M = new hdk_amg_s();
+   M->prm       = *prm;
+   int rc       = HDK_OK;
+   M->lev.emplace_back();
+   M->lev[0].A = const_cast<hdk_csr_s *>(A0);
+   M->lev[0].owns_A = false;
+   M->lev[0].n = A0->diag.nrows;
+   int  level = 0;
+   bool more  = prm->max_levels > 1;
+   double nnz0 = (double)A0->diag.nnz + A0->offd.nnz, nnz_sum = nnz0;
+   while (more && rc == HDK_OK)
+   {
+      AmgLevel        &L = M->lev[(size_t)level];
+      const hdk_csr_s &A = *L.A;
+      int              n = L.n;
+      if ((rc = build_strength(A, prm->strong_th, prm->max_row_sum, L.S))) break;
+      if ((rc = dalloc(&L.cf, (size_t)n + 1))) break;
+      double *meas, *keep = nullptr;
+      if ((rc = dalloc(&meas, (size_t)n + 1))) break;
+      if (M->keep_debug) { if ((rc = dalloc(&keep, (size_t)n + 1))) break; }
+      L.measure = keep;
+      int64_t goff = (level == 0) ? A.row_start : 0;
+      rc = run_pmis(L.S, prm->rand_seed, goff, L.cf, meas, keep, nullptr);
+      dfree(meas);
+      if (rc) break;
+      int *flag, *f2c;
+      if ((rc = dalloc(&flag, (size_t)n + 1))) break;
+      if ((rc = dalloc(&f2c, (size_t)n + 1))) break;
+      k_cf_flag<<<cdiv(n + 1, 256), 256, 0, g.stream>>>(L.cf, n, flag);
+      g.launches++;
+      if ((rc = exclusive_scan_int(flag, f2c, n + 1))) break;
+      int nc = 0;
+      cudaMemcpyAsync(&nc, f2c + n, sizeof(int), cudaMemcpyDeviceToHost, g.stream);
+      cudaStreamSynchronize(g.stream);
+      dfree(flag);
+      if (nc == 0 || nc == n || nc < prm->min_coarse_size) { dfree(f2c); break; }
+      DevCSR P, R, C;
+      rc = build_interp(A.diag, L.S, L.cf, f2c, nc, prm->max_nnz_row, P);
+      dfree(f2c);
+      if (rc) break;
+      if ((rc = csr_transpose(P, R))) break;
+      if ((rc = build_rap(R, A.diag, P, C))) break;
+      if ((rc = csr_analyze(P))) break;
+      if ((rc = csr_analyze(R))) break;
+      if ((rc = csr_analyze(C))) break;
+      nnz_sum += C.nnz;
+      L.P = wrap_local(P, n);
+      L.R = wrap_local(R, nc);
+      M->lev.emplace_back();
+      AmgLevel &N = M->lev.back();
+      N.A = wrap_local(C, nc); N.owns_A = true; N.n = nc;
+      level++;
+      if (level == prm->max_levels - 1 || nc <= prm->max_coarse_size) more = false;
+      if (!M->keep_debug) csr_free(M->lev[(size_t)level - 1].S);
+   }
+   if (rc == HDK_OK)
+   {
+      M->nlev = level + 1;
+      M->op_complexity = nnz_sum / (nnz0 > 0 ? nnz0 : 1.0);
+      double bytes = 0.0;
+      for (int l = 0; l < M->nlev && rc == HDK_OK; l++)
+      {
+         AmgLevel &L = M->lev[(size_t)l];
+         int       n = L.n;
+         if ((rc = build_l1(*L.A, relax_l1_option(prm->relax_down), &L.l1_down))) break;
+         if (relax_l1_option(prm->relax_up) == relax_l1_option(prm->relax_down)) L.l1_up = L.l1_down;
+         else if ((rc = build_l1(*L.A, relax_l1_option(prm->relax_up), &L.l1_up))) break;
+         if ((rc = dalloc(&L.t, (size_t)n + 8))) break;
+         if (l > 0)
+         {
+            if ((rc = dalloc(&L.u, (size_t)n + 8))) break;
+            if ((rc = dalloc(&L.f, (size_t)n + 8))) break;
+         }
+         bool tsgs = (prm->relax_down == 11 || prm->relax_down == 12 || prm->relax_up == 11 || prm->relax_up == 12);
+         if (tsgs && (rc = build_lower(L.A->diag, L.L))) break;
+         // algorithmic bytes of one V-cycle: zero-guess pre-smooth 24n, residual,
+         // restriction, prolongation, post-smooth
+         double nnzA = (double)L.A->diag.nnz + L.A->offd.nnz;
+         if (l < M->nlev - 1)
+         {
+            double nnzP = (double)L.P->diag.nnz, ncl = (double)M->lev[(size_t)l + 1].n;
+            bytes += 24.0 * n;                                       // u = w f / d
+            bytes += 12.0 * nnzA + 4.0 * (n + 1) + 24.0 * n;         // r = f - A u
+            bytes += 12.0 * nnzP + 4.0 * (ncl + 1) + 8.0 * n + 8.0 * ncl; // f_c = R r
+            bytes += 12.0 * nnzP + 4.0 * (n + 1) + 16.0 * n + 8.0 * ncl;  // u += P e
+            bytes += 12.0 * nnzA + 4.0 * (n + 1) + 32.0 * n;         // post-smooth
+         }
+         else bytes += 8.0 * (double)n * n + 16.0 * n;
+      }
+      M->vcycle_bytes = bytes;
+   }
+   if (rc == HDK_OK)
+   {
+      AmgLevel &Lc = M->lev[(size_t)M->nlev - 1];
+      bool      want_ge = (prm->relax_coarse == 9 || prm->relax_coarse == 99 || prm->relax_coarse == 19);
+      if (want_ge && Lc.n <= 1024 && Lc.n > 0 && Lc.A->offd.nnz == 0)
+      {
+         rc = build_dense_inverse(Lc.A->diag, &M->ge_inv);
+         M->ge_n = Lc.n;
+      }
+   }
+   if (rc == HDK_OK) rc = (cudaStreamSynchronize(g.stream) == cudaSuccess) ? HDK_OK : set_error(HDK_ERR_CUDA, "setup sync failed: %s", cudaGetErrorString(cudaGetLastError()));
+   if (rc != HDK_OK) { hdk_amg_destroy(M); return rc; }
+   *out = M;
+   return HDK_OK;
+}
+
+int hdk_amg_num_levels(const hdk_amg *M) { return M ? M->nlev : 0; }
+double hdk_amg_operator_complexity(const hdk_amg *M) { return M ? M->op_complexity : 0.0; }
+double hdk_amg_vcycle_bytes(const hdk_amg *M) { return M ? M->vcycle_bytes : 0.0; }
+
+int hdk_amg_level_info(const hdk_amg *M, int level, int64_t *rows, int64_t *nnz_A, int64_t *nnz_P)
+{
+   if (!M || level < 0 || level >= M->nlev) return set_error(HDK_ERR_INVALID, "level out of range");
+   const AmgLevel &L = M->lev[(size_t)level];
+   if (rows) *rows = L.n;
+   if (nnz_A) *nnz_A = (int64_t)L.A->diag.nnz + L.A->offd.nnz;
+   if (nnz_P) *nnz_P = L.P ? L.P->diag.nnz : 0;
+   return HDK_OK;
+}
+
+int hdk_amg_get_matrix(const hdk_amg *M, int level, int which, int32_t *rowptr_h, int32_t *col_h, double *val_h)
+{
+   HDK_TRY(require_init());
+   if (!M || level < 0 || level >= M->nlev) return set_error(HDK_ERR_INVALID, "level out of range");
+   const AmgLevel &L = M->lev[(size_t)level];
+   const DevCSR   *D = nullptr;
+   if (which == 0) D = &L.A->diag;
+   else if (which == 1 && L.P) D = &L.P->diag;
+   else if (which == 2 && L.R) D = &L.R->diag;
+   else if (which == 3 && L.S.rowptr) D = &L.S;
+   if (!D) return set_error(HDK_ERR_INVALID, "matrix %d not available on level %d", which, level);
+   if (rowptr_h) HDK_CUDA(cudaMemcpyAsync(rowptr_h, D->rowptr, sizeof(int) * ((size_t)D->nrows + 1), cudaMemcpyDeviceToHost, g.stream));
+   if (col_h && D->nnz) HDK_CUDA(cudaMemcpyAsync(col_h, D->col, sizeof(int) * (size_t)D->nnz, cudaMemcpyDeviceToHost, g.stream));
+   if (val_h && D->val && D->nnz) HDK_CUDA(cudaMemcpyAsync(val_h, D->val, sizeof(double) * (size_t)D->nnz, cudaMemcpyDeviceToHost, g.stream));
+   HDK_CUDA(cudaStreamSynchronize(g.stream));
+   return HDK_OK;
+}
+
+static int get_level_array(const hdk_amg *M, int level, const void *src, size_t bytes, void *dst)
+{
+   HDK_TRY(require_init());
+   if (!M || level < 0 || level >= M->nlev || !src) return set_error(HDK_ERR_INVALID, "array not available on level %d", level);
+   return hdk_copy_d2h(dst, src, bytes);
+}
+int hdk_amg_get_cf(const hdk_amg *M, int level, int32_t *cf_h)
+{
+   if (!M || level < 0 || level >= M->nlev) return set_error(HDK_ERR_INVALID, "level out of range");
+   return get_level_array(M, level, M->lev[(size_t)level].cf, sizeof(int) * (size_t)M->lev[(size_t)level].n, cf_h);
+}
+int hdk_amg_get_measure(const hdk_amg *M, int level, double *m_h)
+{
+   if (!M || level < 0 || level >= M->nlev) return set_error(HDK_ERR_INVALID, "level out of range");
+   return get_level_array(M, level, M->lev[(size_t)level].measure, sizeof(double) * (size_t)M->lev[(size_t)level].n, m_h);
+}
+int hdk_amg_get_l1(const hdk_amg *M, int level, double *l1_h)
+{
+   if (!M || level < 0 || level >= M->nlev) return set_error(HDK_ERR_INVALID, "level out of range");
+   return get_level_array(M, level, M->lev[(size_t)level].l1_down, sizeof(double) * (size_t)M->lev[(size_t)level].n, l1_h);
+}
+
+int hdk_amg_strength(const hdk_csr *A, double theta, double max_row_sum, int64_t *nnz_S, int32_t **rowptr_d, int32_t **col_d)
+{
+   HDK_TRY(require_init());
+   if (!A) return set_error(HDK_ERR_INVALID, "null matrix");
+   DevCSR S;
+   HDK_TRY(build_strength(*A, theta, max_row_sum, S));
+   *nnz_S = S.nnz; *rowptr_d = S.rowptr; *col_d = S.col;
+   return HDK_OK;
+}
+
+int hdk_amg_pmis(int64_t n, const int32_t *S_rowptr_d, const int32_t *S_col_d, int seed, int64_t global_offset,
+                 int32_t *cf_d, double *measure_d, int *iterations)
+{
+   HDK_TRY(require_init());
+   DevCSR S;
+   S.nrows = (int)n; S.ncols = (int)n; S.rowptr = const_cast<int *>(S_rowptr_d); S.col = const_cast<int *>(S_col_d);
+   HDK_CUDA(cudaMemcpyAsync(&S.nnz, S_rowptr_d + n, sizeof(int), cudaMemcpyDeviceToHost, g.stream));
+   HDK_CUDA(cudaStreamSynchronize(g.stream));
+   double *work;
+   HDK_TRY(dalloc(&work, (size_t)n + 1));
+   int rc = run_pmis(S, seed, global_offset, cf_d, work, measure_d, iterations);
+   dfree(work);
+   return rc;
+}
+
+} // extern "C"

@@ -1,0 +1,276 @@
+// hdk_amg_solve.cu -- BoomerAMG V-cycle on the device (north-star item 2).
+// Stands in for HYPRE_BoomerAMGSolve / hypre_BoomerAMGCycle (cycle_type 1, relax_order 0,
+// max_iter 1, tol 0) reached from PreconSolveDispatch (reference src/internal/solver.c:314-329)
+// and HYPREDRV_PreconApply (src/HYPREDRV.c:3345).  Per level: l1-Jacobi (18) / Jacobi (7) /
+// two-stage Gauss-Seidel (11, 12) sweeps fused with their residual evaluation, explicit
+// R = P^T restriction, P prolongation fused with the correction, dense coarsest solve kept
+// on the GPU (pre-inverted operator, one matvec).
+#include "hdk_amg.cuh"
+
+namespace hdk {
+
+// u = Ainv f  (n <= 1024): one warp per row of the dense inverse
+__global__ void __launch_bounds__(256) k_dense_apply(const double *__restrict__ Ainv, const double *__restrict__ f,
+                                                     double *__restrict__ u, int n)
+{
+   int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+   if (row >= n) return;
+   double acc = 0.0;
+   for (int j = lane; j < n; j += 32) acc += Ainv[(size_t)row * n + j] * f[j];
+   acc = warp_sum(acc);
+   if (lane == 0) u[row] = acc;
+}
+
+static bool is_jacobi(int t) { return t == 18 || t == 7 || t == 0; }
+
+// one smoothing sweep u_new = S(u_old); result written to `out` (out != in)
+static int relax_sweep(hdk_amg_s *M, int l, int type, const double *l1, const double *f, const double *in,
+                       double *out, int fin, double *fin_out)
+{
+   AmgLevel &L = M->lev[(size_t)l];
+   SpmvArgs  a;
+   a.x = in; a.y = out; a.b = f; a.d = l1; a.w = M->prm.relax_weight;
+   if (is_jacobi(type))
+   {
+      if (fin != FIN_NONE) { a.dotv = f; a.fin = fin; a.fin_out = fin_out; }
+      return parcsr_matvec(*L.A, SPMV_JACOBI, a);
+   }
+   if (type == 11 || type == 12)
+   {
+      // two-stage GS: r = w D^{-1}(f - A u); u += r; then r <- D^{-1} L r, u += (-1)^k r
+      double *r, *r2;
+      HDK_TRY(dalloc(&r, (size_t)L.n + 8));
+      HDK_TRY(dalloc(&r2, (size_t)L.n + 8));
+      a.y = r;                                 // r = w D^{-1} (f - A u_old)
+      HDK_TRY(parcsr_matvec(*L.A, SPMV_JACOBI_R, a));
+      HDK_TRY(vec_copy(out, in, L.n));         // out = u_old
+      HDK_TRY(vec_axpy(1.0, r, out, L.n));     // out = u_old + r
+      int    inner = (type == 11) ? 1 : 2;
+      double mult  = 1.0;
+      double *cur = r, *nxt = r2;
+      for (int it = 0; it < inner; it++)
+      {
+         // nxt = D^{-1} L cur  (out-of-place strict-lower SpMV; hypre does this in place
+         // bottom-up, which reads only not-yet-updated entries, i.e. the same Jacobi-type product)
+         SpmvArgs b2;
+         b2.x = cur; b2.y = nxt;
+         HDK_TRY(spmv_launch(L.L, SPMV_SET, b2));
+         HDK_TRY(vec_scaled_div(nxt, nxt, l1, 1.0, L.n));
+         mult = -mult;
+         HDK_TRY(vec_axpy(mult, nxt, out, L.n));
+         double *tmp = cur; cur = nxt; nxt = tmp;
+      }
+      dfree(r); dfree(r2);
+      if (fin != FIN_NONE) HDK_TRY(vec_dot_dev(f, out, L.n, fin, fin_out));
+      return HDK_OK;
+   }
+   return set_error(HDK_ERR_UNSUPPORTED, "relaxation type %d has no device kernel (use 18, 7, 0, 11 or 12)", type);
+}
+
+static int coarse_solve(hdk_amg_s *M, int l, const double *f, double *u, double *alt, bool zero_guess, double **result)
+{
+   AmgLevel &L = M->lev[(size_t)l];
+   *result     = u;
+   if (M->ge_inv && M->ge_n == L.n)
+   {
+      k_dense_apply<<<cdiv(L.n, 8), 256, 0, g.stream>>>(M->ge_inv, f, u, L.n);
+      HDK_LAUNCH_CHECK();
+      return HDK_OK;
+   }
+   // no dense factor (operator too large or smoother requested): relaxation sweeps
+   int     type = (M->prm.relax_coarse == 9 || M->prm.relax_coarse == 99) ? 18 : M->prm.relax_coarse;
+   double *cur = u, *oth = alt;
+   int     sweeps = M->prm.sweeps_coarse < 1 ? 1 : M->prm.sweeps_coarse;
+   for (int s = 0; s < sweeps; s++)
+   {
+      if (s == 0 && zero_guess && is_jacobi(type))
+      {
+         HDK_TRY(vec_scaled_div(cur, f, L.l1_down, M->prm.relax_weight, L.n));
+      }
+      else
+      {
+         if (s == 0 && zero_guess) HDK_TRY(vec_fill(cur, 0.0, L.n));
+         HDK_TRY(relax_sweep(M, l, type, L.l1_down, f, cur, oth, FIN_NONE, nullptr));
+         double *tmp = cur; cur = oth; oth = tmp;
+      }
+   }
+   *result = cur;
+   return HDK_OK;
+}
+
+// One V-cycle.  Level-0 vectors are the caller's (f, u); u is also used as scratch.
+int amg_cycle(hdk_amg_s *M, const double *f0, double *u0, bool zero_guess, int fin, double *fin_out)
+{
+   const int            nl = M->nlev, Lc = nl - 1;
+   const hdk_amg_params &p = M->prm;
+   std::vector<double *> cur((size_t)nl), alt((size_t)nl);
+   std::vector<const double *> rhs((size_t)nl);
+   bool                  fin_done = false;
+   // level-0 buffer parity so that the result lands in u0 without a copy (default sweeps)
+   {
+      AmgLevel &L0 = M->lev[0];
+      int       oop;
+      if (nl == 1) oop = 0;
+      else
+      {
+         int down_oop = zero_guess && is_jacobi(p.relax_down) ? (p.sweeps_down > 0 ? p.sweeps_down - 1 : 0) : p.sweeps_down;
+         oop          = down_oop + p.sweeps_up;
+      }
+      bool start_in_u0 = zero_guess ? (oop % 2 == 0) : true;
+      cur[0] = start_in_u0 ? u0 : L0.t;
+      alt[0] = start_in_u0 ? L0.t : u0;
+      rhs[0] = f0;
+   }
+   for (int l = 1; l < nl; l++) { cur[(size_t)l] = M->lev[(size_t)l].u; alt[(size_t)l] = M->lev[(size_t)l].t; rhs[(size_t)l] = M->lev[(size_t)l].f; }
+
+   for (int l = 0; l < Lc; l++)
+   {
+      AmgLevel &L = M->lev[(size_t)l];
+      bool      zg = (l > 0) || zero_guess;
+      for (int s = 0; s < p.sweeps_down; s++)
+      {
+         if (s == 0 && zg && is_jacobi(p.relax_down))
+         {
+            HDK_TRY(vec_scaled_div(cur[(size_t)l], rhs[(size_t)l], L.l1_down, p.relax_weight, L.n));
+         }
+         else
+         {
+            if (s == 0 && zg) HDK_TRY(vec_fill(cur[(size_t)l], 0.0, L.n));
+            HDK_TRY(relax_sweep(M, l, p.relax_down, L.l1_down, rhs[(size_t)l], cur[(size_t)l], alt[(size_t)l], FIN_NONE, nullptr));
+            std::swap(cur[(size_t)l], alt[(size_t)l]);
+         }
+      }
+      if (p.sweeps_down == 0 && zg) HDK_TRY(vec_fill(cur[(size_t)l], 0.0, L.n));
+      // residual into the spare buffer, restrict to the next level
+      SpmvArgs a;
+      if (p.sweeps_down == 0 && zg)
+      {
+         HDK_TRY(vec_copy(alt[(size_t)l], rhs[(size_t)l], L.n));
+      }
+      else
+      {
+         a.x = cur[(size_t)l]; a.y = alt[(size_t)l]; a.b = rhs[(size_t)l];
+         HDK_TRY(parcsr_matvec(*L.A, SPMV_RESIDUAL, a));
+      }
+      SpmvArgs rr;
+      rr.x = alt[(size_t)l]; rr.y = M->lev[(size_t)l + 1].f;
+      HDK_TRY(parcsr_matvec(*L.R, SPMV_SET, rr));
+   }
+   // coarsest level
+   {
+      double *res;
+      bool    zg = (Lc > 0) || zero_guess;
+      if (nl == 1 && !(M->ge_inv && M->ge_n == M->lev[0].n))
+      {
+         // single-level hierarchy without a dense factor: smoother sweeps on the caller's vectors
+         HDK_TRY(coarse_solve(M, 0, rhs[0], cur[0], alt[0], zg, &res));
+         if (res != u0) HDK_TRY(vec_copy(u0, res, M->lev[0].n));
+      }
+      else
+      {
+         HDK_TRY(coarse_solve(M, Lc, rhs[(size_t)Lc], cur[(size_t)Lc], alt[(size_t)Lc], zg, &res));
+         if (res != cur[(size_t)Lc]) std::swap(cur[(size_t)Lc], alt[(size_t)Lc]);
+         if (nl == 1 && res != u0) HDK_TRY(vec_copy(u0, res, M->lev[0].n));
+      }
+   }
+   for (int l = Lc - 1; l >= 0; l--)
+   {
+      AmgLevel &L = M->lev[(size_t)l];
+      // u += P e_c
+      SpmvArgs a;
+      a.x = cur[(size_t)l + 1]; a.y = cur[(size_t)l];
+      HDK_TRY(parcsr_matvec(*L.P, SPMV_ADD, a));
+      for (int s = 0; s < p.sweeps_up; s++)
+      {
+         bool last = (l == 0 && s == p.sweeps_up - 1);
+         int  f_   = (last && fin != FIN_NONE) ? fin : FIN_NONE;
+         HDK_TRY(relax_sweep(M, l, p.relax_up, L.l1_up, rhs[(size_t)l], cur[(size_t)l], alt[(size_t)l], f_, fin_out));
+         std::swap(cur[(size_t)l], alt[(size_t)l]);
+         if (f_ != FIN_NONE) fin_done = true;
+      }
+   }
+   if (cur[0] != u0) HDK_TRY(vec_copy(u0, cur[0], M->lev[0].n));
+   if (fin != FIN_NONE && !fin_done) HDK_TRY(vec_dot_dev(f0, u0, M->lev[0].n, fin, fin_out));
+   return HDK_OK;
+}
+
+int amg_precond(hdk_amg_s *M, const double *r, double *z, int fin, double *fin_out)
+{
+   return amg_cycle(M, r, z, true, fin, fin_out);
+}
+
+} // namespace hdk
+
+using namespace hdk;
+
+extern "C" {
+
+int hdk_amg_apply(hdk_amg *M, const double *r_d, double *z_d)
+{
+   HDK_TRY(require_init());
+   if (!M) return set_error(HDK_ERR_INVALID, "null hierarchy");
+   return amg_precond(M, r_d, z_d, FIN_NONE, nullptr);
+}
+
+int hdk_amg_vcycle(hdk_amg *M, const double *f_d, double *u_d)
+{
+   HDK_TRY(require_init());
+   if (!M) return set_error(HDK_ERR_INVALID, "null hierarchy");
+   return amg_cycle(M, f_d, u_d, false, FIN_NONE, nullptr);
+}
+
+// CUDA-event timing of one hot kernel, `reps` back-to-back launches (bench.py roofline leg)
+int hdk_time_kernel(const hdk_csr *A, hdk_amg *M, int kernel, int reps, double *avg_ms, double *bytes)
+{
+   HDK_TRY(require_init());
+   if (!A) return set_error(HDK_ERR_INVALID, "null matrix");
+   const int64_t n = A->diag.nrows;
+   const double  nnz = (double)A->diag.nnz + A->offd.nnz;
+   double *x, *y, *b, *d;
+   HDK_TRY(dalloc(&x, (size_t)n + 8)); HDK_TRY(dalloc(&y, (size_t)n + 8));
+   HDK_TRY(dalloc(&b, (size_t)n + 8)); HDK_TRY(dalloc(&d, (size_t)n + 8));
+   HDK_TRY(hdk_vec_random(x, n, A->row_start, 1));
+   HDK_TRY(hdk_vec_random(b, n, A->row_start, 2));
+   HDK_TRY(vec_fill(d, 6.0, n));
+   HDK_TRY(vec_fill(y, 0.0, n));
+   double by = 0.0;
+   int    rc = HDK_OK;
+   for (int pass = 0; pass < 2 && rc == HDK_OK; pass++)
+   {
+      int count = pass == 0 ? 3 : reps; // warm-up, then timed
+      if (pass == 1) HDK_CUDA(cudaEventRecord(g.ev_a, g.stream));
+      for (int it = 0; it < count && rc == HDK_OK; it++)
+      {
+         SpmvArgs a;
+         a.x = x; a.y = y; a.b = b; a.d = d;
+         switch (kernel)
+         {
+            case 0: rc = parcsr_matvec(*A, SPMV_SET, a); by = 12.0 * nnz + 4.0 * (n + 1) + 16.0 * n; break;
+            case 1: rc = parcsr_matvec(*A, SPMV_JACOBI, a); by = 12.0 * nnz + 4.0 * (n + 1) + 32.0 * n; break;
+            case 2: rc = parcsr_matvec(*A, SPMV_RESIDUAL, a); by = 12.0 * nnz + 4.0 * (n + 1) + 24.0 * n; break;
+            case 3:
+               rc = vec_fill(g.dscal + S_ALPHA, 1e-3, 1);
+               if (rc == HDK_OK) rc = pcg_update_xr(y, b, x, d, n, g.dscal);
+               by = 48.0 * n; break;
+            case 4:
+               if (!M) rc = set_error(HDK_ERR_INVALID, "V-cycle timing needs a hierarchy");
+               else { rc = amg_precond(M, b, y, FIN_NONE, nullptr); by = M->vcycle_bytes; }
+               break;
+            default: rc = set_error(HDK_ERR_INVALID, "unknown kernel id %d", kernel);
+         }
+      }
+   }
+   if (rc == HDK_OK)
+   {
+      HDK_CUDA(cudaEventRecord(g.ev_b, g.stream));
+      HDK_CUDA(cudaEventSynchronize(g.ev_b));
+      float ms = 0.f;
+      HDK_CUDA(cudaEventElapsedTime(&ms, g.ev_a, g.ev_b));
+      if (avg_ms) *avg_ms = (double)ms / (reps > 0 ? reps : 1);
+      if (bytes) *bytes = by;
+   }
+   dfree(x); dfree(y); dfree(b); dfree(d);
+   return rc;
+}
+
+} // extern "C"

@@ -1,0 +1,261 @@
+// hdk_internal.cuh -- shared device-side plumbing of the hdk kernels (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+#include <string>
+#include <vector>
+#include "hdk.h"
+
+namespace hdk {
+
+struct Ctx
+{
+   bool         inited = false;
+   int          device = 0;
+   int          sm_count = 148;
+   cudaStream_t stream = nullptr;     // compute stream
+   cudaStream_t comm_stream = nullptr; // halo exchange stream
+   cudaEvent_t  ev_a = nullptr, ev_b = nullptr, ev_scal = nullptr, ev_halo = nullptr, ev_pack = nullptr;
+   int          rank = 0, nranks = 1;
+   void        *nccl = nullptr;        // ncclComm_t
+   int64_t      launches = 0;
+   // reduction scratch
+   double      *partials = nullptr;    // device, PARTIALS_CAP doubles
+   unsigned    *counters = nullptr;    // device, 64 tickets (zero-initialised, self-resetting)
+   double      *dscal = nullptr;       // device scalar block (64 doubles)
+   double      *hscal = nullptr;       // pinned host mirror (64 doubles)
+   char         err[1024] = {0};
+};
+
+extern Ctx g;
+constexpr int PARTIALS_CAP = 1 << 20;
+
+int  set_error(int code, const char *fmt, ...);
+int  require_init();
+
+#define HDK_CUDA(call)                                                                     \
+   do {                                                                                    \
+      cudaError_t e__ = (call);                                                            \
+      if (e__ != cudaSuccess)                                                              \
+         return hdk::set_error(HDK_ERR_CUDA, "%s:%d %s -> %s", __FILE__, __LINE__, #call,  \
+                               cudaGetErrorString(e__));                                   \
+   } while (0)
+
+#define HDK_TRY(call)                  \
+   do {                                \
+      int rc__ = (call);               \
+      if (rc__ != HDK_OK) return rc__; \
+   } while (0)
+
+#define HDK_LAUNCH_CHECK()                                                                  \
+   do {                                                                                     \
+      hdk::g.launches++;                                                                    \
+      cudaError_t e__ = cudaGetLastError();                                                 \
+      if (e__ != cudaSuccess)                                                               \
+         return hdk::set_error(HDK_ERR_CUDA, "%s:%d launch -> %s", __FILE__, __LINE__,      \
+                               cudaGetErrorString(e__));                                    \
+   } while (0)
+
+// stream-ordered allocation from the device memory pool (cached between calls)
+template <class T>
+inline int dalloc(T **p, size_t n)
+{
+   *p = nullptr;
+   if (n == 0) n = 1;
+   cudaError_t e = cudaMallocAsync((void **)p, n * sizeof(T), g.stream);
+   if (e != cudaSuccess)
+      return set_error(HDK_ERR_ALLOC, "cudaMallocAsync(%zu bytes) -> %s", n * sizeof(T),
+                       cudaGetErrorString(e));
+   return HDK_OK;
+}
+inline void dfree(void *p)
+{
+   if (p) cudaFreeAsync(p, g.stream);
+}
+
+inline int cdiv(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
+
+// ---------------------------------------------------------------------------------------
+// One CSR block on the device.  rowptr/col are int32 (hypre HYPRE_Int), values fp64.
+// col/val are allocated with 8 slack entries (col = 0, val = 0) so 128-bit loads that
+// start at a 4-entry aligned index never leave the allocation.
+// ---------------------------------------------------------------------------------------
+struct DevCSR
+{
+   int     nrows = 0, ncols = 0;
+   int     nnz = 0;
+   int    *rowptr = nullptr;
+   int    *col = nullptr;
+   double *val = nullptr;
+   // SpMV analysis (row-length statistics -> kernel choice)
+   int     kind = 0;          // 0 stream, 1 vector (warp per row)
+   int     max_row = 0;
+   double  avg_row = 0.0;
+   int     nblk = 0;          // stream kernel: number of nnz-balanced row blocks
+   int    *blk_row = nullptr; // nblk+1 first rows
+   bool    owns = true;
+};
+
+int  csr_alloc(DevCSR &A, int nrows, int ncols, int nnz, bool values = true);
+void csr_free(DevCSR &A);
+int  csr_analyze(DevCSR &A);
+
+// epilogue selectors of the fused SpMV family (see hdk_spmv.cu)
+enum SpmvMode
+{
+   SPMV_SET = 0,      // y = A x
+   SPMV_RESIDUAL = 1, // y = b - A x        (res = b; res -= a*x in CSR order)
+   SPMV_JACOBI = 2,   // y = x + w*(b - A x)/d
+   SPMV_ADD = 3,      // y = y + A x        (s = y; s += a*x in CSR order)
+   SPMV_AXPBY = 4,    // y = alpha*(A x) + beta*y
+   SPMV_JACOBI_R = 5  // y = w*(b - A x)/d  (two-stage GS first stage)
+};
+
+// what the last block does with a fused dot product
+enum FinOp
+{
+   FIN_NONE = 0,
+   FIN_STORE = 1,  // out[0] = v
+   FIN_SDOTP = 2,  // PCG: sdotp = v; alpha = gamma / v
+   FIN_IPROD = 3,  // PCG: i_prod = v
+   FIN_GAMMA = 4   // PCG: gamma_old = gamma; gamma = v; beta = v / gamma_old
+};
+
+// layout of the device scalar block used by the Krylov drivers
+enum ScalIdx
+{
+   S_BIPROD = 0, S_GAMMA = 1, S_GAMMA_OLD = 2, S_SDOTP = 3, S_IPROD = 4, S_ALPHA = 5, S_BETA = 6,
+   S_TMP0 = 8, S_TMP1 = 9, S_TMP2 = 10, S_TMP3 = 11, S_H0 = 16 /* 16..63: GMRES h column */
+};
+
+struct SpmvArgs
+{
+   const double *x = nullptr;   // input vector (gathered)
+   double       *y = nullptr;   // output
+   const double *b = nullptr;   // rhs (RESIDUAL / JACOBI)
+   const double *d = nullptr;   // diagonal scaling (JACOBI)
+   const double *xo = nullptr;  // halo part of x (offd block), appended columns
+   double        w = 1.0, alpha = 1.0, beta = 0.0;
+   // fused dot: sum_i dotv[i]*y_new[i]  (dotv may alias x or b)
+   const double *dotv = nullptr;
+   int           fin = FIN_NONE;
+   double       *fin_out = nullptr;
+};
+
+int spmv_launch(const DevCSR &A, int mode, const SpmvArgs &a);
+
+// vector kernels (hdk_vec.cu)
+int vec_fill(double *x, double v, int64_t n);
+int vec_copy(double *dst, const double *src, int64_t n);
+int vec_axpy(double a, const double *x, double *y, int64_t n);
+int vec_scale(double a, double *x, int64_t n);
+int vec_dot_dev(const double *x, const double *y, int64_t n, int fin, double *out_d); // device result
+int vec_dot_host(const double *x, const double *y, int64_t n, double *out_h);         // + allreduce
+int vec_scaled_div(double *u, const double *f, const double *d, double w, int64_t n); // u = w f / d
+int pcg_update_xr(double *x, double *r, const double *p, const double *s, int64_t n, double *scal);
+int pcg_update_p(double *p, const double *z, int64_t n, const double *scal);
+int vec_copy_dot(double *z, const double *r, int64_t n, int fin, double *out_d);      // z=r, <r,r>
+int allreduce_dev(double *buf_d, int count);                                          // NCCL sum (no-op on 1 rank)
+
+// ---------------------------------------------------------------------------------------
+// ParCSR of one rank: diag + offd blocks, halo bookkeeping
+// ---------------------------------------------------------------------------------------
+struct HaloPlan
+{
+   int                 n_halo = 0;         // number of offd columns (size of x_halo)
+   int64_t            *col_map = nullptr;  // device, sorted global ids of offd columns
+   std::vector<int>     recv_rank, recv_off, recv_cnt; // per neighbour (host)
+   std::vector<int>     send_rank, send_off, send_cnt;
+   int                 n_send = 0;
+   int                *send_idx = nullptr; // device, local row ids to pack
+   double             *send_buf = nullptr; // device
+   double             *x_halo = nullptr;   // device
+};
+
+} // namespace hdk
+
+struct hdk_csr_s
+{
+   int64_t       row_start = 0, row_end = -1, global_rows = 0, global_nnz = 0;
+   hdk::DevCSR   diag, offd;
+   hdk::HaloPlan halo;
+   std::vector<int64_t> row_starts; // partition (nranks+1), host
+};
+
+namespace hdk {
+int parcsr_matvec(const hdk_csr_s &A, int mode, SpmvArgs a); // halo exchange + diag + offd
+int halo_exchange_begin(const hdk_csr_s &A, const double *x);
+int halo_exchange_end(const hdk_csr_s &A);
+
+// ---------------------------------------------------------------------------------------
+// device reduction helper: block sum -> partials -> last block finishes (deterministic)
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ double warp_sum(double v)
+{
+#pragma unroll
+   for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+   return v;
+}
+
+template <int THREADS>
+__device__ __forceinline__ double block_sum(double v, double *sm /* THREADS/32 */)
+{
+   int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+   v = warp_sum(v);
+   if (lane == 0) sm[w] = v;
+   __syncthreads();
+   double r = 0.0;
+   if (w == 0)
+   {
+      r = (lane < THREADS / 32) ? sm[lane] : 0.0;
+      r = warp_sum(r);
+   }
+   return r; // valid in thread 0
+}
+
+__device__ __forceinline__ void apply_fin(int fin, double v, double *out, double *scal)
+{
+   switch (fin)
+   {
+      case FIN_STORE: out[0] = v; break;
+      case FIN_SDOTP: scal[S_SDOTP] = v; scal[S_ALPHA] = scal[S_GAMMA] / v; break;
+      case FIN_IPROD: scal[S_IPROD] = v; break;
+      case FIN_GAMMA:
+      {
+         double go = scal[S_GAMMA];
+         scal[S_GAMMA_OLD] = go; scal[S_GAMMA] = v; scal[S_BETA] = v / go;
+         break;
+      }
+      default: break;
+   }
+}
+
+// Every block calls this with its (thread-0 valid) block sum.  The last block to arrive adds
+// the partials in a fixed order and applies `fin`.  ticket counters wrap back to zero.
+template <int THREADS>
+__device__ __forceinline__ void grid_finish(double blocksum, double *partials, unsigned *ticket,
+                                            int fin, double *out, double *scal, double *sm,
+                                            int *flag_sm)
+{
+   if (threadIdx.x == 0)
+   {
+      partials[blockIdx.x] = blocksum;
+      __threadfence();
+      unsigned t = atomicInc(ticket, gridDim.x - 1);
+      *flag_sm   = (t == gridDim.x - 1);
+   }
+   __syncthreads();
+   if (*flag_sm)
+   {
+      __threadfence();
+      double s = 0.0;
+      for (unsigned i = threadIdx.x; i < gridDim.x; i += THREADS) s += __ldcg(partials + i);
+      __syncthreads();
+      s = block_sum<THREADS>(s, sm);
+      if (threadIdx.x == 0) apply_fin(fin, s, out, scal);
+   }
+}
+
+} // namespace hdk

@@ -1,0 +1,309 @@
+// hdk_krylov.cu -- PCG and right-preconditioned GMRES(k) drivers on the device.
+// Stands in for HYPRE_ParCSRPCGSolve / HYPRE_ParCSRGMRESSolve (hypre krylov/pcg.c,
+// krylov/gmres.c) as called from src/internal/solver.c:211, 223, 614 of the reference, with the
+// option sets of src/internal/pcg.c:15-25 (two_norm 1, rel_change 0, stop_crit 0) and
+// src/internal/gmres.c:16-27.  All vector work and every scalar recurrence stay on the GPU:
+// the host only reads one small scalar block per iteration to take the stopping decision, and
+// that read overlaps the preconditioner application that hypre performs before its test.
+#include "hdk_internal.cuh"
+#include "hdk_amg.cuh"
+#include <math.h>
+
+namespace hdk {
+
+__global__ void k_apply_fin(int fin, const double *v, double *out, double *scal)
+{
+   apply_fin(fin, v[0], out, scal);
+}
+
+// with one rank the last block of the producing kernel applies `fin`; with several ranks the
+// local partial sits in S_TMP0 and is summed over NVLink first
+static int finish_dot(int fin, double *out)
+{
+   if (g.nranks <= 1) return HDK_OK;
+   HDK_TRY(allreduce_dev(g.dscal + S_TMP0, 1));
+   k_apply_fin<<<1, 1, 0, g.stream>>>(fin, g.dscal + S_TMP0, out, g.dscal);
+   HDK_LAUNCH_CHECK();
+   return HDK_OK;
+}
+static inline int local_fin(int fin) { return g.nranks <= 1 ? fin : FIN_STORE; }
+static inline double *local_out(double *out) { return g.nranks <= 1 ? out : g.dscal + S_TMP0; }
+
+// z = M^{-1} r, fused <r,z> -> fin
+static int precond_dot(hdk_amg_s *M, const double *r, double *z, int64_t n, int fin, double *out)
+{
+   if (M)
+   {
+      HDK_TRY(amg_precond(M, r, z, local_fin(fin), local_out(out)));
+   }
+   else
+   {
+      HDK_TRY(vec_copy_dot(z, r, n, local_fin(fin), local_out(out)));
+   }
+   return finish_dot(fin, out);
+}
+
+static int read_scalars(int count)
+{
+   HDK_CUDA(cudaMemcpyAsync(g.hscal, g.dscal, sizeof(double) * (size_t)count, cudaMemcpyDeviceToHost, g.stream));
+   HDK_CUDA(cudaEventRecord(g.ev_scal, g.stream));
+   return HDK_OK;
+}
+
+__global__ void k_axpy_dev(const double *coef, double sign, const double *__restrict__ x,
+                           double *__restrict__ y, int64_t n)
+{
+   const double a = sign * coef[0];
+   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+      y[i] = __dadd_rn(y[i], __dmul_rn(a, x[i]));
+}
+
+static int axpy_dev(const double *coef, double sign, const double *x, double *y, int64_t n)
+{
+   if (n <= 0) return HDK_OK;
+   int64_t want = (n + 1023) / 1024, cap = (int64_t)g.sm_count * 8;
+   int     grid = (int)(want < cap ? (want < 1 ? 1 : want) : cap);
+   k_axpy_dev<<<grid, 256, 0, g.stream>>>(coef, sign, x, y, n);
+   HDK_LAUNCH_CHECK();
+   return HDK_OK;
+}
+
+} // namespace hdk
+
+using namespace hdk;
+
+extern "C" {
+
+int hdk_pcg(const hdk_csr *A, hdk_amg *M, const double *b, double *x, hdk_krylov *k)
+{
+   HDK_TRY(require_init());
+   if (!A || !b || !x || !k) return set_error(HDK_ERR_INVALID, "hdk_pcg: null argument");
+   const int64_t n = A->diag.nrows;
+   k->iters = 0; k->converged = 0; k->rel_res_norm = 0.0; k->solve_ms = 0.0;
+   double *r, *p, *s;
+   HDK_TRY(dalloc(&r, (size_t)n + 8));
+   HDK_TRY(dalloc(&p, (size_t)n + 8));
+   HDK_TRY(dalloc(&s, (size_t)n + 8));
+   double *S = g.dscal;
+   HDK_CUDA(cudaEventRecord(g.ev_a, g.stream));
+
+   double bi_prod;
+   HDK_TRY(vec_dot_host(b, b, n, &bi_prod));
+   double eps = k->rel_tol * k->rel_tol;
+   int    rc  = HDK_OK;
+   int    i   = 0;
+   double i_prod = 0.0;
+   if (bi_prod > 0.0)
+   {
+      if (k->abs_tol > 0 && k->abs_tol * k->abs_tol / bi_prod > eps) eps = k->abs_tol * k->abs_tol / bi_prod;
+   }
+   else
+   {
+      // zero right-hand side: x = 0 (hypre_PCGSolve)
+      rc = vec_fill(x, 0.0, n);
+      k->converged = 1;
+      goto done;
+   }
+   {
+      // r = b - A x ; p = M^{-1} r ; gamma = <r,p> ; i_prod = <r,r>
+      SpmvArgs a;
+      a.x = x; a.y = r; a.b = b;
+      if ((rc = parcsr_matvec(*A, SPMV_RESIDUAL, a))) goto done;
+      if ((rc = precond_dot(M, r, p, n, FIN_STORE, S + S_GAMMA))) goto done;
+   }
+   while (i + 1 <= k->max_iter)
+   {
+      i++;
+      // s = A p ; sdotp = <s,p> ; alpha = gamma / sdotp   (one kernel)
+      SpmvArgs a;
+      a.x = p; a.y = s; a.dotv = p; a.fin = local_fin(FIN_SDOTP); a.fin_out = local_out(nullptr);
+      if ((rc = parcsr_matvec(*A, SPMV_SET, a))) goto done;
+      if ((rc = finish_dot(FIN_SDOTP, nullptr))) goto done;
+      // x += alpha p ; r -= alpha s ; i_prod = <r,r>       (one kernel)
+      if (g.nranks <= 1) { if ((rc = pcg_update_xr(x, r, p, s, n, S))) goto done; }
+      else
+      {
+         if ((rc = axpy_dev(S + S_ALPHA, 1.0, p, x, n))) goto done;
+         if ((rc = axpy_dev(S + S_ALPHA, -1.0, s, r, n))) goto done;
+         if ((rc = vec_dot_dev(r, r, n, FIN_STORE, S + S_TMP0))) goto done;
+         if ((rc = finish_dot(FIN_IPROD, nullptr))) goto done;
+      }
+      if ((rc = read_scalars(8))) goto done;
+      // s = M^{-1} r ; gamma_new = <r,s> ; beta = gamma_new / gamma  (V-cycle; the host
+      // decision below overlaps it -- hypre also preconditions before testing)
+      if ((rc = precond_dot(M, r, s, n, FIN_GAMMA, nullptr))) goto done;
+      cudaError_t e = cudaEventSynchronize(g.ev_scal);
+      if (e != cudaSuccess) { rc = set_error(HDK_ERR_CUDA, "event sync: %s", cudaGetErrorString(e)); goto done; }
+      i_prod = g.hscal[S_IPROD];
+      if (g.hscal[S_SDOTP] == 0.0 || i_prod != i_prod) { break; }
+      if (i_prod / bi_prod < eps) { k->converged = 1; break; }
+      // p = s + beta p
+      if ((rc = pcg_update_p(p, s, n, S))) goto done;
+   }
+   k->iters        = i;
+   k->rel_res_norm = sqrt(i_prod / bi_prod);
+done:
+   cudaEventRecord(g.ev_b, g.stream);
+   cudaEventSynchronize(g.ev_b);
+   float ms = 0.f;
+   cudaEventElapsedTime(&ms, g.ev_a, g.ev_b);
+   k->solve_ms = ms;
+   dfree(r); dfree(p); dfree(s);
+   return rc;
+}
+
+int hdk_gmres(const hdk_csr *A, hdk_amg *M, const double *b, double *x, hdk_krylov *k)
+{
+   HDK_TRY(require_init());
+   if (!A || !b || !x || !k) return set_error(HDK_ERR_INVALID, "hdk_gmres: null argument");
+   const int64_t n  = A->diag.nrows;
+   const int     kd = k->krylov_dim > 0 ? (k->krylov_dim > 46 ? 46 : k->krylov_dim) : 30;
+   k->iters = 0; k->converged = 0; k->rel_res_norm = 0.0; k->solve_ms = 0.0;
+   std::vector<double *> p((size_t)kd + 1, nullptr);
+   double *r = nullptr, *w = nullptr;
+   int     rc = HDK_OK;
+   for (int j = 0; j <= kd; j++) if ((rc = dalloc(&p[(size_t)j], (size_t)n + 8))) return rc;
+   HDK_TRY(dalloc(&r, (size_t)n + 8));
+   HDK_TRY(dalloc(&w, (size_t)n + 8));
+   std::vector<double> c((size_t)kd + 1, 0.0), s((size_t)kd + 1, 0.0), rs((size_t)kd + 2, 0.0);
+   std::vector<double> hh((size_t)(kd + 2) * (kd + 1), 0.0);
+#define HH(a_, b_) hh[(size_t)(a_) * (kd + 1) + (b_)]
+   const double epsmac = 1.e-16;
+   double *S = g.dscal;
+   HDK_CUDA(cudaEventRecord(g.ev_a, g.stream));
+   double b_norm = 0, r_norm = 0, t = 0;
+   int    iter = 0;
+   {
+      double d;
+      if ((rc = vec_dot_host(b, b, n, &d))) goto done;
+      b_norm = sqrt(d);
+      SpmvArgs a;
+      a.x = x; a.y = p[0]; a.b = b;
+      if ((rc = parcsr_matvec(*A, SPMV_RESIDUAL, a))) goto done;
+      if ((rc = vec_dot_host(p[0], p[0], n, &d))) goto done;
+      r_norm = sqrt(d);
+   }
+   {
+      double den = b_norm > 0.0 ? b_norm : r_norm;
+      double eps = k->rel_tol * den;
+      if (k->abs_tol > eps) eps = k->abs_tol;
+      double real_old = r_norm;
+      while (iter < k->max_iter)
+      {
+         rs[0] = r_norm;
+         if (r_norm == 0.0) { k->converged = 1; break; }
+         if (r_norm <= eps && iter >= k->min_iter)
+         {
+            SpmvArgs a;
+            a.x = x; a.y = r; a.b = b;
+            if ((rc = parcsr_matvec(*A, SPMV_RESIDUAL, a))) goto done;
+            double d;
+            if ((rc = vec_dot_host(r, r, n, &d))) goto done;
+            r_norm = sqrt(d);
+            if (r_norm <= eps) { k->converged = 1; break; }
+         }
+         if ((rc = vec_scale(1.0 / r_norm, p[0], n))) goto done;
+         int i = 0;
+         while (i < kd && iter < k->max_iter)
+         {
+            i++; iter++;
+            // r = M^{-1} p[i-1] ; p[i] = A r
+            if (M) { if ((rc = amg_precond(M, p[(size_t)i - 1], r, FIN_NONE, nullptr))) goto done; }
+            else if ((rc = vec_copy(r, p[(size_t)i - 1], n))) goto done;
+            SpmvArgs a;
+            a.x = r; a.y = p[(size_t)i];
+            if ((rc = parcsr_matvec(*A, SPMV_SET, a))) goto done;
+            // modified Gram-Schmidt: coefficients stay on the device (S_H0 + j)
+            for (int j = 0; j < i; j++)
+            {
+               if ((rc = vec_dot_dev(p[(size_t)j], p[(size_t)i], n, FIN_STORE, S + S_H0 + j))) goto done;
+               if ((rc = allreduce_dev(S + S_H0 + j, 1))) goto done;
+               if ((rc = axpy_dev(S + S_H0 + j, -1.0, p[(size_t)j], p[(size_t)i], n))) goto done;
+            }
+            if ((rc = vec_dot_dev(p[(size_t)i], p[(size_t)i], n, FIN_STORE, S + S_H0 + i))) goto done;
+            if ((rc = allreduce_dev(S + S_H0 + i, 1))) goto done;
+            HDK_CUDA(cudaMemcpyAsync(g.hscal + S_H0, S + S_H0, sizeof(double) * (size_t)(i + 1), cudaMemcpyDeviceToHost, g.stream));
+            HDK_CUDA(cudaStreamSynchronize(g.stream));
+            for (int j = 0; j < i; j++) HH(j, i - 1) = g.hscal[S_H0 + j];
+            t            = sqrt(g.hscal[S_H0 + i]);
+            HH(i, i - 1) = t;
+            if (t != 0.0) { if ((rc = vec_scale(1.0 / t, p[(size_t)i], n))) goto done; }
+            for (int j = 1; j < i; j++)
+            {
+               t                = HH(j - 1, i - 1);
+               HH(j - 1, i - 1) = s[(size_t)j - 1] * HH(j, i - 1) + c[(size_t)j - 1] * t;
+               HH(j, i - 1)     = -s[(size_t)j - 1] * t + c[(size_t)j - 1] * HH(j, i - 1);
+            }
+            t = HH(i, i - 1) * HH(i, i - 1);
+            t += HH(i - 1, i - 1) * HH(i - 1, i - 1);
+            double gamma = sqrt(t);
+            if (gamma == 0.0) gamma = epsmac;
+            c[(size_t)i - 1] = HH(i - 1, i - 1) / gamma;
+            s[(size_t)i - 1] = HH(i, i - 1) / gamma;
+            rs[(size_t)i]    = -HH(i, i - 1) * rs[(size_t)i - 1];
+            rs[(size_t)i] /= gamma;
+            rs[(size_t)i - 1] = c[(size_t)i - 1] * rs[(size_t)i - 1];
+            HH(i - 1, i - 1)  = s[(size_t)i - 1] * HH(i, i - 1) + c[(size_t)i - 1] * HH(i - 1, i - 1);
+            r_norm            = fabs(rs[(size_t)i]);
+            if (r_norm <= eps && iter >= k->min_iter) break;
+         }
+         // solve the triangular system, w = sum rs_j p_j, x += M^{-1} w
+         rs[(size_t)i - 1] = rs[(size_t)i - 1] / HH(i - 1, i - 1);
+         for (int kk = i - 2; kk >= 0; kk--)
+         {
+            t = 0.0;
+            for (int j = kk + 1; j < i; j++) t -= HH(kk, j) * rs[(size_t)j];
+            t += rs[(size_t)kk];
+            rs[(size_t)kk] = t / HH(kk, kk);
+         }
+         if ((rc = vec_copy(w, p[(size_t)i - 1], n))) goto done;
+         if ((rc = vec_scale(rs[(size_t)i - 1], w, n))) goto done;
+         for (int j = i - 2; j >= 0; j--) if ((rc = vec_axpy(rs[(size_t)j], p[(size_t)j], w, n))) goto done;
+         if (M) { if ((rc = amg_precond(M, w, r, FIN_NONE, nullptr))) goto done; }
+         else if ((rc = vec_copy(r, w, n))) goto done;
+         if ((rc = vec_axpy(1.0, r, x, n))) goto done;
+         if (r_norm <= eps && iter >= k->min_iter)
+         {
+            if (k->skip_real_res_check) { k->converged = 1; break; }
+            SpmvArgs a;
+            a.x = x; a.y = r; a.b = b;
+            if ((rc = parcsr_matvec(*A, SPMV_RESIDUAL, a))) goto done;
+            double d;
+            if ((rc = vec_dot_host(r, r, n, &d))) goto done;
+            double real_new = r_norm = sqrt(d);
+            if (r_norm <= eps) { k->converged = 1; break; }
+            if (real_new >= real_old) { k->converged = 1; break; }
+            if ((rc = vec_copy(p[0], r, n))) goto done;
+            i        = 0;
+            real_old = real_new;
+         }
+         // residual vector for the restart from the rotations
+         for (int j = i; j > 0; j--)
+         {
+            rs[(size_t)j - 1] = -s[(size_t)j - 1] * rs[(size_t)j];
+            rs[(size_t)j]     = c[(size_t)j - 1] * rs[(size_t)j];
+         }
+         if (i) if ((rc = vec_scale(rs[(size_t)i], p[(size_t)i], n))) goto done; // p_i += (rs_i - 1) p_i
+         for (int j = i - 1; j > 0; j--) if ((rc = vec_axpy(rs[(size_t)j], p[(size_t)j], p[(size_t)i], n))) goto done;
+         if (i)
+         {
+            if ((rc = vec_scale(rs[0], p[0], n))) goto done;
+            if ((rc = vec_axpy(1.0, p[(size_t)i], p[0], n))) goto done;
+         }
+      }
+      k->iters        = iter;
+      k->rel_res_norm = b_norm > 0.0 ? r_norm / b_norm : r_norm;
+   }
+#undef HH
+done:
+   cudaEventRecord(g.ev_b, g.stream);
+   cudaEventSynchronize(g.ev_b);
+   float ms = 0.f;
+   cudaEventElapsedTime(&ms, g.ev_a, g.ev_b);
+   k->solve_ms = ms;
+   for (auto q : p) dfree(q);
+   dfree(r); dfree(w);
+   return rc;
+}
+
+} // extern "C"

@@ -1,0 +1,288 @@
+// hdk_vec.cu -- Krylov vector layer: fused axpy / dot / norm single-pass kernels with
+// warp-shuffle block reductions (north-star item 3).  Stands in for hypre_ParVectorAxpy,
+// hypre_ParVectorInnerProd, hypre_ParVectorScale, hypre_ParVectorCopy as driven from
+// hypre_PCGSolve / hypre_GMRESSolve (reference call sites src/internal/solver.c:614,
+// src/internal/linsys.c:2875).
+#include "hdk_internal.cuh"
+#include <math.h>
+
+namespace hdk {
+
+constexpr int VT = 256;
+
+static inline int vec_grid(int64_t n)
+{
+   int64_t want = (n + (int64_t)VT * 4 - 1) / ((int64_t)VT * 4);
+   int64_t cap  = (int64_t)g.sm_count * 8;
+   if (want < 1) want = 1;
+   return (int)(want < cap ? want : cap);
+}
+
+__global__ void __launch_bounds__(VT) k_fill(double *x, double v, int64_t n)
+{
+   for (int64_t i = blockIdx.x * (int64_t)VT + threadIdx.x; i < n; i += (int64_t)gridDim.x * VT) x[i] = v;
+}
+
+__global__ void __launch_bounds__(VT) k_copy(double *__restrict__ d, const double *__restrict__ s, int64_t n)
+{
+   for (int64_t i = blockIdx.x * (int64_t)VT + threadIdx.x; i < n; i += (int64_t)gridDim.x * VT) d[i] = s[i];
+}
+
+__global__ void __launch_bounds__(VT) k_axpy(double a, const double *__restrict__ x, double *__restrict__ y, int64_t n)
+{
+   for (int64_t i = blockIdx.x * (int64_t)VT + threadIdx.x; i < n; i += (int64_t)gridDim.x * VT)
+      y[i] = __dadd_rn(y[i], __dmul_rn(a, x[i]));
+}
+
+__global__ void __launch_bounds__(VT) k_scale(double a, double *x, int64_t n)
+{
+   for (int64_t i = blockIdx.x * (int64_t)VT + threadIdx.x; i < n; i += (int64_t)gridDim.x * VT) x[i] *= a;
+}
+
+// u = (w*f)/d : an l1-Jacobi sweep from a zero initial guess (bit-identical to the general
+// sweep with u_old = 0)
+__global__ void __launch_bounds__(VT) k_scaled_div(double *__restrict__ u, const double *__restrict__ f,
+                                                   const double *__restrict__ d, double w, int64_t n)
+{
+   for (int64_t i = blockIdx.x * (int64_t)VT + threadIdx.x; i < n; i += (int64_t)gridDim.x * VT)
+   {
+      double dd = d[i];
+      u[i]      = (dd != 0.0) ? __ddiv_rn(__dmul_rn(w, f[i]), dd) : 0.0;
+   }
+}
+
+// kind: 0 dot(x,y), 1 sum|x|, 2 max|x| (max uses the same tree with fmax)
+template <int KIND>
+__global__ void __launch_bounds__(VT) k_reduce(const double *__restrict__ x, const double *__restrict__ y,
+                                               int64_t n, double *partials, unsigned *ticket, int fin,
+                                               double *out, double *scal)
+{
+   __shared__ double sm[VT / 32];
+   __shared__ int    flag;
+   double            acc = 0.0;
+   for (int64_t i = blockIdx.x * (int64_t)VT + threadIdx.x; i < n; i += (int64_t)gridDim.x * VT)
+   {
+      if (KIND == 0) acc += x[i] * y[i];
+      else if (KIND == 1) acc += fabs(x[i]);
+      else acc = fmax(acc, fabs(x[i]));
+   }
+   if (KIND == 2)
+   {
+      // max-reduction: reuse the sum tree on a per-block basis through shared memory
+      int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+      for (int o = 16; o > 0; o >>= 1) acc = fmax(acc, __shfl_down_sync(0xffffffffu, acc, o));
+      if (lane == 0) sm[w] = acc;
+      __syncthreads();
+      if (w == 0)
+      {
+         acc = lane < VT / 32 ? sm[lane] : 0.0;
+         for (int o = 16; o > 0; o >>= 1) acc = fmax(acc, __shfl_down_sync(0xffffffffu, acc, o));
+      }
+      if (threadIdx.x == 0)
+      {
+         partials[blockIdx.x] = acc;
+         __threadfence();
+         unsigned t = atomicInc(ticket, gridDim.x - 1);
+         if (t == gridDim.x - 1)
+         {
+            __threadfence();
+            double m = 0.0;
+            for (unsigned b = 0; b < gridDim.x; b++) m = fmax(m, __ldcg(partials + b));
+            out[0] = m;
+         }
+      }
+      return;
+   }
+   double bs = block_sum<VT>(acc, sm);
+   __syncthreads();
+   grid_finish<VT>(bs, partials, ticket, fin, out, scal, sm, &flag);
+}
+
+// PCG: x += alpha p ; r -= alpha s ; i_prod = <r,r>   (one pass, 48 bytes per row)
+__global__ void __launch_bounds__(VT) k_pcg_xr(double *__restrict__ x, double *__restrict__ r,
+                                               const double *__restrict__ p, const double *__restrict__ s,
+                                               int64_t n, double *partials, unsigned *ticket, double *scal)
+{
+   __shared__ double sm[VT / 32];
+   __shared__ int    flag;
+   const double      alpha = scal[S_ALPHA];
+   double            acc   = 0.0;
+   for (int64_t i = blockIdx.x * (int64_t)VT + threadIdx.x; i < n; i += (int64_t)gridDim.x * VT)
+   {
+      x[i]      = __dadd_rn(x[i], __dmul_rn(alpha, p[i]));
+      double rn = __dadd_rn(r[i], -__dmul_rn(alpha, s[i]));
+      r[i]      = rn;
+      acc += rn * rn;
+   }
+   double bs = block_sum<VT>(acc, sm);
+   __syncthreads();
+   grid_finish<VT>(bs, partials, ticket, FIN_IPROD, nullptr, scal, sm, &flag);
+}
+
+// PCG: p = z + beta p
+__global__ void __launch_bounds__(VT) k_pcg_p(double *__restrict__ p, const double *__restrict__ z,
+                                              int64_t n, const double *__restrict__ scal)
+{
+   const double beta = scal[S_BETA];
+   for (int64_t i = blockIdx.x * (int64_t)VT + threadIdx.x; i < n; i += (int64_t)gridDim.x * VT)
+      p[i] = __dadd_rn(z[i], __dmul_rn(beta, p[i]));
+}
+
+// z = r and <r,r> (identity preconditioner)
+__global__ void __launch_bounds__(VT) k_copy_dot(double *__restrict__ z, const double *__restrict__ r,
+                                                 int64_t n, double *partials, unsigned *ticket, int fin,
+                                                 double *out, double *scal)
+{
+   __shared__ double sm[VT / 32];
+   __shared__ int    flag;
+   double            acc = 0.0;
+   for (int64_t i = blockIdx.x * (int64_t)VT + threadIdx.x; i < n; i += (int64_t)gridDim.x * VT)
+   {
+      double v = r[i];
+      z[i]     = v;
+      acc += v * v;
+   }
+   double bs = block_sum<VT>(acc, sm);
+   __syncthreads();
+   grid_finish<VT>(bs, partials, ticket, fin, out, scal, sm, &flag);
+}
+
+// counter-hash uniform values in [-1,1): splitmix64 of (seed, global index)
+__global__ void __launch_bounds__(VT) k_random(double *x, int64_t n, int64_t off, uint64_t seed)
+{
+   for (int64_t i = blockIdx.x * (int64_t)VT + threadIdx.x; i < n; i += (int64_t)gridDim.x * VT)
+   {
+      uint64_t z = (uint64_t)(i + off) + seed * 0x9E3779B97F4A7C15ull + 0x9E3779B97F4A7C15ull;
+      z          = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+      z          = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+      z          = z ^ (z >> 31);
+      x[i]       = (double)(z >> 11) * (2.0 / 9007199254740992.0) - 1.0;
+   }
+}
+
+int vec_fill(double *x, double v, int64_t n)
+{
+   if (n <= 0) return HDK_OK;
+   k_fill<<<vec_grid(n), VT, 0, g.stream>>>(x, v, n);
+   HDK_LAUNCH_CHECK();
+   return HDK_OK;
+}
+int vec_copy(double *d, const double *s, int64_t n)
+{
+   if (n <= 0 || d == s) return HDK_OK;
+   k_copy<<<vec_grid(n), VT, 0, g.stream>>>(d, s, n);
+   HDK_LAUNCH_CHECK();
+   return HDK_OK;
+}
+int vec_axpy(double a, const double *x, double *y, int64_t n)
+{
+   if (n <= 0) return HDK_OK;
+   k_axpy<<<vec_grid(n), VT, 0, g.stream>>>(a, x, y, n);
+   HDK_LAUNCH_CHECK();
+   return HDK_OK;
+}
+int vec_scale(double a, double *x, int64_t n)
+{
+   if (n <= 0) return HDK_OK;
+   k_scale<<<vec_grid(n), VT, 0, g.stream>>>(a, x, n);
+   HDK_LAUNCH_CHECK();
+   return HDK_OK;
+}
+int vec_scaled_div(double *u, const double *f, const double *d, double w, int64_t n)
+{
+   if (n <= 0) return HDK_OK;
+   k_scaled_div<<<vec_grid(n), VT, 0, g.stream>>>(u, f, d, w, n);
+   HDK_LAUNCH_CHECK();
+   return HDK_OK;
+}
+int vec_dot_dev(const double *x, const double *y, int64_t n, int fin, double *out_d)
+{
+   k_reduce<0><<<vec_grid(n), VT, 0, g.stream>>>(x, y, n, g.partials, g.counters, fin, out_d, g.dscal);
+   HDK_LAUNCH_CHECK();
+   return HDK_OK;
+}
+int vec_copy_dot(double *z, const double *r, int64_t n, int fin, double *out_d)
+{
+   k_copy_dot<<<vec_grid(n), VT, 0, g.stream>>>(z, r, n, g.partials, g.counters, fin, out_d, g.dscal);
+   HDK_LAUNCH_CHECK();
+   return HDK_OK;
+}
+int pcg_update_xr(double *x, double *r, const double *p, const double *s, int64_t n, double *scal)
+{
+   k_pcg_xr<<<vec_grid(n), VT, 0, g.stream>>>(x, r, p, s, n, g.partials, g.counters, scal);
+   HDK_LAUNCH_CHECK();
+   return HDK_OK;
+}
+int pcg_update_p(double *p, const double *z, int64_t n, const double *scal)
+{
+   if (n <= 0) return HDK_OK;
+   k_pcg_p<<<vec_grid(n), VT, 0, g.stream>>>(p, z, n, scal);
+   HDK_LAUNCH_CHECK();
+   return HDK_OK;
+}
+
+// device-resident partial result -> global result on the host (sum over ranks through NCCL)
+int vec_dot_host(const double *x, const double *y, int64_t n, double *out_h)
+{
+   HDK_TRY(vec_dot_dev(x, y, n, FIN_STORE, g.dscal + S_TMP0));
+   HDK_TRY(allreduce_dev(g.dscal + S_TMP0, 1));
+   HDK_CUDA(cudaMemcpyAsync(g.hscal + S_TMP0, g.dscal + S_TMP0, sizeof(double), cudaMemcpyDeviceToHost, g.stream));
+   HDK_CUDA(cudaStreamSynchronize(g.stream));
+   *out_h = g.hscal[S_TMP0];
+   return HDK_OK;
+}
+
+} // namespace hdk
+
+using namespace hdk;
+
+extern "C" {
+
+int hdk_vec_alloc(int64_t n, double **x_d)
+{
+   HDK_TRY(require_init());
+   HDK_TRY(dalloc(x_d, (size_t)(n > 0 ? n : 1) + 8));
+   return vec_fill(*x_d, 0.0, n + 8);
+}
+int hdk_vec_free(double *x_d) { return hdk_free_device(x_d); }
+int hdk_vec_h2d(double *x_d, const double *x_h, int64_t n) { return hdk_copy_h2d(x_d, x_h, sizeof(double) * (size_t)n); }
+int hdk_vec_d2h(double *x_h, const double *x_d, int64_t n) { return hdk_copy_d2h(x_h, x_d, sizeof(double) * (size_t)n); }
+int hdk_vec_fill(double *x_d, double v, int64_t n) { HDK_TRY(require_init()); return vec_fill(x_d, v, n); }
+int hdk_vec_copy(double *d, const double *s, int64_t n) { HDK_TRY(require_init()); return vec_copy(d, s, n); }
+int hdk_vec_axpy(double a, const double *x, double *y, int64_t n) { HDK_TRY(require_init()); return vec_axpy(a, x, y, n); }
+int hdk_vec_scale(double a, double *x, int64_t n) { HDK_TRY(require_init()); return vec_scale(a, x, n); }
+int hdk_vec_dot(const double *x, const double *y, int64_t n, double *r) { HDK_TRY(require_init()); return vec_dot_host(x, y, n, r); }
+
+int hdk_vec_norm(const double *x_d, int64_t n, int kind, double *result_h)
+{
+   HDK_TRY(require_init());
+   if (kind == 1)
+   {
+      double d;
+      HDK_TRY(vec_dot_host(x_d, x_d, n, &d));
+      *result_h = sqrt(d);
+      return HDK_OK;
+   }
+   if (kind == 0)
+      k_reduce<1><<<vec_grid(n), VT, 0, g.stream>>>(x_d, x_d, n, g.partials, g.counters, FIN_STORE, g.dscal + S_TMP0, g.dscal);
+   else
+      k_reduce<2><<<vec_grid(n), VT, 0, g.stream>>>(x_d, x_d, n, g.partials, g.counters, FIN_STORE, g.dscal + S_TMP0, g.dscal);
+   HDK_LAUNCH_CHECK();
+   if (kind == 0) HDK_TRY(allreduce_dev(g.dscal + S_TMP0, 1));
+   HDK_CUDA(cudaMemcpyAsync(g.hscal + S_TMP0, g.dscal + S_TMP0, sizeof(double), cudaMemcpyDeviceToHost, g.stream));
+   HDK_CUDA(cudaStreamSynchronize(g.stream));
+   *result_h = g.hscal[S_TMP0];
+   // Linf over ranks is not summed: the host layer takes the max of per-rank values
+   return HDK_OK;
+}
+
+int hdk_vec_random(double *x_d, int64_t n, int64_t off, int seed)
+{
+   HDK_TRY(require_init());
+   if (n <= 0) return HDK_OK;
+   k_random<<<vec_grid(n), VT, 0, g.stream>>>(x_d, n, off, (uint64_t)(uint32_t)seed);
+   HDK_LAUNCH_CHECK();
+   return HDK_OK;
+}
+
+} // extern "C"
