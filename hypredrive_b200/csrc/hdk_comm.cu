@@ -231,6 +231,27 @@ int hdk_comm_init(int rank, int nranks, const void *id128_h)
    return HDK_OK;
 }
 
+int hdk_comm_max_i64(int64_t local, int64_t *global)
+{
+   *global = local;
+   if (g.nranks <= 1) return HDK_OK;
+   std::vector<int64_t> all;
+   HDK_TRY(allgather_i64_host(local, all));
+   for (int64_t v : all) if (v > *global) *global = v;
+   return HDK_OK;
+}
+
+int hdk_comm_sum_i64(int64_t local, int64_t *global)
+{
+   *global = local;
+   if (g.nranks <= 1) return HDK_OK;
+   std::vector<int64_t> all;
+   HDK_TRY(allgather_i64_host(local, all));
+   *global = 0;
+   for (int64_t v : all) *global += v;
+   return HDK_OK;
+}
+
 int hdk_comm_rank(void) { return g.rank; }
 int hdk_comm_size(void) { return g.nranks; }
 

@@ -1,0 +1,2 @@
+/* HYPRE_utilities.h -- forwarding header of the hypre interface shim (see HYPRE.h). */
+#include "HYPRE.h"

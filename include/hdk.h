@@ -46,6 +46,9 @@ int hdk_comm_init(int rank, int nranks, const void *id128_h);
 int hdk_comm_rank(void);
 int hdk_comm_size(void);
 int hdk_comm_finalize(void);
+/* max / sum of one 64-bit integer over all ranks (control plane: global sizes) */
+int hdk_comm_max_i64(int64_t local, int64_t *global);
+int hdk_comm_sum_i64(int64_t local, int64_t *global);
 
 /* ---- device vectors (reference: HYPRE_IJVector / hypre_ParVector, src/internal/linsys.c:1412-1491) */
 int hdk_vec_alloc(int64_t n, double **x_d);

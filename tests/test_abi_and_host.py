@@ -1,0 +1,175 @@
+"""CPU tests: the C-ABI library loads and exports every declared symbol, and the host-side
+logic (YAML subset parser, option tables, presets, overrides, argument validation, error
+bitfield) behaves like the reference's.  No compute call is made without a GPU."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+from hypredrive_b200 import driver, hdk
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+INVALID_KEY, INVALID_VAL, MISSING_KEY, TREE_INVALID = 0x100, 0x200, 0x1000, 0x20
+INVALID_SOLVER, INVALID_PRECON, UNKNOWN_OBJ, NOT_INIT = 0x20000, 0x40000, 0x200000, 0x400000
+
+
+def _declared(header, prefix):
+    text = open(os.path.join(ROOT, "include", header)).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(%s\w+)\s*\(" % prefix, text)))
+
+
+def test_library_exports_every_declared_symbol():
+    L = hdk.lib()
+    names = _declared("HYPREDRV.h", "HYPREDRV_") + _declared("hdk.h", "hdk_") + _declared("HYPRE.h", "HYPRE_") + \
+        _declared("mpi.h", "MPI_")
+    names = [n for n in names if n not in ("HYPREDRV_SAFE_CALL", "HYPREDRV_SAFE_CALL_COMM", "HYPREDRV_SUCCESS")]
+    assert len(names) > 150
+    missing = [n for n in names if not hasattr(L, n)]
+    assert not missing, missing
+
+
+def test_scalar_widths():
+    L = hdk.lib()
+    assert L.HYPREDRV_SizeofBigInt() == 8 and L.HYPREDRV_SizeofReal() == 8 and L.HYPREDRV_SizeofInt() == 4
+
+
+def _obj():
+    driver.initialize()
+    h = C.c_void_p()
+    assert driver.api().HYPREDRV_Create(1, C.byref(h)) == 0
+    assert driver.api().HYPREDRV_SetLibraryMode(h) == 0
+    return h
+
+
+def _parse(h, text, *over):
+    argv = [text.encode()] + [o.encode() for o in over]
+    arr = (C.c_char_p * len(argv))(*argv)
+    code = driver.api().HYPREDRV_InputArgsParse(len(argv), arr, h)
+    driver.api().HYPREDRV_ErrorCodeClear()
+    return code
+
+
+def test_yaml_forms_accepted():
+    h = _obj()
+    good = [
+        "solver: pcg\npreconditioner: amg\n",
+        "solver: PCG\npreconditioner: AMG\n",                                   # values are lower-cased
+        "general:\n  use_millisec: on # comment\n\nsolver: gmres\npreconditioner:\n  preset: poisson\n",
+        "solver:\n  pcg:\n    max_iter: 50\n    relative_tol: 1.0e-8\npreconditioner:\n  amg:\n    coarsening:\n      type: pmis\n"
+        "      strong_th: 0.5\n    interpolation:\n      prolongation_type: extended+i\n      max_nnz_row: 4\n"
+        "    relaxation:\n      down_type: l1-jacobi\n      up_type: 18\n      coarse_type: ge\n",
+        "solver:\n    gmres:\n        krylov_dim: 20\npreconditioner: jacobi\n",  # 4-space base indent
+        "solver: pcg\npreconditioner:\n  amg: { print_level: 0, coarsening: { type: pmis, max_levels: 10 } }\n",
+        "solver: pcg\npreconditioner:\n  amg:\n    - print_level: 0\n      coarsening:\n        type: pmis\n",
+    ]
+    for text in good:
+        assert _parse(h, text) == 0, text
+    assert _parse(h, "solver: pcg\npreconditioner: amg\n", "--solver:pcg:relative_tol", "1.0e-2") == 0
+    assert _parse(h, "solver: pcg\npreconditioner: amg\n", "-a", "--solver:pcg:max_iter", "7", "--general:name", "run.yml") == 0
+    driver.api().HYPREDRV_Destroy(C.byref(h))
+
+
+def test_yaml_errors_set_the_reference_error_bits():
+    h = _obj()
+    cases = [
+        ("solver: pcg\n", MISSING_KEY),                                          # preconditioner is mandatory
+        ("solver: pcg\npreconditioner: amg\nbogus: 1\n", INVALID_KEY),
+        ("solver:\n  pcg:\n    max_itr: 5\npreconditioner: amg\n", INVALID_KEY),
+        ("solver:\n  pcg:\n    max_iter: many\npreconditioner: amg\n", INVALID_VAL),
+        ("solver: pcg\npreconditioner:\n  amg:\n    coarsening:\n      type: banana\n", INVALID_VAL),
+        ("solver: bicgstab\npreconditioner: amg\n", INVALID_SOLVER),
+        ("solver: pcg\npreconditioner: mgr\n", INVALID_PRECON),
+        ("solver: pcg\n\tpreconditioner: amg\n", 0x41),                           # tab indentation
+        ("solver:\n  pcg:\n   max_iter: 5\npreconditioner: amg\n", 0x4),          # inconsistent indent
+        ("solver:\n      pcg:\n        max_iter: 5\n  x: 1\npreconditioner: amg\n", 0x4 | 0x80 | INVALID_KEY),
+        ("solver pcg\npreconditioner: amg\n", 0x8),                               # missing divisor
+    ]
+    for text, bits in cases:
+        code = _parse(h, text)
+        assert code & bits, (text, hex(code))
+    assert _parse(h, "solver: pcg\npreconditioner: amg\n", "--solver:pcg:max_iter") & INVALID_VAL   # odd token count
+    driver.api().HYPREDRV_Destroy(C.byref(h))
+
+
+def test_guards_and_argument_validation():
+    L = driver.api()
+    h = _obj()
+    bogus = C.c_void_p(12345)
+    assert L.HYPREDRV_LinearSolverCreate(bogus) & UNKNOWN_OBJ
+    L.HYPREDRV_ErrorCodeClear()
+    assert L.HYPREDRV_LinearSolverCreate(h) & MISSING_KEY           # no input args parsed yet
+    L.HYPREDRV_ErrorCodeClear()
+    one = np.array([0], dtype=np.int64)
+    # tests/test_setmatrix_from_csr.c:249-350
+    assert L.HYPREDRV_LinearSystemSetMatrixFromCSR(h, 0, 4, None, None, None) & INVALID_VAL
+    L.HYPREDRV_ErrorCodeClear()
+    assert L.HYPREDRV_LinearSystemSetMatrixFromCSR(h, 5, 4, one.ctypes.data, None, None) & INVALID_VAL
+    L.HYPREDRV_ErrorCodeClear()
+    ip = np.array([0, 1], dtype=np.int64)
+    assert L.HYPREDRV_LinearSystemSetMatrixFromCSR(h, 0, 0, ip.ctypes.data, None, None) & INVALID_VAL
+    L.HYPREDRV_ErrorCodeClear()
+    neg = np.array([-1, 0], dtype=np.int64)
+    cj, va = np.array([0], dtype=np.int64), np.array([1.0])
+    assert L.HYPREDRV_LinearSystemSetMatrixFromCSR(h, 0, 0, neg.ctypes.data, cj.ctypes.data, va.ctypes.data) & INVALID_VAL
+    L.HYPREDRV_ErrorCodeClear()
+    bad = np.array([0, 2, 1, 3], dtype=np.int64)
+    c3, v3 = np.array([0, 1, 2], dtype=np.int64), np.ones(3)
+    assert L.HYPREDRV_LinearSystemSetMatrixFromCSR(h, 0, 2, bad.ctypes.data, c3.ctypes.data, v3.ctypes.data) & INVALID_VAL
+    L.HYPREDRV_ErrorCodeClear()
+    assert L.HYPREDRV_LinearSystemSetRHSFromArray(h, 0, 4, None) & INVALID_VAL
+    L.HYPREDRV_ErrorCodeClear()
+    assert L.HYPREDRV_LinearSystemSetRHSFromArray(h, 5, 4, va.ctypes.data) & INVALID_VAL
+    L.HYPREDRV_ErrorCodeClear()
+    assert L.HYPREDRV_LinearSystemSetRHSFromArray(h, 0, 0, va.ctypes.data) & INVALID_VAL    # RHS before matrix
+    L.HYPREDRV_ErrorCodeClear()
+    assert L.HYPREDRV_Destroy(C.byref(h)) == 0
+    assert L.HYPREDRV_Destroy(C.byref(h)) & UNKNOWN_OBJ                                      # already destroyed
+    L.HYPREDRV_ErrorCodeClear()
+
+
+def test_no_cpu_fallback_without_a_gpu():
+    if hdk.device_count() > 0:
+        pytest.skip("a GPU is visible")
+    ip = np.array([0, 1], dtype=np.int64)
+    cj, va = np.array([0], dtype=np.int64), np.array([3.0])
+    with pytest.raises(driver.HypreDriveError) as e:
+        with driver.HypreDrive() as drv:
+            drv.set_matrix_from_csr(ip, cj, va)
+    assert "no CUDA device" in str(e.value) and e.value.code & 0x01000000
+
+
+def test_ij_shim_containers():
+    L = hdk.lib()
+    A = C.c_void_p()
+    assert L.HYPRE_IJMatrixCreate(1, C.c_longlong(0), C.c_longlong(2), C.c_longlong(0), C.c_longlong(2), C.byref(A)) == 0
+    L.HYPRE_IJMatrixSetObjectType(A, 5555)
+    L.HYPRE_IJMatrixInitialize(A)
+    for r, (cols, vals) in enumerate([([0, 1], [2.0, -1.0]), ([0, 1, 2], [-1.0, 2.0, -1.0]), ([1, 2], [-1.0, 2.0])]):
+        n = C.c_int(len(cols))
+        row = C.c_longlong(r)
+        cc = (C.c_longlong * len(cols))(*cols)
+        vv = (C.c_double * len(vals))(*vals)
+        assert L.HYPRE_IJMatrixSetValues(A, 1, C.byref(n), C.byref(row), cc, vv) == 0
+    assert L.HYPRE_IJMatrixAssemble(A) == 0
+    lo, hi = C.c_longlong(), C.c_longlong()
+    L.HYPRE_IJMatrixGetLocalRange(A, C.byref(lo), C.byref(hi), None, None)
+    assert (lo.value, hi.value) == (0, 2)
+    v = C.c_void_p()
+    assert L.HYPRE_IJVectorCreate(1, C.c_longlong(0), C.c_longlong(2), C.byref(v)) == 0
+    L.HYPRE_IJVectorInitialize(v)
+    idx = (C.c_longlong * 3)(0, 1, 2)
+    val = (C.c_double * 3)(1.0, 2.0, 3.0)
+    L.HYPRE_IJVectorSetValues(v, 3, idx, val)
+    out = (C.c_double * 3)()
+    L.HYPRE_IJVectorGetValues(v, 3, idx, out)
+    assert list(out) == [1.0, 2.0, 3.0]
+    assert L.HYPRE_IJVectorDestroy(v) == 0 and L.HYPRE_IJMatrixDestroy(A) == 0
+
+
+def test_options_dict_to_yaml():
+    y = driver.normalize_options({"general": {"statistics": False}, "solver": {"pcg": {"max_iter": 10}},
+                                  "preconditioner": {"amg": {"print_level": 0}}})
+    assert "statistics: off" in y and "    max_iter: 10" in y and y.startswith("general:")

@@ -1,0 +1,98 @@
+"""CPU tests: the oracle against every golden number the reference tree holds for this path
+ and against independent scipy solves."""
+import numpy as np
+import scipy.sparse as sp
+import scipy.sparse.linalg as spla
+
+from oracle import oracle as O
+
+
+def test_park_miller_stream_known_answer():
+    # minimal-standard generator: seed 1 -> 10000th value 1043618065 (Park & Miller 1988)
+    r = O.rand_stream(1, 10000)
+    assert round(r[-1] * 2147483647) == 1043618065
+    r = O.rand_stream(2747, 3)
+    s = 2747
+    for i in range(3):
+        s = (16807 * s) % 2147483647
+        assert r[i] == s / 2147483647
+
+
+def test_golden_ex1_cpu_defaults():
+    # examples/refOutput/ex1.txt:17,27 -- 1000 rows / 6400 nnz, r0 3.16e+01, 6 iterations, 4.98e-08
+    A, _ = O.gen("lap7", 10, 10, 10)
+    assert A.shape == (1000, 1000) and A.nnz == 6400
+    b = np.ones(1000)
+    H = O.Hierarchy(A, O.default_params(False))          # CPU defaults: HMIS, ext+i, hybrid l1-GS 13/14
+    x, info = O.pcg(A, b, M=H, rel_tol=1e-6, max_iter=100)
+    assert f"{np.linalg.norm(b):.2e}" == "3.16e+01"
+    assert info["iters"] == 6
+    assert f"{np.linalg.norm(b - A @ x) / np.linalg.norm(b):.2e}" == "4.98e-08"
+
+
+def test_golden_laplacian_example_cpu_defaults():
+    # examples/refOutput/laplacian.txt:34-38 -- laplacian -n 10 10 10, r0 1.00e+01, 5 iterations, 6.12e-07
+    A, b = O.gen("lap7", 10, 10, 10)
+    H = O.Hierarchy(A, O.default_params(False))
+    x, info = O.pcg(A, b, M=H, rel_tol=1e-6, max_iter=100)
+    assert f"{np.linalg.norm(b):.2e}" == "1.00e+01"
+    assert info["iters"] == 5
+    assert f"{np.linalg.norm(b - A @ x) / np.linalg.norm(b):.2e}" == "6.12e-07"
+
+
+def test_known_answer_systems():
+    # tests/test_setmatrix_from_csr.c:395-421 and interfaces/python/tests/test_solve_serial.py:127-145,262-277
+    for diag, rhs, sol in (([3.0], [6.0], [2.0]), ([1.0, 2.0, 3.0, 4.0], [1.0, 4.0, 9.0, 16.0], [1, 2, 3, 4]),
+                           ([2.0, 4.0], [8.0, 16.0], [4.0, 4.0]), ([4.0, 8.0], [8.0, 16.0], [2.0, 2.0])):
+        A = sp.diags(diag).tocsr()
+        for gpu in (True, False):
+            H = O.Hierarchy(A, O.default_params(gpu))
+            x, info = O.pcg(A, np.array(rhs), M=H, rel_tol=1e-8)
+            assert info["converged"] and np.allclose(x, sol, atol=1e-6)
+
+
+def test_north_star_config_against_scipy():
+    for kind, dims, c in (("lap7", (16, 16, 16), (1, 1, 1)), ("lap27", (12, 12, 12), (1, 1, 0.01))):
+        A, b = O.gen(kind, *dims, c=c)
+        H = O.Hierarchy(A, O.default_params(True))
+        x, info = O.pcg(A, b, M=H, rel_tol=1e-10, max_iter=200)
+        xs = spla.spsolve(A.tocsc(), b)
+        assert info["converged"]
+        assert np.linalg.norm(x - xs) <= 1e-8 * np.linalg.norm(xs)
+
+
+def test_gmres_convdif_against_scipy():
+    A, b = O.gen("convdif", 24, 8, 8, c=(1e-3, 1.0, 0.1))
+    assert abs(A - A.T).max() > 0                         # nonsymmetric
+    H = O.Hierarchy(A, O.default_params(True))
+    x, info = O.gmres(A, b, M=H, rel_tol=1e-10, max_iter=100)
+    xs = spla.spsolve(A.tocsc(), b)
+    assert info["converged"] and np.linalg.norm(x - xs) <= 1e-8 * np.linalg.norm(xs)
+
+
+def test_looser_tolerance_fewer_iterations_and_determinism():
+    # interfaces/python/tests/test_solve_serial.py:83-126 on the 1-D Laplacian n = 32
+    n = 32
+    A = sp.diags([-1, 2, -1], [-1, 0, 1], shape=(n, n)).tocsr()
+    b = np.ones(n)
+    H = O.Hierarchy(A, O.default_params(True))
+    x1, i1 = O.pcg(A, b, M=H, rel_tol=1e-8)
+    x2, i2 = O.pcg(A, b, M=H, rel_tol=1e-8)
+    _, i3 = O.pcg(A, b, M=H, rel_tol=1e-2)
+    assert np.array_equal(x1, x2) and i1["iters"] == i2["iters"]
+    assert i3["iters"] < i1["iters"]
+
+
+def test_hierarchy_invariants():
+    A, _ = O.gen("lap7", 12, 12, 12)
+    H = O.Hierarchy(A, O.default_params(True))
+    for l in range(H.nlev - 1):
+        P, cf = H.P(l), H.cf(l)
+        Ac = H.A(l + 1)
+        assert P.shape == (H.A(l).shape[0], Ac.shape[0]) and (cf == 1).sum() == Ac.shape[0]
+        assert np.diff(P.indptr).max() <= 4                # max_nnz_row
+        G = (P.T @ H.A(l) @ P).tocsr()
+        assert abs(G - Ac).max() < 1e-12                   # Galerkin product
+        assert np.array_equal(Ac.indices[Ac.indptr[:-1]], np.arange(Ac.shape[0]))  # diagonal first
+        Pc = P[cf == 1]
+        assert np.allclose(Pc.data, 1.0) and Pc.nnz == Ac.shape[0]
