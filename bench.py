@@ -227,6 +227,9 @@ def ours(args):
         one_solve()
     barrier()
     sampler = ClockSampler(local) if rank == 0 else None
+    prof = os.environ.get("HDK_PROFILE_RANGE") == "1"     # ncu --profile-from-start off
+    if prof:
+        hdk.lib().hdk_profiler_range(1)
     hdk.launch_count_reset()
     wall0 = time.time()
     solve_s, iters = 0.0, 0
@@ -236,6 +239,8 @@ def ours(args):
         solve_s += s
     barrier()
     wall = time.time() - wall0
+    if prof:
+        hdk.lib().hdk_profiler_range(0)
     launches = hdk.launch_count_reset()
     if dist is not None:
         import torch

@@ -147,3 +147,13 @@ int hdk_copy_h2d(void *dst_d, const void *src_h, size_t bytes)
 }
 
 } // extern "C"
+
+// cudaProfilerStart/Stop bracket for `ncu --profile-from-start off` (bench.py HDK_PROFILE_RANGE=1)
+#include <cuda_profiler_api.h>
+extern "C" int hdk_profiler_range(int start)
+{
+   HDK_TRY(hdk::require_init());
+   cudaStreamSynchronize(hdk::g.stream);
+   if (start) cudaProfilerStart(); else cudaProfilerStop();
+   return HDK_OK;
+}

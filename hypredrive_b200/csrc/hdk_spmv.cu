@@ -42,42 +42,60 @@ __device__ __forceinline__ double2 ld_double2(const double *p)
    return __ldg(reinterpret_cast<const double2 *>(p));
 }
 
+// per-row operands of the epilogue; the first PF rounds are prefetched before the CTA barrier
+// so that phase 2 does not pay a second full DRAM round trip
+struct RowOps
+{
+   int    s, e;
+   double b, d, xo, yo, dv;
+};
+
+template <int MODE, bool DOT>
+__device__ __forceinline__ void row_load(const SpmvDev &a, int r, int ka, RowOps &o)
+{
+   o.s = __ldg(a.rowptr + r) - ka;
+   o.e = __ldg(a.rowptr + r + 1) - ka;
+   if (MODE == SPMV_RESIDUAL || MODE == SPMV_JACOBI || MODE == SPMV_JACOBI_R) o.b = a.b[r];
+   if (MODE == SPMV_JACOBI || MODE == SPMV_JACOBI_R) o.d = a.d[r];
+   if (MODE == SPMV_JACOBI) o.xo = a.x[r];
+   if (MODE == SPMV_ADD || MODE == SPMV_AXPBY) o.yo = a.y[r];
+   if (DOT) o.dv = a.dotv[r];
+}
+
 template <int MODE>
-__device__ __forceinline__ double row_epilogue(const SpmvDev &a, int r, const double *prod, int s, int e)
+__device__ __forceinline__ double row_epilogue(const SpmvDev &a, const RowOps &o, const double *prod)
 {
    double acc;
    if (MODE == SPMV_SET || MODE == SPMV_AXPBY)
    {
       acc = 0.0;
-      for (int k = s; k < e; k++) acc = __dadd_rn(acc, prod[k]);
+      for (int k = o.s; k < o.e; k++) acc = __dadd_rn(acc, prod[k]);
       if (MODE == SPMV_AXPBY)
          acc = (a.beta == 0.0) ? __dmul_rn(a.alpha, acc)
-                               : __dadd_rn(__dmul_rn(a.alpha, acc), __dmul_rn(a.beta, a.y[r]));
+                               : __dadd_rn(__dmul_rn(a.alpha, acc), __dmul_rn(a.beta, o.yo));
       return acc;
    }
    if (MODE == SPMV_ADD)
    {
-      acc = a.y[r];
-      for (int k = s; k < e; k++) acc = __dadd_rn(acc, prod[k]);
+      acc = o.yo;
+      for (int k = o.s; k < o.e; k++) acc = __dadd_rn(acc, prod[k]);
       return acc;
    }
    // residual-type modes: res = b; res -= a_ij x_j in CSR order
-   acc = a.b[r];
-   for (int k = s; k < e; k++) acc = __dadd_rn(acc, -prod[k]);
+   acc = o.b;
+   for (int k = o.s; k < o.e; k++) acc = __dadd_rn(acc, -prod[k]);
    if (MODE == SPMV_RESIDUAL) return acc;
-   double dd = a.d[r];
    if (MODE == SPMV_JACOBI)
-   {
-      double xo = a.x[r];
-      return (dd != 0.0) ? __dadd_rn(xo, __ddiv_rn(__dmul_rn(a.w, acc), dd)) : xo;
-   }
+      return (o.d != 0.0) ? __dadd_rn(o.xo, __ddiv_rn(__dmul_rn(a.w, acc), o.d)) : o.xo;
    /* SPMV_JACOBI_R */
-   return (dd != 0.0) ? __ddiv_rn(__dmul_rn(a.w, acc), dd) : 0.0;
+   return (o.d != 0.0) ? __ddiv_rn(__dmul_rn(a.w, acc), o.d) : 0.0;
 }
 
 template <int MODE, bool DOT>
 __global__ void __launch_bounds__(ST) k_spmv_stream(SpmvDev a)
 {
+   constexpr int NIT = S_CAP / (4 * ST); // phase-1 steps per thread
+   constexpr int PF  = 2;                // prefetched phase-2 rounds
    __shared__ __align__(16) double prod[S_CAP];
    __shared__ double red[ST / 32];
    __shared__ int    flag;
@@ -86,13 +104,13 @@ __global__ void __launch_bounds__(ST) k_spmv_stream(SpmvDev a)
    double    dacc = 0.0;
    if (r0 < r1)
    {
-      const int k0 = a.rowptr[r0], k1 = a.rowptr[r1];
+      const int k0 = __ldg(a.rowptr + r0), k1 = __ldg(a.rowptr + r1);
       const int ka = k0 & ~3;
-      // phase 1: stream 4 non-zeros per thread per step, gather x, park products
-      int4    c[S_CAP / (4 * ST)];
-      double2 v0[S_CAP / (4 * ST)], v1[S_CAP / (4 * ST)];
+      // phase 1: stream 4 non-zeros per thread per step (128-bit loads) ...
+      int4    c[NIT];
+      double2 v0[NIT], v1[NIT];
 #pragma unroll
-      for (int it = 0; it < S_CAP / (4 * ST); ++it)
+      for (int it = 0; it < NIT; ++it)
       {
          int k = ka + (it * ST + tid) * 4;
          if (k < k1)
@@ -102,8 +120,17 @@ __global__ void __launch_bounds__(ST) k_spmv_stream(SpmvDev a)
             v1[it] = ld_double2(a.val + k + 2);
          }
       }
+      // ... issue the per-row operand loads of phase 2 while those are in flight ...
+      RowOps ro[PF];
 #pragma unroll
-      for (int it = 0; it < S_CAP / (4 * ST); ++it)
+      for (int j = 0; j < PF; ++j)
+      {
+         int r = r0 + tid + j * ST;
+         if (r < r1) row_load<MODE, DOT>(a, r, ka, ro[j]);
+      }
+      // ... gather x and park the products in shared memory
+#pragma unroll
+      for (int it = 0; it < NIT; ++it)
       {
          int k = ka + (it * ST + tid) * 4;
          if (k < k1)
@@ -119,12 +146,24 @@ __global__ void __launch_bounds__(ST) k_spmv_stream(SpmvDev a)
       }
       __syncthreads();
       // phase 2: one thread per row, sequential sum in CSR order
-      for (int r = r0 + tid; r < r1; r += ST)
+#pragma unroll
+      for (int j = 0; j < PF; ++j)
       {
-         int    s = a.rowptr[r] - ka, e = a.rowptr[r + 1] - ka;
-         double yn = row_epilogue<MODE>(a, r, prod, s, e);
+         int r = r0 + tid + j * ST;
+         if (r < r1)
+         {
+            double yn = row_epilogue<MODE>(a, ro[j], prod);
+            a.y[r]    = yn;
+            if (DOT) dacc += ro[j].dv * yn;
+         }
+      }
+      for (int r = r0 + tid + PF * ST; r < r1; r += ST)
+      {
+         RowOps o;
+         row_load<MODE, DOT>(a, r, ka, o);
+         double yn = row_epilogue<MODE>(a, o, prod);
          a.y[r]    = yn;
-         if (DOT) dacc += a.dotv[r] * yn;
+         if (DOT) dacc += o.dv * yn;
       }
    }
    if (DOT)

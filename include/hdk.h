@@ -182,6 +182,8 @@ int hdk_time_kernel(const hdk_csr *A, hdk_amg *M, int kernel, int reps, double *
                     double *algorithmic_bytes);
 /* number of kernel launches issued by this library since the last call (and reset) */
 int64_t hdk_launch_count_reset(void);
+/* cudaProfilerStart (1) / cudaProfilerStop (0) for `ncu --profile-from-start off` */
+int hdk_profiler_range(int start);
 
 #ifdef __cplusplus
 }
