@@ -93,6 +93,7 @@ struct DevCSR
    int     kind = 0;          // 0 stream, 1 vector (warp per row)
    int     max_row = 0;
    double  avg_row = 0.0;
+   int     tgt = 0, cap = 0;  // stream kernel: non-zeros per CTA, shared-memory entries per stage
    int     nblk = 0;          // stream kernel: number of nnz-balanced row blocks
    int    *blk_row = nullptr; // nblk+1 first rows
    bool    owns = true;

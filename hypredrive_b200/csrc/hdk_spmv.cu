@@ -13,6 +13,7 @@
 //    results are bit-identical to the CPU restatement.
 //  * VECTOR (long rows): one warp per row, 128-bit loads along the row, shuffle reduction.
 #include "hdk_internal.cuh"
+#include <stdlib.h>
 
 namespace hdk {
 
@@ -174,6 +175,165 @@ __global__ void __launch_bounds__(ST) k_spmv_stream(SpmvDev a)
    }
 }
 
+// ---------------------------------------------------------------------------------------
+// TMA variant of the stream kernel (default): persistent CTAs, two shared-memory stages.
+// One elected thread issues 1-D bulk copies (cp.async.bulk -> UBLKCP) of the block's
+// contiguous val / col ranges, completion is tracked by an mbarrier; the copies of block
+// i+1 are in flight while block i gathers x, multiplies in place and reduces its rows.
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
+{
+   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes)
+{
+   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_1d(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar)
+{
+   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
+{
+   asm volatile("{\n"
+                ".reg .pred P1;\n"
+                "LAB_WAIT:\n"
+                "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+                "@P1 bra DONE;\n"
+                "bra LAB_WAIT;\n"
+                "DONE:\n"
+                "}" ::"r"(bar), "r"(parity) : "memory");
+}
+
+struct BlkMeta { int r0, r1, k0, k1; };
+__device__ __forceinline__ BlkMeta blk_meta(const SpmvDev &a, int b)
+{
+   BlkMeta m;
+   m.r0 = __ldg(a.blk_row + b);
+   m.r1 = __ldg(a.blk_row + b + 1);
+   m.k0 = __ldg(a.rowptr + m.r0);
+   m.k1 = __ldg(a.rowptr + m.r1);
+   return m;
+}
+
+template <int MODE, bool DOT>
+__global__ void __launch_bounds__(ST, 4) k_spmv_tma(SpmvDev a, int nblk, int cap)
+{
+   constexpr int PF = 2;
+   extern __shared__ __align__(128) unsigned char smem_raw[];
+   __shared__ double red[ST / 32];
+   __shared__ int    flag;
+   double *vbuf = reinterpret_cast<double *>(smem_raw + 128);
+   int    *cbuf = reinterpret_cast<int *>(smem_raw + 128 + (size_t)2 * cap * sizeof(double));
+   const uint32_t bar0 = smem_u32(smem_raw), bar1 = bar0 + 8;
+   const int tid = threadIdx.x, G = gridDim.x;
+   if (tid == 0)
+   {
+      mbar_init(bar0, 1);
+      mbar_init(bar1, 1);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+   }
+   __syncthreads();
+   int      b = blockIdx.x, nb = b + G;
+   int      stage = 0;
+   uint32_t ph[2] = {0u, 0u};
+   double   dacc = 0.0;
+   BlkMeta  cur, nxt;
+   cur = nxt = BlkMeta{0, 0, 0, 0};
+   if (b < nblk)
+   {
+      cur = blk_meta(a, b);
+      int ka = cur.k0 & ~3, len4 = (cur.k1 - ka + 3) & ~3;
+      if (tid == 0 && len4 > 0)
+      {
+         mbar_expect_tx(bar0, (uint32_t)len4 * 12u);
+         tma_load_1d(smem_u32(vbuf), a.val + ka, (uint32_t)len4 * 8u, bar0);
+         tma_load_1d(smem_u32(cbuf), a.col + ka, (uint32_t)len4 * 4u, bar0);
+      }
+   }
+   if (nb < nblk) nxt = blk_meta(a, nb);
+   while (b < nblk)
+   {
+      // 1. bulk copies of the next block into the other stage (its readers finished before the
+      //    barrier that closed the previous iteration)
+      if (nb < nblk && tid == 0)
+      {
+         int ka = nxt.k0 & ~3, len4 = (nxt.k1 - ka + 3) & ~3;
+         if (len4 > 0)
+         {
+            const uint32_t bar = stage ? bar0 : bar1;
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            mbar_expect_tx(bar, (uint32_t)len4 * 12u);
+            tma_load_1d(smem_u32(vbuf + (size_t)(stage ^ 1) * cap), a.val + ka, (uint32_t)len4 * 8u, bar);
+            tma_load_1d(smem_u32(cbuf + (size_t)(stage ^ 1) * cap), a.col + ka, (uint32_t)len4 * 4u, bar);
+         }
+      }
+      // 2. metadata two blocks ahead, 3. per-row operands of this block (plain global loads)
+      const int nnb = nb + G;
+      BlkMeta   nn  = BlkMeta{0, 0, 0, 0};
+      if (nnb < nblk) nn = blk_meta(a, nnb);
+      const int ka = cur.k0 & ~3, len = cur.k1 - ka;
+      RowOps    ro[PF];
+#pragma unroll
+      for (int j = 0; j < PF; ++j)
+      {
+         int r = cur.r0 + tid + j * ST;
+         if (r < cur.r1) row_load<MODE, DOT>(a, r, ka, ro[j]);
+      }
+      // 4. wait for this block's val / col
+      double *prod = vbuf + (size_t)stage * cap;
+      const int *cs = cbuf + (size_t)stage * cap;
+      if (len > 0)
+      {
+         mbar_wait(stage ? bar1 : bar0, ph[stage]);
+         ph[stage] ^= 1u;
+      }
+      // 5. gather x and multiply in place
+      for (int k = tid * 4; k < len; k += ST * 4)
+      {
+         int4    c  = *reinterpret_cast<const int4 *>(cs + k);
+         double2 v0 = *reinterpret_cast<const double2 *>(prod + k);
+         double2 v1 = *reinterpret_cast<const double2 *>(prod + k + 2);
+         double  x0 = __ldg(a.x + c.x), x1 = __ldg(a.x + c.y), x2 = __ldg(a.x + c.z), x3 = __ldg(a.x + c.w);
+         v0.x = __dmul_rn(v0.x, x0); v0.y = __dmul_rn(v0.y, x1);
+         v1.x = __dmul_rn(v1.x, x2); v1.y = __dmul_rn(v1.y, x3);
+         *reinterpret_cast<double2 *>(prod + k)     = v0;
+         *reinterpret_cast<double2 *>(prod + k + 2) = v1;
+      }
+      __syncthreads();
+      // 6. one thread per row, sequential sum in CSR order, fused epilogue
+#pragma unroll
+      for (int j = 0; j < PF; ++j)
+      {
+         int r = cur.r0 + tid + j * ST;
+         if (r < cur.r1)
+         {
+            double yn = row_epilogue<MODE>(a, ro[j], prod);
+            a.y[r]    = yn;
+            if (DOT) dacc += ro[j].dv * yn;
+         }
+      }
+      for (int r = cur.r0 + tid + PF * ST; r < cur.r1; r += ST)
+      {
+         RowOps o;
+         row_load<MODE, DOT>(a, r, ka, o);
+         double yn = row_epilogue<MODE>(a, o, prod);
+         a.y[r]    = yn;
+         if (DOT) dacc += o.dv * yn;
+      }
+      __syncthreads();
+      b = nb; nb = nnb; cur = nxt; nxt = nn; stage ^= 1;
+   }
+   if (DOT)
+   {
+      double bs = block_sum<ST>(dacc, red);
+      __syncthreads();
+      grid_finish<ST>(bs, a.partials, a.ticket, a.fin, a.fin_out, a.scal, red, &flag);
+   }
+}
+
 // one warp per row; lanes stride the row with scalar loads (rows here are long, so each warp
 // reads whole 128-byte lines).  Summation order differs from the oracle (tolerance parity).
 template <int MODE, bool DOT>
@@ -219,10 +379,41 @@ __global__ void __launch_bounds__(ST) k_spmv_vector(SpmvDev a)
    }
 }
 
+static int g_spmv_impl = -1; // 0 = LDG stream kernel, 1 = TMA stream kernel (default)
+
+template <int MODE, bool DOT>
+static int launch_tma(const DevCSR &A, const SpmvDev &d)
+{
+   static int    occ = 0;
+   static size_t occ_smem = 0;
+   size_t        smem = 128 + (size_t)2 * A.cap * 12;
+   if (smem != occ_smem)
+   {
+      HDK_CUDA(cudaFuncSetAttribute(k_spmv_tma<MODE, DOT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      HDK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_spmv_tma<MODE, DOT>, ST, smem));
+      if (occ < 1) occ = 1;
+      occ_smem = smem;
+   }
+   int grid = g.sm_count * occ;
+   if (grid > A.nblk) grid = A.nblk;
+   k_spmv_tma<MODE, DOT><<<grid, ST, smem, g.stream>>>(d, A.nblk, A.cap);
+   return HDK_OK;
+}
+
 template <int MODE>
 static int launch_mode(const DevCSR &A, const SpmvDev &d, bool dot)
 {
-   if (A.kind == 0)
+   if (g_spmv_impl < 0)
+   {
+      const char *e = getenv("HDK_SPMV_IMPL");
+      g_spmv_impl   = (e && !strcmp(e, "ldg")) ? 0 : 1;
+   }
+   if (A.kind == 0 && g_spmv_impl == 1)
+   {
+      if (dot) HDK_TRY((launch_tma<MODE, true>(A, d)));
+      else HDK_TRY((launch_tma<MODE, false>(A, d)));
+   }
+   else if (A.kind == 0)
    {
       if (dot) k_spmv_stream<MODE, true><<<A.nblk, ST, 0, g.stream>>>(d);
       else k_spmv_stream<MODE, false><<<A.nblk, ST, 0, g.stream>>>(d);
@@ -278,12 +469,12 @@ __global__ void k_row_stats(const int *rowptr, int nrows, int *max_row)
    if ((threadIdx.x & 31) == 0 && m > 0) atomicMax(max_row, m);
 }
 
-__global__ void k_blk_rows(const int *rowptr, int nrows, int nblk, int *blk_row)
+__global__ void k_blk_rows(const int *rowptr, int nrows, int nblk, int tgt, int *blk_row)
 {
    int b = blockIdx.x * blockDim.x + threadIdx.x;
    if (b > nblk) return;
    if (b == nblk) { blk_row[b] = nrows; return; }
-   int target = b * S_TGT;
+   int target = b * tgt;
    int lo = 0, hi = nrows; // first i in [0,nrows] with rowptr[i] >= target
    while (lo < hi)
    {
@@ -312,9 +503,15 @@ int csr_analyze(DevCSR &A)
    A.kind    = (hmax <= S_MAXR) ? 0 : 1;
    if (A.kind == 0)
    {
-      A.nblk = A.nnz / S_TGT + 1;
+      // non-zeros per CTA: about one row per thread (256 rows), 64-aligned, within [1024, 3072]
+      int tgt = ((int)(A.avg_row * 256.0) / 64) * 64;
+      if (tgt < 1024) tgt = 1024;
+      if (tgt > S_TGT) tgt = S_TGT;
+      A.tgt  = tgt;
+      A.cap  = (tgt + hmax + 8 + 3) & ~3;   // shared-memory entries per stage (<= S_CAP)
+      A.nblk = A.nnz / tgt + 1;
       HDK_TRY(dalloc(&A.blk_row, (size_t)A.nblk + 1));
-      k_blk_rows<<<cdiv(A.nblk + 1, 256), 256, 0, g.stream>>>(A.rowptr, A.nrows, A.nblk, A.blk_row);
+      k_blk_rows<<<cdiv(A.nblk + 1, 256), 256, 0, g.stream>>>(A.rowptr, A.nrows, A.nblk, tgt, A.blk_row);
       HDK_LAUNCH_CHECK();
    }
    return HDK_OK;
