@@ -6,21 +6,25 @@
 // src/internal/solver.c:614 (every Krylov iteration) and the V-cycle behind solver.c:314-329.
 //
 // Kernel choice by measured row-length statistics (csr_analyze):
-//  * STREAM (short rows, max_row <= 1024): each CTA owns ~3072 consecutive non-zeros.  All
-//    256 threads stream col/val with 128-bit loads (perfectly coalesced regardless of row
-//    boundaries), gather x, and park the products in shared memory; then one thread per row
-//    adds its products sequentially in CSR order.  The per-row order equals the oracle's, so
-//    results are bit-identical to the CPU restatement.
-//  * VECTOR (long rows): one warp per row, 128-bit loads along the row, shuffle reduction.
+//  * STREAM (max_row <= 1024): persistent CTAs walk nnz-balanced row blocks (about one row per
+//    thread).  One elected thread issues 1-D TMA bulk copies (cp.async.bulk -> UBLKCP) of the
+//    block's contiguous val / col ranges into one of two shared-memory stages, tracked by an
+//    mbarrier; while block i+1 is in flight, block i is consumed one row per thread: col/val
+//    come from shared memory (conflict-free for odd row lengths), x is gathered through L1 --
+//    coalesced across the rows of a warp on stencil matrices -- and the row is accumulated
+//    sequentially in CSR order with separately rounded multiply and add, so results are
+//    bit-identical to the CPU oracle.  HBM sees only perfectly contiguous bulk reads.
+//  * VECTOR (longer rows): one warp per row, shuffle reduction.
 #include "hdk_internal.cuh"
 #include <stdlib.h>
+#include <map>
 
 namespace hdk {
 
-constexpr int ST     = 256;        // threads per CTA
-constexpr int S_TGT  = 3072;       // target non-zeros per CTA
-constexpr int S_CAP  = 4096;       // product slots in shared memory (32 KB)
-constexpr int S_MAXR = S_CAP - S_TGT; // longest row the stream kernel accepts (1024)
+constexpr int ST       = 256;   // threads per CTA
+constexpr int S_TGT_LO = 1024;  // non-zeros per block: bounds
+constexpr int S_TGT_HI = 8192;
+constexpr int S_MAXR   = 1024;  // longest row the stream kernel accepts
 
 struct SpmvDev
 {
@@ -34,153 +38,7 @@ struct SpmvDev
    unsigned     *ticket;
 };
 
-__device__ __forceinline__ int4 ld_int4(const int *p)
-{
-   return __ldg(reinterpret_cast<const int4 *>(p));
-}
-__device__ __forceinline__ double2 ld_double2(const double *p)
-{
-   return __ldg(reinterpret_cast<const double2 *>(p));
-}
-
-// per-row operands of the epilogue; the first PF rounds are prefetched before the CTA barrier
-// so that phase 2 does not pay a second full DRAM round trip
-struct RowOps
-{
-   int    s, e;
-   double b, d, xo, yo, dv;
-};
-
-template <int MODE, bool DOT>
-__device__ __forceinline__ void row_load(const SpmvDev &a, int r, int ka, RowOps &o)
-{
-   o.s = __ldg(a.rowptr + r) - ka;
-   o.e = __ldg(a.rowptr + r + 1) - ka;
-   if (MODE == SPMV_RESIDUAL || MODE == SPMV_JACOBI || MODE == SPMV_JACOBI_R) o.b = a.b[r];
-   if (MODE == SPMV_JACOBI || MODE == SPMV_JACOBI_R) o.d = a.d[r];
-   if (MODE == SPMV_JACOBI) o.xo = a.x[r];
-   if (MODE == SPMV_ADD || MODE == SPMV_AXPBY) o.yo = a.y[r];
-   if (DOT) o.dv = a.dotv[r];
-}
-
-template <int MODE>
-__device__ __forceinline__ double row_epilogue(const SpmvDev &a, const RowOps &o, const double *prod)
-{
-   double acc;
-   if (MODE == SPMV_SET || MODE == SPMV_AXPBY)
-   {
-      acc = 0.0;
-      for (int k = o.s; k < o.e; k++) acc = __dadd_rn(acc, prod[k]);
-      if (MODE == SPMV_AXPBY)
-         acc = (a.beta == 0.0) ? __dmul_rn(a.alpha, acc)
-                               : __dadd_rn(__dmul_rn(a.alpha, acc), __dmul_rn(a.beta, o.yo));
-      return acc;
-   }
-   if (MODE == SPMV_ADD)
-   {
-      acc = o.yo;
-      for (int k = o.s; k < o.e; k++) acc = __dadd_rn(acc, prod[k]);
-      return acc;
-   }
-   // residual-type modes: res = b; res -= a_ij x_j in CSR order
-   acc = o.b;
-   for (int k = o.s; k < o.e; k++) acc = __dadd_rn(acc, -prod[k]);
-   if (MODE == SPMV_RESIDUAL) return acc;
-   if (MODE == SPMV_JACOBI)
-      return (o.d != 0.0) ? __dadd_rn(o.xo, __ddiv_rn(__dmul_rn(a.w, acc), o.d)) : o.xo;
-   /* SPMV_JACOBI_R */
-   return (o.d != 0.0) ? __ddiv_rn(__dmul_rn(a.w, acc), o.d) : 0.0;
-}
-
-template <int MODE, bool DOT>
-__global__ void __launch_bounds__(ST) k_spmv_stream(SpmvDev a)
-{
-   constexpr int NIT = S_CAP / (4 * ST); // phase-1 steps per thread
-   constexpr int PF  = 2;                // prefetched phase-2 rounds
-   __shared__ __align__(16) double prod[S_CAP];
-   __shared__ double red[ST / 32];
-   __shared__ int    flag;
-   const int tid = threadIdx.x;
-   const int r0 = a.blk_row[blockIdx.x], r1 = a.blk_row[blockIdx.x + 1];
-   double    dacc = 0.0;
-   if (r0 < r1)
-   {
-      const int k0 = __ldg(a.rowptr + r0), k1 = __ldg(a.rowptr + r1);
-      const int ka = k0 & ~3;
-      // phase 1: stream 4 non-zeros per thread per step (128-bit loads) ...
-      int4    c[NIT];
-      double2 v0[NIT], v1[NIT];
-#pragma unroll
-      for (int it = 0; it < NIT; ++it)
-      {
-         int k = ka + (it * ST + tid) * 4;
-         if (k < k1)
-         {
-            c[it]  = ld_int4(a.col + k);
-            v0[it] = ld_double2(a.val + k);
-            v1[it] = ld_double2(a.val + k + 2);
-         }
-      }
-      // ... issue the per-row operand loads of phase 2 while those are in flight ...
-      RowOps ro[PF];
-#pragma unroll
-      for (int j = 0; j < PF; ++j)
-      {
-         int r = r0 + tid + j * ST;
-         if (r < r1) row_load<MODE, DOT>(a, r, ka, ro[j]);
-      }
-      // ... gather x and park the products in shared memory
-#pragma unroll
-      for (int it = 0; it < NIT; ++it)
-      {
-         int k = ka + (it * ST + tid) * 4;
-         if (k < k1)
-         {
-            double x0 = __ldg(a.x + c[it].x), x1 = __ldg(a.x + c[it].y);
-            double x2 = __ldg(a.x + c[it].z), x3 = __ldg(a.x + c[it].w);
-            double2 p0, p1;
-            p0.x = __dmul_rn(v0[it].x, x0); p0.y = __dmul_rn(v0[it].y, x1);
-            p1.x = __dmul_rn(v1[it].x, x2); p1.y = __dmul_rn(v1[it].y, x3);
-            *reinterpret_cast<double2 *>(prod + (k - ka))     = p0;
-            *reinterpret_cast<double2 *>(prod + (k - ka) + 2) = p1;
-         }
-      }
-      __syncthreads();
-      // phase 2: one thread per row, sequential sum in CSR order
-#pragma unroll
-      for (int j = 0; j < PF; ++j)
-      {
-         int r = r0 + tid + j * ST;
-         if (r < r1)
-         {
-            double yn = row_epilogue<MODE>(a, ro[j], prod);
-            a.y[r]    = yn;
-            if (DOT) dacc += ro[j].dv * yn;
-         }
-      }
-      for (int r = r0 + tid + PF * ST; r < r1; r += ST)
-      {
-         RowOps o;
-         row_load<MODE, DOT>(a, r, ka, o);
-         double yn = row_epilogue<MODE>(a, o, prod);
-         a.y[r]    = yn;
-         if (DOT) dacc += o.dv * yn;
-      }
-   }
-   if (DOT)
-   {
-      double bs = block_sum<ST>(dacc, red);
-      __syncthreads();
-      grid_finish<ST>(bs, a.partials, a.ticket, a.fin, a.fin_out, a.scal, red, &flag);
-   }
-}
-
-// ---------------------------------------------------------------------------------------
-// TMA variant of the stream kernel (default): persistent CTAs, two shared-memory stages.
-// One elected thread issues 1-D bulk copies (cp.async.bulk -> UBLKCP) of the block's
-// contiguous val / col ranges, completion is tracked by an mbarrier; the copies of block
-// i+1 are in flight while block i gathers x, multiplies in place and reduces its rows.
-// ---------------------------------------------------------------------------------------
+// ---- PTX helpers: mbarrier + 1-D bulk tensor-memory-accelerator copies -------------------
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
 {
@@ -218,10 +76,65 @@ __device__ __forceinline__ BlkMeta blk_meta(const SpmvDev &a, int b)
    return m;
 }
 
+// per-row operands of the epilogue, loaded before the wait on the bulk copy
+struct RowOps
+{
+   int    s, e;
+   double b, d, xo, yo, dv;
+};
+
+template <int MODE, bool DOT>
+__device__ __forceinline__ void row_load(const SpmvDev &a, int r, int ka, RowOps &o)
+{
+   o.s = __ldg(a.rowptr + r) - ka;
+   o.e = __ldg(a.rowptr + r + 1) - ka;
+   if (MODE == SPMV_RESIDUAL || MODE == SPMV_JACOBI || MODE == SPMV_JACOBI_R) o.b = a.b[r];
+   if (MODE == SPMV_JACOBI || MODE == SPMV_JACOBI_R) o.d = a.d[r];
+   if (MODE == SPMV_JACOBI) o.xo = a.x[r];
+   if (MODE == SPMV_ADD || MODE == SPMV_AXPBY) o.yo = a.y[r];
+   if (DOT) o.dv = a.dotv[r];
+}
+
+// one row: sequential accumulation in CSR order from the staged val / col, fused epilogue
+template <int MODE>
+__device__ __forceinline__ double row_compute(const SpmvDev &a, const RowOps &o, const double *vs, const int *cs)
+{
+   constexpr bool SUB = (MODE == SPMV_RESIDUAL || MODE == SPMV_JACOBI || MODE == SPMV_JACOBI_R);
+   double acc = SUB ? o.b : ((MODE == SPMV_ADD) ? o.yo : 0.0);
+   int    k = o.s;
+   // groups of four: issue the gathers together, then accumulate in order
+   for (; k + 4 <= o.e; k += 4)
+   {
+      int    c0 = cs[k], c1 = cs[k + 1], c2 = cs[k + 2], c3 = cs[k + 3];
+      double x0 = __ldg(a.x + c0), x1 = __ldg(a.x + c1), x2 = __ldg(a.x + c2), x3 = __ldg(a.x + c3);
+      double p0 = __dmul_rn(vs[k], x0), p1 = __dmul_rn(vs[k + 1], x1);
+      double p2 = __dmul_rn(vs[k + 2], x2), p3 = __dmul_rn(vs[k + 3], x3);
+      if (SUB) { acc = __dadd_rn(acc, -p0); acc = __dadd_rn(acc, -p1); acc = __dadd_rn(acc, -p2); acc = __dadd_rn(acc, -p3); }
+      else { acc = __dadd_rn(acc, p0); acc = __dadd_rn(acc, p1); acc = __dadd_rn(acc, p2); acc = __dadd_rn(acc, p3); }
+   }
+   if (k < o.e)
+   {
+      // tail of 1..3 entries, gathers issued together
+      int    c0 = cs[k], c1 = (k + 1 < o.e) ? cs[k + 1] : c0, c2 = (k + 2 < o.e) ? cs[k + 2] : c0;
+      double x0 = __ldg(a.x + c0), x1 = __ldg(a.x + c1), x2 = __ldg(a.x + c2);
+      double p0 = __dmul_rn(vs[k], x0);
+      acc       = __dadd_rn(acc, SUB ? -p0 : p0);
+      if (k + 1 < o.e) { double p1 = __dmul_rn(vs[k + 1], x1); acc = __dadd_rn(acc, SUB ? -p1 : p1); }
+      if (k + 2 < o.e) { double p2 = __dmul_rn(vs[k + 2], x2); acc = __dadd_rn(acc, SUB ? -p2 : p2); }
+   }
+   if (MODE == SPMV_SET || MODE == SPMV_ADD || MODE == SPMV_RESIDUAL) return acc;
+   if (MODE == SPMV_AXPBY)
+      return (a.beta == 0.0) ? __dmul_rn(a.alpha, acc) : __dadd_rn(__dmul_rn(a.alpha, acc), __dmul_rn(a.beta, o.yo));
+   if (MODE == SPMV_JACOBI)
+      return (o.d != 0.0) ? __dadd_rn(o.xo, __ddiv_rn(__dmul_rn(a.w, acc), o.d)) : o.xo;
+   /* SPMV_JACOBI_R */
+   return (o.d != 0.0) ? __ddiv_rn(__dmul_rn(a.w, acc), o.d) : 0.0;
+}
+
 template <int MODE, bool DOT>
 __global__ void __launch_bounds__(ST, 4) k_spmv_tma(SpmvDev a, int nblk, int cap)
 {
-   constexpr int PF = 2;
+   constexpr int PF = 2; // row rounds whose operands are prefetched
    extern __shared__ __align__(128) unsigned char smem_raw[];
    __shared__ double red[ST / 32];
    __shared__ int    flag;
@@ -238,10 +151,9 @@ __global__ void __launch_bounds__(ST, 4) k_spmv_tma(SpmvDev a, int nblk, int cap
    __syncthreads();
    int      b = blockIdx.x, nb = b + G;
    int      stage = 0;
-   uint32_t ph[2] = {0u, 0u};
+   uint32_t ph0 = 0u, ph1 = 0u;
    double   dacc = 0.0;
-   BlkMeta  cur, nxt;
-   cur = nxt = BlkMeta{0, 0, 0, 0};
+   BlkMeta  cur = BlkMeta{0, 0, 0, 0}, nxt = BlkMeta{0, 0, 0, 0};
    if (b < nblk)
    {
       cur = blk_meta(a, b);
@@ -256,8 +168,8 @@ __global__ void __launch_bounds__(ST, 4) k_spmv_tma(SpmvDev a, int nblk, int cap
    if (nb < nblk) nxt = blk_meta(a, nb);
    while (b < nblk)
    {
-      // 1. bulk copies of the next block into the other stage (its readers finished before the
-      //    barrier that closed the previous iteration)
+      // 1. bulk copies of the next block into the other stage (its readers passed the barrier
+      //    that closed the previous iteration)
       if (nb < nblk && tid == 0)
       {
          int ka = nxt.k0 & ~3, len4 = (nxt.k1 - ka + 3) & ~3;
@@ -283,34 +195,21 @@ __global__ void __launch_bounds__(ST, 4) k_spmv_tma(SpmvDev a, int nblk, int cap
          if (r < cur.r1) row_load<MODE, DOT>(a, r, ka, ro[j]);
       }
       // 4. wait for this block's val / col
-      double *prod = vbuf + (size_t)stage * cap;
-      const int *cs = cbuf + (size_t)stage * cap;
+      const double *vs = vbuf + (size_t)stage * cap;
+      const int    *cs = cbuf + (size_t)stage * cap;
       if (len > 0)
       {
-         mbar_wait(stage ? bar1 : bar0, ph[stage]);
-         ph[stage] ^= 1u;
+         if (stage) { mbar_wait(bar1, ph1); ph1 ^= 1u; }
+         else { mbar_wait(bar0, ph0); ph0 ^= 1u; }
       }
-      // 5. gather x and multiply in place
-      for (int k = tid * 4; k < len; k += ST * 4)
-      {
-         int4    c  = *reinterpret_cast<const int4 *>(cs + k);
-         double2 v0 = *reinterpret_cast<const double2 *>(prod + k);
-         double2 v1 = *reinterpret_cast<const double2 *>(prod + k + 2);
-         double  x0 = __ldg(a.x + c.x), x1 = __ldg(a.x + c.y), x2 = __ldg(a.x + c.z), x3 = __ldg(a.x + c.w);
-         v0.x = __dmul_rn(v0.x, x0); v0.y = __dmul_rn(v0.y, x1);
-         v1.x = __dmul_rn(v1.x, x2); v1.y = __dmul_rn(v1.y, x3);
-         *reinterpret_cast<double2 *>(prod + k)     = v0;
-         *reinterpret_cast<double2 *>(prod + k + 2) = v1;
-      }
-      __syncthreads();
-      // 6. one thread per row, sequential sum in CSR order, fused epilogue
+      // 5. one row per thread
 #pragma unroll
       for (int j = 0; j < PF; ++j)
       {
          int r = cur.r0 + tid + j * ST;
          if (r < cur.r1)
          {
-            double yn = row_epilogue<MODE>(a, ro[j], prod);
+            double yn = row_compute<MODE>(a, ro[j], vs, cs);
             a.y[r]    = yn;
             if (DOT) dacc += ro[j].dv * yn;
          }
@@ -319,11 +218,11 @@ __global__ void __launch_bounds__(ST, 4) k_spmv_tma(SpmvDev a, int nblk, int cap
       {
          RowOps o;
          row_load<MODE, DOT>(a, r, ka, o);
-         double yn = row_epilogue<MODE>(a, o, prod);
+         double yn = row_compute<MODE>(a, o, vs, cs);
          a.y[r]    = yn;
          if (DOT) dacc += o.dv * yn;
       }
-      __syncthreads();
+      __syncthreads(); // stage may be overwritten by the copies issued in the next iteration
       b = nb; nb = nnb; cur = nxt; nxt = nn; stage ^= 1;
    }
    if (DOT)
@@ -379,22 +278,26 @@ __global__ void __launch_bounds__(ST) k_spmv_vector(SpmvDev a)
    }
 }
 
-static int g_spmv_impl = -1; // 0 = LDG stream kernel, 1 = TMA stream kernel (default)
-
 template <int MODE, bool DOT>
 static int launch_tma(const DevCSR &A, const SpmvDev &d)
 {
-   static int    occ = 0;
-   static size_t occ_smem = 0;
-   size_t        smem = 128 + (size_t)2 * A.cap * 12;
-   if (smem != occ_smem)
+   static bool                  attr_set = false;
+   static std::map<size_t, int> occ_cache; // per template instantiation: smem bytes -> CTAs/SM
+   size_t                       smem = 128 + (size_t)2 * A.cap * 12;
+   if (!attr_set)
    {
-      HDK_CUDA(cudaFuncSetAttribute(k_spmv_tma<MODE, DOT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      HDK_CUDA(cudaFuncSetAttribute(k_spmv_tma<MODE, DOT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
+      attr_set = true;
+   }
+   auto it = occ_cache.find(smem);
+   if (it == occ_cache.end())
+   {
+      int occ = 0;
       HDK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_spmv_tma<MODE, DOT>, ST, smem));
       if (occ < 1) occ = 1;
-      occ_smem = smem;
+      it = occ_cache.emplace(smem, occ).first;
    }
-   int grid = g.sm_count * occ;
+   int grid = g.sm_count * it->second;
    if (grid > A.nblk) grid = A.nblk;
    k_spmv_tma<MODE, DOT><<<grid, ST, smem, g.stream>>>(d, A.nblk, A.cap);
    return HDK_OK;
@@ -403,20 +306,10 @@ static int launch_tma(const DevCSR &A, const SpmvDev &d)
 template <int MODE>
 static int launch_mode(const DevCSR &A, const SpmvDev &d, bool dot)
 {
-   if (g_spmv_impl < 0)
-   {
-      const char *e = getenv("HDK_SPMV_IMPL");
-      g_spmv_impl   = (e && !strcmp(e, "ldg")) ? 0 : 1;
-   }
-   if (A.kind == 0 && g_spmv_impl == 1)
+   if (A.kind == 0)
    {
       if (dot) HDK_TRY((launch_tma<MODE, true>(A, d)));
       else HDK_TRY((launch_tma<MODE, false>(A, d)));
-   }
-   else if (A.kind == 0)
-   {
-      if (dot) k_spmv_stream<MODE, true><<<A.nblk, ST, 0, g.stream>>>(d);
-      else k_spmv_stream<MODE, false><<<A.nblk, ST, 0, g.stream>>>(d);
    }
    else
    {
@@ -441,7 +334,6 @@ int spmv_launch(const DevCSR &A, int mode, const SpmvArgs &s)
    d.nrows = A.nrows; d.fin = s.fin; d.fin_out = s.fin_out;
    d.scal = g.dscal; d.partials = g.partials; d.ticket = g.counters;
    bool dot = (s.fin != FIN_NONE && s.dotv != nullptr);
-   if (A.kind == 0 && A.nblk > PARTIALS_CAP) return set_error(HDK_ERR_UNSUPPORTED, "matrix too large for reduction scratch");
    switch (mode)
    {
       case SPMV_SET: return launch_mode<SPMV_SET>(A, d, dot);
@@ -503,13 +395,18 @@ int csr_analyze(DevCSR &A)
    A.kind    = (hmax <= S_MAXR) ? 0 : 1;
    if (A.kind == 0)
    {
-      // non-zeros per CTA: about one row per thread (256 rows), 64-aligned, within [1024, 3072]
-      int tgt = ((int)(A.avg_row * 256.0) / 64) * 64;
-      if (tgt < 1024) tgt = 1024;
-      if (tgt > S_TGT) tgt = S_TGT;
+      // non-zeros per block: about one row per thread (`mult` x 256 rows), 64-aligned
+      static double mult = -1.0;
+      if (mult < 0) { const char *e = getenv("HDK_SPMV_ROWS_MULT"); mult = e ? atof(e) : 1.0; if (mult <= 0) mult = 1.0; }
+      static int thi = -1;
+      if (thi < 0) { const char *e = getenv("HDK_SPMV_TGT_MAX"); thi = e ? atoi(e) : 3072; if (thi < S_TGT_LO) thi = S_TGT_LO; if (thi > S_TGT_HI) thi = S_TGT_HI; }
+      int tgt = ((int)(A.avg_row * 256.0 * mult) / 64) * 64;
+      if (tgt < S_TGT_LO) tgt = S_TGT_LO;
+      if (tgt > thi) tgt = thi;
       A.tgt  = tgt;
-      A.cap  = (tgt + hmax + 8 + 3) & ~3;   // shared-memory entries per stage (<= S_CAP)
+      A.cap  = (tgt + hmax + 8 + 3) & ~3; // shared-memory entries per stage
       A.nblk = A.nnz / tgt + 1;
+      if (A.nblk > PARTIALS_CAP) return set_error(HDK_ERR_UNSUPPORTED, "matrix too large for the reduction scratch");
       HDK_TRY(dalloc(&A.blk_row, (size_t)A.nblk + 1));
       k_blk_rows<<<cdiv(A.nblk + 1, 256), 256, 0, g.stream>>>(A.rowptr, A.nrows, A.nblk, tgt, A.blk_row);
       HDK_LAUNCH_CHECK();
