@@ -12,12 +12,32 @@
 #include <cub/cub.cuh>
 #include <algorithm>
 #include <math.h>
+#include <stdlib.h>
+#include <time.h>
 
 namespace hdk {
 
 #define C_PT 1
 #define F_PT -1
 #define SF_PT -3
+
+// HDK_SETUP_TIMING=1: synchronise and print the wall time of every setup stage
+static double g_t_last = 0.0;
+static bool   g_timing = false;
+static double wall_now()
+{
+   struct timespec ts;
+   clock_gettime(CLOCK_MONOTONIC, &ts);
+   return (double)ts.tv_sec + 1e-9 * (double)ts.tv_nsec;
+}
+static void stage_mark(const char *name, int level)
+{
+   if (!g_timing) return;
+   cudaStreamSynchronize(g.stream);
+   double t = wall_now();
+   if (name) fprintf(stderr, "[hdk setup] level %d %-12s %8.3f ms\n", level, name, 1e3 * (t - g_t_last));
+   g_t_last = t;
+}
 
 static const int64_t SCRATCH_BUDGET = (int64_t)1 << 30; // hash slots per chunk (4-8 GB)
 
@@ -980,6 +1000,23 @@ static int build_dense_inverse(const DevCSR &A, double **inv)
    return HDK_OK;
 }
 
+// sort the off-diagonal entries of every row by column (diagonal stays first): improves the
+// coalescing of the x gathers across consecutive coarse rows in the solve phase
+__global__ void k_sort_rows(const int *rp, int *col, double *val, int n)
+{
+   int i = blockIdx.x * blockDim.x + threadIdx.x;
+   if (i >= n) return;
+   int b = rp[i] + 1, e = rp[i + 1];
+   for (int k = b + 1; k < e; k++)
+   {
+      int    c = col[k];
+      double v = val[k];
+      int    j = k - 1;
+      while (j >= b && col[j] > c) { col[j + 1] = col[j]; val[j + 1] = val[j]; j--; }
+      col[j + 1] = c; val[j + 1] = v;
+   }
+}
+
 // wrap a rank-local DevCSR as a ParCSR object with an empty offd block
 static hdk_csr_s *wrap_local(DevCSR &D, int64_t grows)
 {
@@ -1045,6 +1082,7 @@ int hdk_amg_setup(const hdk_csr *A0, const hdk_amg_params *prm, hdk_amg **out)
    if (prm->trunc_factor != 0.0) return set_error(HDK_ERR_UNSUPPORTED, "interpolation trunc_factor != 0 is not supported on the device path");
    hdk_amg_s *M = new hdk_amg_s();
    M->prm       = *prm;
+   g_timing     = getenv("HDK_SETUP_TIMING") && atoi(getenv("HDK_SETUP_TIMING")) == 1;
    int rc       = HDK_OK;
    M->lev.emplace_back();
    M->lev[0].A = const_cast<hdk_csr_s *>(A0);
@@ -1058,7 +1096,9 @@ int hdk_amg_setup(const hdk_csr *A0, const hdk_amg_params *prm, hdk_amg **out)
       AmgLevel        &L = M->lev[(size_t)level];
       const hdk_csr_s &A = *L.A;
       int              n = L.n;
+      stage_mark(nullptr, level);
       if ((rc = build_strength(A, prm->strong_th, prm->max_row_sum, L.S))) break;
+      stage_mark("strength", level);
       if ((rc = dalloc(&L.cf, (size_t)n + 1))) break;
       double *meas, *keep = nullptr;
       if ((rc = dalloc(&meas, (size_t)n + 1))) break;
@@ -1066,6 +1106,7 @@ int hdk_amg_setup(const hdk_csr *A0, const hdk_amg_params *prm, hdk_amg **out)
       L.measure = keep;
       int64_t goff = (level == 0) ? A.row_start : 0;
       rc = run_pmis(L.S, prm->rand_seed, goff, L.cf, meas, keep, nullptr);
+      stage_mark("pmis", level);
       dfree(meas);
       if (rc) break;
       int *flag, *f2c;
@@ -1081,13 +1122,17 @@ int hdk_amg_setup(const hdk_csr *A0, const hdk_amg_params *prm, hdk_amg **out)
       if (nc == 0 || nc == n || nc < prm->min_coarse_size) { dfree(f2c); break; }
       DevCSR P, R, C;
       rc = build_interp(A.diag, L.S, L.cf, f2c, nc, prm->max_nnz_row, P);
+      stage_mark("interp", level);
       dfree(f2c);
       if (rc) break;
       if ((rc = csr_transpose(P, R))) break;
+      stage_mark("transpose", level);
       if ((rc = build_rap(R, A.diag, P, C))) break;
+      stage_mark("rap", level);
       if ((rc = csr_analyze(P))) break;
       if ((rc = csr_analyze(R))) break;
       if ((rc = csr_analyze(C))) break;
+      stage_mark("analyze", level);
       nnz_sum += C.nnz;
       L.P = wrap_local(P, n);
       L.R = wrap_local(R, nc);
@@ -1097,6 +1142,16 @@ int hdk_amg_setup(const hdk_csr *A0, const hdk_amg_params *prm, hdk_amg **out)
       level++;
       if (level == prm->max_levels - 1 || nc <= prm->max_coarse_size) more = false;
       if (!M->keep_debug) csr_free(M->lev[(size_t)level - 1].S);
+   }
+   if (rc == HDK_OK && getenv("HDK_SORT_COARSE") && atoi(getenv("HDK_SORT_COARSE")) == 1)
+   {
+      for (int l = 1; l <= level && rc == HDK_OK; l++)
+      {
+         DevCSR &D = M->lev[(size_t)l].A->diag;
+         k_sort_rows<<<cdiv(D.nrows, 128), 128, 0, g.stream>>>(D.rowptr, D.col, D.val, D.nrows);
+         g.launches++;
+         rc = csr_analyze(D);
+      }
    }
    if (rc == HDK_OK)
    {

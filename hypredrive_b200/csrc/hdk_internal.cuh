@@ -94,6 +94,7 @@ struct DevCSR
    int     max_row = 0;
    double  avg_row = 0.0;
    int     tgt = 0, cap = 0;  // stream kernel: non-zeros per CTA, shared-memory entries per stage
+   int     lpr = 1;           // stream kernel: lanes per row (1, 2, 4, 8)
    int     nblk = 0;          // stream kernel: number of nnz-balanced row blocks
    int    *blk_row = nullptr; // nblk+1 first rows
    bool    owns = true;

@@ -131,10 +131,45 @@ __device__ __forceinline__ double row_compute(const SpmvDev &a, const RowOps &o,
    return (o.d != 0.0) ? __ddiv_rn(__dmul_rn(a.w, acc), o.d) : 0.0;
 }
 
-template <int MODE, bool DOT>
+// several lanes per row (long rows): lane `sub` of LPR sums entries s+sub, s+sub+LPR, ...;
+// the LPR partials are combined by a fixed-order butterfly (deterministic, but not the
+// sequential CSR order -- fp parity with the oracle within tolerance)
+template <int LPR>
+__device__ __forceinline__ double row_partial(const SpmvDev &a, int k, int e, const double *vs, const int *cs)
+{
+   double acc = 0.0;
+   for (; k + 3 * LPR < e; k += 4 * LPR)
+   {
+      int    c0 = cs[k], c1 = cs[k + LPR], c2 = cs[k + 2 * LPR], c3 = cs[k + 3 * LPR];
+      double x0 = __ldg(a.x + c0), x1 = __ldg(a.x + c1), x2 = __ldg(a.x + c2), x3 = __ldg(a.x + c3);
+      acc = __dadd_rn(acc, __dmul_rn(vs[k], x0));
+      acc = __dadd_rn(acc, __dmul_rn(vs[k + LPR], x1));
+      acc = __dadd_rn(acc, __dmul_rn(vs[k + 2 * LPR], x2));
+      acc = __dadd_rn(acc, __dmul_rn(vs[k + 3 * LPR], x3));
+   }
+   for (; k < e; k += LPR) acc = __dadd_rn(acc, __dmul_rn(vs[k], __ldg(a.x + cs[k])));
+   return acc;
+}
+
+template <int MODE>
+__device__ __forceinline__ double row_finish(const SpmvDev &a, const RowOps &o, double total)
+{
+   if (MODE == SPMV_SET) return total;
+   if (MODE == SPMV_ADD) return __dadd_rn(o.yo, total);
+   if (MODE == SPMV_AXPBY)
+      return (a.beta == 0.0) ? __dmul_rn(a.alpha, total) : __dadd_rn(__dmul_rn(a.alpha, total), __dmul_rn(a.beta, o.yo));
+   double res = __dadd_rn(o.b, -total);
+   if (MODE == SPMV_RESIDUAL) return res;
+   if (MODE == SPMV_JACOBI)
+      return (o.d != 0.0) ? __dadd_rn(o.xo, __ddiv_rn(__dmul_rn(a.w, res), o.d)) : o.xo;
+   return (o.d != 0.0) ? __ddiv_rn(__dmul_rn(a.w, res), o.d) : 0.0;
+}
+
+template <int MODE, bool DOT, int LPR>
 __global__ void __launch_bounds__(ST, 4) k_spmv_tma(SpmvDev a, int nblk, int cap)
 {
-   constexpr int PF = 2; // row rounds whose operands are prefetched
+   constexpr int PF  = 2;        // row rounds whose operands are prefetched
+   constexpr int RPB = ST / LPR; // rows per round
    extern __shared__ __align__(128) unsigned char smem_raw[];
    __shared__ double red[ST / 32];
    __shared__ int    flag;
@@ -191,7 +226,7 @@ __global__ void __launch_bounds__(ST, 4) k_spmv_tma(SpmvDev a, int nblk, int cap
 #pragma unroll
       for (int j = 0; j < PF; ++j)
       {
-         int r = cur.r0 + tid + j * ST;
+         int r = cur.r0 + tid / LPR + j * RPB;
          if (r < cur.r1) row_load<MODE, DOT>(a, r, ka, ro[j]);
       }
       // 4. wait for this block's val / col
@@ -202,25 +237,64 @@ __global__ void __launch_bounds__(ST, 4) k_spmv_tma(SpmvDev a, int nblk, int cap
          if (stage) { mbar_wait(bar1, ph1); ph1 ^= 1u; }
          else { mbar_wait(bar0, ph0); ph0 ^= 1u; }
       }
-      // 5. one row per thread
-#pragma unroll
-      for (int j = 0; j < PF; ++j)
+      // 5. one row per thread (LPR == 1, exact CSR order) or per group of LPR lanes
+      if (LPR == 1)
       {
-         int r = cur.r0 + tid + j * ST;
-         if (r < cur.r1)
+#pragma unroll
+         for (int j = 0; j < PF; ++j)
          {
-            double yn = row_compute<MODE>(a, ro[j], vs, cs);
+            int r = cur.r0 + tid + j * ST;
+            if (r < cur.r1)
+            {
+               double yn = row_compute<MODE>(a, ro[j], vs, cs);
+               a.y[r]    = yn;
+               if (DOT) dacc += ro[j].dv * yn;
+            }
+         }
+         for (int r = cur.r0 + tid + PF * ST; r < cur.r1; r += ST)
+         {
+            RowOps o;
+            row_load<MODE, DOT>(a, r, ka, o);
+            double yn = row_compute<MODE>(a, o, vs, cs);
             a.y[r]    = yn;
-            if (DOT) dacc += ro[j].dv * yn;
+            if (DOT) dacc += o.dv * yn;
          }
       }
-      for (int r = cur.r0 + tid + PF * ST; r < cur.r1; r += ST)
+      else
       {
-         RowOps o;
-         row_load<MODE, DOT>(a, r, ka, o);
-         double yn = row_compute<MODE>(a, o, vs, cs);
-         a.y[r]    = yn;
-         if (DOT) dacc += o.dv * yn;
+         const int sub = tid % LPR, rl = tid / LPR;
+#pragma unroll
+         for (int j = 0; j < PF; ++j)
+         {
+            int    r = cur.r0 + rl + j * RPB;
+            bool   valid = r < cur.r1;
+            double part = valid ? row_partial<LPR>(a, ro[j].s + sub, ro[j].e, vs, cs) : 0.0;
+#pragma unroll
+            for (int o = LPR / 2; o > 0; o >>= 1) part = __dadd_rn(part, __shfl_xor_sync(0xffffffffu, part, o));
+            if (valid && sub == 0)
+            {
+               double yn = row_finish<MODE>(a, ro[j], part);
+               a.y[r]    = yn;
+               if (DOT) dacc += ro[j].dv * yn;
+            }
+         }
+         for (int base = cur.r0 + PF * RPB; base < cur.r1; base += RPB) // uniform trip count
+         {
+            int    r = base + rl;
+            bool   valid = r < cur.r1;
+            RowOps o;
+            o.s = o.e = 0;
+            if (valid) row_load<MODE, DOT>(a, r, ka, o);
+            double part = valid ? row_partial<LPR>(a, o.s + sub, o.e, vs, cs) : 0.0;
+#pragma unroll
+            for (int w = LPR / 2; w > 0; w >>= 1) part = __dadd_rn(part, __shfl_xor_sync(0xffffffffu, part, w));
+            if (valid && sub == 0)
+            {
+               double yn = row_finish<MODE>(a, o, part);
+               a.y[r]    = yn;
+               if (DOT) dacc += o.dv * yn;
+            }
+         }
       }
       __syncthreads(); // stage may be overwritten by the copies issued in the next iteration
       b = nb; nb = nnb; cur = nxt; nxt = nn; stage ^= 1;
@@ -278,7 +352,7 @@ __global__ void __launch_bounds__(ST) k_spmv_vector(SpmvDev a)
    }
 }
 
-template <int MODE, bool DOT>
+template <int MODE, bool DOT, int LPR>
 static int launch_tma(const DevCSR &A, const SpmvDev &d)
 {
    static bool                  attr_set = false;
@@ -286,20 +360,20 @@ static int launch_tma(const DevCSR &A, const SpmvDev &d)
    size_t                       smem = 128 + (size_t)2 * A.cap * 12;
    if (!attr_set)
    {
-      HDK_CUDA(cudaFuncSetAttribute(k_spmv_tma<MODE, DOT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
+      HDK_CUDA(cudaFuncSetAttribute(k_spmv_tma<MODE, DOT, LPR>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
       attr_set = true;
    }
    auto it = occ_cache.find(smem);
    if (it == occ_cache.end())
    {
       int occ = 0;
-      HDK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_spmv_tma<MODE, DOT>, ST, smem));
+      HDK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_spmv_tma<MODE, DOT, LPR>, ST, smem));
       if (occ < 1) occ = 1;
       it = occ_cache.emplace(smem, occ).first;
    }
    int grid = g.sm_count * it->second;
    if (grid > A.nblk) grid = A.nblk;
-   k_spmv_tma<MODE, DOT><<<grid, ST, smem, g.stream>>>(d, A.nblk, A.cap);
+   k_spmv_tma<MODE, DOT, LPR><<<grid, ST, smem, g.stream>>>(d, A.nblk, A.cap);
    return HDK_OK;
 }
 
@@ -308,8 +382,13 @@ static int launch_mode(const DevCSR &A, const SpmvDev &d, bool dot)
 {
    if (A.kind == 0)
    {
-      if (dot) HDK_TRY((launch_tma<MODE, true>(A, d)));
-      else HDK_TRY((launch_tma<MODE, false>(A, d)));
+      switch (A.lpr)
+      {
+         case 2: if (dot) HDK_TRY((launch_tma<MODE, true, 2>(A, d))); else HDK_TRY((launch_tma<MODE, false, 2>(A, d))); break;
+         case 4: if (dot) HDK_TRY((launch_tma<MODE, true, 4>(A, d))); else HDK_TRY((launch_tma<MODE, false, 4>(A, d))); break;
+         case 8: if (dot) HDK_TRY((launch_tma<MODE, true, 8>(A, d))); else HDK_TRY((launch_tma<MODE, false, 8>(A, d))); break;
+         default: if (dot) HDK_TRY((launch_tma<MODE, true, 1>(A, d))); else HDK_TRY((launch_tma<MODE, false, 1>(A, d))); break;
+      }
    }
    else
    {
@@ -400,7 +479,13 @@ int csr_analyze(DevCSR &A)
       if (mult < 0) { const char *e = getenv("HDK_SPMV_ROWS_MULT"); mult = e ? atof(e) : 1.0; if (mult <= 0) mult = 1.0; }
       static int thi = -1;
       if (thi < 0) { const char *e = getenv("HDK_SPMV_TGT_MAX"); thi = e ? atoi(e) : 3072; if (thi < S_TGT_LO) thi = S_TGT_LO; if (thi > S_TGT_HI) thi = S_TGT_HI; }
-      int tgt = ((int)(A.avg_row * 256.0 * mult) / 64) * 64;
+      // lanes per row from the average row length (1 keeps the exact sequential CSR order)
+      static int lpr_force = -1;
+      if (lpr_force < 0) { const char *e = getenv("HDK_SPMV_LPR"); lpr_force = e ? atoi(e) : 0; }
+      int lpr = A.avg_row <= 12.0 ? 1 : (A.avg_row <= 24.0 ? 2 : (A.avg_row <= 56.0 ? 4 : 8));
+      if (lpr_force == 1 || lpr_force == 2 || lpr_force == 4 || lpr_force == 8) lpr = lpr_force;
+      A.lpr   = lpr;
+      int tgt = ((int)(A.avg_row * (256.0 / lpr) * mult) / 64) * 64;
       if (tgt < S_TGT_LO) tgt = S_TGT_LO;
       if (tgt > thi) tgt = thi;
       A.tgt  = tgt;

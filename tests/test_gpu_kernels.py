@@ -41,7 +41,11 @@ def test_spmv_bit_exact(gpu, kind, dims, c):
     x = rng.standard_normal(A.shape[0])
     dx, dy = gpu.DVec(x.size, x), gpu.DVec(x.size)
     dA.matvec(dx, dy)
-    assert np.array_equal(dy.get(), O.matvec(Ad, x))       # bit-exact: same per-row order
+    ref = O.matvec(Ad, x)
+    if dA.spmv_kind()["avg_row"] <= 12.0:
+        assert np.array_equal(dy.get(), ref)               # one lane per row: the oracle's exact order
+    else:                                                  # several lanes per row: fixed butterfly order
+        assert np.allclose(dy.get(), ref, rtol=0, atol=1e-14 * np.abs(Ad).sum(axis=1).max() * np.abs(x).max())
     db, dr = gpu.DVec(x.size, b), gpu.DVec(x.size)
     dA.residual(dx, db, dr)
     assert np.allclose(dr.get(), b - Ad @ x, rtol=0, atol=1e-12 * np.abs(Ad).sum(axis=1).max() * np.abs(x).max())
