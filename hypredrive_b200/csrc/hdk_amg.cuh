@@ -12,6 +12,7 @@ struct AmgLevel
    hdk_csr_s *R = nullptr;  // n_{l+1} x n_l  (P^T stored explicitly: keep_transpose)
    DevCSR     S;            // strength pattern (diag block)
    int       *cf = nullptr;
+   int       *f2c = nullptr; // exclusive scan of (cf > 0), n+1 entries (kept for the N > 1 slicing)
    double    *measure = nullptr;
    double    *l1_down = nullptr, *l1_up = nullptr; // smoother diagonals (may alias)
    double    *u = nullptr, *f = nullptr, *t = nullptr;
@@ -31,12 +32,21 @@ struct hdk_amg_s
    double                     op_complexity = 0.0;
    double                     vcycle_bytes = 0.0;
    bool                       keep_debug = true; // keep S / measure for introspection
+   bool                       keep_f2c = false;
+   // N > 1: levels [0, nlev) are row-distributed; from level `tail_level` on, the hierarchy is
+   // replicated on every rank (`tail`, a serial hierarchy of the GLOBAL problem) and the
+   // restricted right-hand side is summed over ranks into `full_f`
+   hdk_amg_s                 *tail = nullptr;
+   int                        tail_level = 0;
+   int64_t                    tail_off = 0, tail_cnt = 0, tail_n = 0; // my slice of the first replicated level
+   double                    *full_f = nullptr, *full_u = nullptr;
 };
 
 namespace hdk {
 // z = M^{-1} r (one V-cycle from a zero guess); if fin != FIN_NONE the last kernel also
 // produces <r,z> and applies `fin`
 int amg_precond(hdk_amg_s *M, const double *r, double *z, int fin, double *fin_out);
-int amg_cycle(hdk_amg_s *M, const double *f, double *u, bool zero_guess, int fin, double *fin_out);
+// V-cycle over levels [l0, nlev) of M; level l0 uses the caller's vectors
+int amg_cycle(hdk_amg_s *M, const double *f, double *u, bool zero_guess, int fin, double *fin_out, int l0 = 0);
 int exclusive_scan_int(const int *in, int *out, int n);
 } // namespace hdk

@@ -1063,26 +1063,62 @@ int hdk_amg_destroy(hdk_amg *M)
          if (L.owns_A) destroy_local(L.A);
          destroy_local(L.P); destroy_local(L.R);
          csr_free(L.S); csr_free(L.L);
-         dfree(L.cf); dfree(L.measure);
+         dfree(L.cf); dfree(L.measure); dfree(L.f2c);
          if (L.l1_up != L.l1_down) dfree(L.l1_up);
          dfree(L.l1_down);
          dfree(L.u); dfree(L.f); dfree(L.t);
       }
-      dfree(M->ge_inv);
+      dfree(M->ge_inv); dfree(M->full_f); dfree(M->full_u);
    }
+   if (M->tail) hdk_amg_destroy(M->tail);
    delete M;
    return HDK_OK;
 }
 
-int hdk_amg_setup(const hdk_csr *A0, const hdk_amg_params *prm, hdk_amg **out)
+// per-level solve data: smoother diagonals, work vectors, (two-stage GS) lower triangles, and the
+// algorithmic byte count of one V-cycle
+static int finalize_levels(hdk_amg_s *M, const hdk_amg_params *prm)
 {
-   HDK_TRY(require_init());
-   if (!A0 || !prm || !out) return set_error(HDK_ERR_INVALID, "hdk_amg_setup: null argument");
-   if (prm->interp_type != 6) return set_error(HDK_ERR_UNSUPPORTED, "interpolation type %d: only extended+i (6) has a device kernel", prm->interp_type);
-   if (prm->trunc_factor != 0.0) return set_error(HDK_ERR_UNSUPPORTED, "interpolation trunc_factor != 0 is not supported on the device path");
+   int    rc = HDK_OK;
+   double bytes = 0.0;
+   for (int l = 0; l < M->nlev && rc == HDK_OK; l++)
+   {
+      AmgLevel &L = M->lev[(size_t)l];
+      int       n = L.n;
+      if ((rc = build_l1(*L.A, relax_l1_option(prm->relax_down), &L.l1_down))) break;
+      if (relax_l1_option(prm->relax_up) == relax_l1_option(prm->relax_down)) L.l1_up = L.l1_down;
+      else if ((rc = build_l1(*L.A, relax_l1_option(prm->relax_up), &L.l1_up))) break;
+      if ((rc = dalloc(&L.t, (size_t)n + 8))) break;
+      if (l > 0)
+      {
+         if ((rc = dalloc(&L.u, (size_t)n + 8))) break;
+         if ((rc = dalloc(&L.f, (size_t)n + 8))) break;
+      }
+      bool tsgs = (prm->relax_down == 11 || prm->relax_down == 12 || prm->relax_up == 11 || prm->relax_up == 12);
+      if (tsgs && (rc = build_lower(L.A->diag, L.L))) break;
+      // algorithmic bytes of one V-cycle: zero-guess pre-smooth 24n, residual,
+      // restriction, prolongation, post-smooth
+      double nnzA = (double)L.A->diag.nnz + L.A->offd.nnz;
+      if (L.P)
+      {
+         double nnzP = (double)L.P->diag.nnz + L.P->offd.nnz, ncl = (double)L.P->diag.ncols;
+         bytes += 24.0 * n;                                       // u = w f / d
+         bytes += 12.0 * nnzA + 4.0 * (n + 1) + 24.0 * n;         // r = f - A u
+         bytes += 12.0 * nnzP + 4.0 * (ncl + 1) + 8.0 * n + 8.0 * ncl; // f_c = R r
+         bytes += 12.0 * nnzP + 4.0 * (n + 1) + 16.0 * n + 8.0 * ncl;  // u += P e
+         bytes += 12.0 * nnzA + 4.0 * (n + 1) + 32.0 * n;         // post-smooth
+      }
+      else bytes += 8.0 * (double)n * n + 16.0 * n;
+   }
+   M->vcycle_bytes = bytes;
+   return rc;
+}
+
+static int setup_serial(const hdk_csr_s *A0, const hdk_amg_params *prm, hdk_amg_s **out, bool keep_f2c)
+{
    hdk_amg_s *M = new hdk_amg_s();
    M->prm       = *prm;
-   g_timing     = getenv("HDK_SETUP_TIMING") && atoi(getenv("HDK_SETUP_TIMING")) == 1;
+   M->keep_f2c  = keep_f2c;
    int rc       = HDK_OK;
    M->lev.emplace_back();
    M->lev[0].A = const_cast<hdk_csr_s *>(A0);
@@ -1123,7 +1159,7 @@ int hdk_amg_setup(const hdk_csr *A0, const hdk_amg_params *prm, hdk_amg **out)
       DevCSR P, R, C;
       rc = build_interp(A.diag, L.S, L.cf, f2c, nc, prm->max_nnz_row, P);
       stage_mark("interp", level);
-      dfree(f2c);
+      if (keep_f2c) L.f2c = f2c; else dfree(f2c);
       if (rc) break;
       if ((rc = csr_transpose(P, R))) break;
       stage_mark("transpose", level);
@@ -1157,37 +1193,7 @@ int hdk_amg_setup(const hdk_csr *A0, const hdk_amg_params *prm, hdk_amg **out)
    {
       M->nlev = level + 1;
       M->op_complexity = nnz_sum / (nnz0 > 0 ? nnz0 : 1.0);
-      double bytes = 0.0;
-      for (int l = 0; l < M->nlev && rc == HDK_OK; l++)
-      {
-         AmgLevel &L = M->lev[(size_t)l];
-         int       n = L.n;
-         if ((rc = build_l1(*L.A, relax_l1_option(prm->relax_down), &L.l1_down))) break;
-         if (relax_l1_option(prm->relax_up) == relax_l1_option(prm->relax_down)) L.l1_up = L.l1_down;
-         else if ((rc = build_l1(*L.A, relax_l1_option(prm->relax_up), &L.l1_up))) break;
-         if ((rc = dalloc(&L.t, (size_t)n + 8))) break;
-         if (l > 0)
-         {
-            if ((rc = dalloc(&L.u, (size_t)n + 8))) break;
-            if ((rc = dalloc(&L.f, (size_t)n + 8))) break;
-         }
-         bool tsgs = (prm->relax_down == 11 || prm->relax_down == 12 || prm->relax_up == 11 || prm->relax_up == 12);
-         if (tsgs && (rc = build_lower(L.A->diag, L.L))) break;
-         // algorithmic bytes of one V-cycle: zero-guess pre-smooth 24n, residual,
-         // restriction, prolongation, post-smooth
-         double nnzA = (double)L.A->diag.nnz + L.A->offd.nnz;
-         if (l < M->nlev - 1)
-         {
-            double nnzP = (double)L.P->diag.nnz, ncl = (double)M->lev[(size_t)l + 1].n;
-            bytes += 24.0 * n;                                       // u = w f / d
-            bytes += 12.0 * nnzA + 4.0 * (n + 1) + 24.0 * n;         // r = f - A u
-            bytes += 12.0 * nnzP + 4.0 * (ncl + 1) + 8.0 * n + 8.0 * ncl; // f_c = R r
-            bytes += 12.0 * nnzP + 4.0 * (n + 1) + 16.0 * n + 8.0 * ncl;  // u += P e
-            bytes += 12.0 * nnzA + 4.0 * (n + 1) + 32.0 * n;         // post-smooth
-         }
-         else bytes += 8.0 * (double)n * n + 16.0 * n;
-      }
-      M->vcycle_bytes = bytes;
+      rc = finalize_levels(M, prm);
    }
    if (rc == HDK_OK)
    {
@@ -1205,12 +1211,216 @@ int hdk_amg_setup(const hdk_csr *A0, const hdk_amg_params *prm, hdk_amg **out)
    return HDK_OK;
 }
 
-int hdk_amg_num_levels(const hdk_amg *M) { return M ? M->nlev : 0; }
+// ------------------------------------------------------------------------------------------
+// N > 1.  Round-1 design: every rank reassembles the GLOBAL operator (NCCL broadcasts of the row
+// slabs), runs the serial device setup on it -- so the hierarchy is bit-identical to the
+// single-GPU one for any partition -- then keeps only its row slabs of A_l, P_l, R_l for the
+// large levels (ParCSR with halo plans) and the complete small levels (replicated "tail").
+// The solve phase is fully distributed; the setup does not scale yet.
+// ------------------------------------------------------------------------------------------
+__global__ void k_shift_i64(const int64_t *in, int64_t *out, int64_t n, int64_t shift)
+{
+   int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+   if (i < n) out[i] = in[i] + shift;
+}
+__global__ void k_slice_indptr(const int *rp, int r0, int n, int64_t *out)
+{
+   int i = blockIdx.x * blockDim.x + threadIdx.x;
+   if (i <= n) out[i] = (int64_t)rp[r0 + i] - (int64_t)rp[r0];
+}
+__global__ void k_slice_entries(const int *col, const double *val, int64_t k0, int64_t cnt, int64_t *ocol, double *oval)
+{
+   int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+   if (k < cnt) { ocol[k] = col[k0 + k]; oval[k] = val[k0 + k]; }
+}
+
+// rows [r0, r1) of a serial block -> ParCSR slab (distributed) or local block over all columns
+static int slice_rows(const DevCSR &D, int r0, int r1, int64_t cs, int64_t ce, int64_t grows, int64_t gcols,
+                      bool square, bool distributed, hdk_csr_s **out)
+{
+   int      n = r1 - r0;
+   int      k[2];
+   HDK_CUDA(cudaMemcpyAsync(&k[0], D.rowptr + r0, sizeof(int), cudaMemcpyDeviceToHost, g.stream));
+   HDK_CUDA(cudaMemcpyAsync(&k[1], D.rowptr + r1, sizeof(int), cudaMemcpyDeviceToHost, g.stream));
+   HDK_CUDA(cudaStreamSynchronize(g.stream));
+   int64_t  cnt = (int64_t)k[1] - k[0];
+   int64_t *ip, *cj;
+   double  *va;
+   HDK_TRY(dalloc(&ip, (size_t)n + 1));
+   HDK_TRY(dalloc(&cj, (size_t)cnt + 1));
+   HDK_TRY(dalloc(&va, (size_t)cnt + 1));
+   k_slice_indptr<<<cdiv(n + 1, 256), 256, 0, g.stream>>>(D.rowptr, r0, n, ip);
+   HDK_LAUNCH_CHECK();
+   if (cnt > 0)
+   {
+      k_slice_entries<<<cdiv(cnt, 256), 256, 0, g.stream>>>(D.col, D.val, k[0], cnt, cj, va);
+      HDK_LAUNCH_CHECK();
+   }
+   int rc = parcsr_build(r0, (int64_t)r1 - 1, cs, ce, grows, gcols, square, distributed, false, ip, cj, va, out);
+   dfree(ip); dfree(cj); dfree(va);
+   return rc;
+}
+
+static int setup_distributed(const hdk_csr_s *A0, const hdk_amg_params *prm, hdk_amg_s **out)
+{
+   const int R = g.nranks, me = g.rank;
+   if (!A0->orig_indptr) return set_error(HDK_ERR_INVALID, "distributed setup needs the matrix to be built at N > 1");
+   // 1. sizes and offsets of every rank's slab
+   std::vector<int64_t> rows_all, nnz_all;
+   HDK_TRY(allgather_i64_host(A0->diag.nrows, rows_all));
+   HDK_TRY(allgather_i64_host(A0->orig_nnz, nnz_all));
+   std::vector<int64_t> roff((size_t)R + 1, 0), koff((size_t)R + 1, 0);
+   for (int r = 0; r < R; r++) { roff[(size_t)r + 1] = roff[(size_t)r] + rows_all[(size_t)r]; koff[(size_t)r + 1] = koff[(size_t)r] + nnz_all[(size_t)r]; }
+   const int64_t N = roff[(size_t)R], NNZ = koff[(size_t)R];
+   if (N > 2000000000LL || NNZ > 2000000000LL)
+      return set_error(HDK_ERR_UNSUPPORTED, "global problem (%lld rows, %lld nnz) exceeds the int32 limits of the replicated setup", (long long)N, (long long)NNZ);
+   if (roff[(size_t)me] != A0->row_start) return set_error(HDK_ERR_INVALID, "row partition is not contiguous in rank order");
+   // 2. reassemble the global operator on every rank
+   int64_t *gip, *gcj;
+   double  *gva;
+   HDK_TRY(dalloc(&gip, (size_t)N + 1));
+   HDK_TRY(dalloc(&gcj, (size_t)NNZ + 1));
+   HDK_TRY(dalloc(&gva, (size_t)NNZ + 1));
+   {
+      int64_t n = rows_all[(size_t)me];
+      k_shift_i64<<<cdiv(n, 256), 256, 0, g.stream>>>(A0->orig_indptr, gip + roff[(size_t)me], n, koff[(size_t)me]);
+      HDK_LAUNCH_CHECK();
+      HDK_CUDA(cudaMemcpyAsync(gcj + koff[(size_t)me], A0->orig_cols, sizeof(int64_t) * (size_t)A0->orig_nnz, cudaMemcpyDeviceToDevice, g.stream));
+      HDK_CUDA(cudaMemcpyAsync(gva + koff[(size_t)me], A0->orig_vals, sizeof(double) * (size_t)A0->orig_nnz, cudaMemcpyDeviceToDevice, g.stream));
+      HDK_CUDA(cudaMemcpyAsync(gip + N, &NNZ, sizeof(int64_t), cudaMemcpyHostToDevice, g.stream));
+   }
+   for (int r = 0; r < R; r++)
+   {
+      HDK_TRY(bcast_bytes(gip + roff[(size_t)r], sizeof(int64_t) * (size_t)rows_all[(size_t)r], r));
+      HDK_TRY(bcast_bytes(gcj + koff[(size_t)r], sizeof(int64_t) * (size_t)nnz_all[(size_t)r], r));
+      HDK_TRY(bcast_bytes(gva + koff[(size_t)r], sizeof(double) * (size_t)nnz_all[(size_t)r], r));
+   }
+   hdk_csr_s *G = nullptr;
+   int rc = parcsr_build(0, N - 1, 0, N - 1, N, N, true, false, false, gip, gcj, gva, &G);
+   dfree(gip); dfree(gcj); dfree(gva);
+   if (rc) return rc;
+   // 3. the global hierarchy (serial algorithm, identical on every rank)
+   hdk_amg_s *Mg = nullptr;
+   rc = setup_serial(G, prm, &Mg, true);
+   if (rc) { destroy_local(G); return rc; }
+   Mg->lev[0].owns_A = true; // G belongs to the global hierarchy
+   // 4. fine ranges of every rank on every level; first replicated level
+   static int64_t rep_rows = -1;
+   if (rep_rows < 0) { const char *e = getenv("HDK_REPLICATE_ROWS"); rep_rows = e ? atoll(e) : 262144; }
+   const int nl = Mg->nlev;
+   std::vector<std::vector<int64_t>> starts((size_t)nl); // starts[l][r], r = 0..R
+   starts[0] = roff;
+   int tail_level = nl - 1;
+   for (int l = 0; l < nl; l++)
+   {
+      bool empty = false;
+      for (int r = 0; r < R; r++) if (starts[(size_t)l][(size_t)r + 1] <= starts[(size_t)l][(size_t)r]) empty = true;
+      if (Mg->lev[(size_t)l].n <= rep_rows || empty) { tail_level = l; break; }
+      if (l + 1 < nl)
+      {
+         // coarse ranges = f2c at the fine range boundaries
+         std::vector<int64_t> nxt((size_t)R + 1, 0);
+         for (int r = 0; r <= R; r++)
+         {
+            int v = 0;
+            HDK_CUDA(cudaMemcpyAsync(&v, Mg->lev[(size_t)l].f2c + starts[(size_t)l][(size_t)r], sizeof(int), cudaMemcpyDeviceToHost, g.stream));
+            HDK_CUDA(cudaStreamSynchronize(g.stream));
+            nxt[(size_t)r] = v;
+         }
+         starts[(size_t)l + 1] = nxt;
+      }
+   }
+   // 5. distributed levels [0, tail_level): slabs of A_l, P_l, R_l
+   hdk_amg_s *M = new hdk_amg_s();
+   M->prm = *prm;
+   M->tail = Mg; M->tail_level = tail_level;
+   M->op_complexity = Mg->op_complexity;
+   for (int l = 0; l < tail_level && rc == HDK_OK; l++)
+   {
+      AmgLevel &Lg = Mg->lev[(size_t)l];
+      M->lev.emplace_back();
+      AmgLevel &L = M->lev.back();
+      const int64_t fs = starts[(size_t)l][(size_t)me], fe = starts[(size_t)l][(size_t)me + 1];
+      const int64_t cs = starts[(size_t)l + 1][(size_t)me], ce = starts[(size_t)l + 1][(size_t)me + 1];
+      const int64_t nf = Lg.n, nc = Mg->lev[(size_t)l + 1].n;
+      L.n = (int)(fe - fs);
+      if (l == 0) { L.A = const_cast<hdk_csr_s *>(A0); L.owns_A = false; }
+      else
+      {
+         if ((rc = slice_rows(Lg.A->diag, (int)fs, (int)fe, fs, fe - 1, nf, nf, true, true, &L.A))) break;
+         L.owns_A = true;
+      }
+      if (l + 1 < tail_level)
+      {
+         if ((rc = slice_rows(Lg.P->diag, (int)fs, (int)fe, cs, ce - 1, nf, nc, false, true, &L.P))) break;
+      }
+      else
+      {
+         // the next level is replicated: P reads the complete coarse vector, no halo
+         if ((rc = slice_rows(Lg.P->diag, (int)fs, (int)fe, 0, nc - 1, nf, nc, false, false, &L.P))) break;
+      }
+      if ((rc = slice_rows(Lg.R->diag, (int)cs, (int)ce, fs, fe - 1, nc, nf, false, true, &L.R))) break;
+   }
+   if (rc == HDK_OK)
+   {
+      M->nlev = tail_level;
+      M->tail_n   = Mg->lev[(size_t)tail_level].n;
+      M->tail_off = starts[(size_t)tail_level][(size_t)me];
+      M->tail_cnt = starts[(size_t)tail_level][(size_t)me + 1] - M->tail_off;
+      rc = finalize_levels(M, prm);
+      double vb = M->vcycle_bytes;
+      // per-rank byte count: distributed levels (local) + replicated tail
+      for (int l = tail_level; l < nl; l++)
+      {
+         AmgLevel &Lg = Mg->lev[(size_t)l];
+         double    n = Lg.n, nnzA = Lg.A->diag.nnz;
+         if (Lg.P) { double nnzP = Lg.P->diag.nnz, ncl = Lg.P->diag.ncols; vb += 24.0 * n + 2 * (12.0 * nnzA + 4.0 * n) + 56.0 * n + 2 * (12.0 * nnzP) + 28.0 * n + 16.0 * ncl; }
+         else vb += 8.0 * n * n + 16.0 * n;
+      }
+      M->vcycle_bytes = vb;
+   }
+   if (rc == HDK_OK) rc = dalloc(&M->full_f, (size_t)M->tail_n + 8);
+   if (rc == HDK_OK) rc = dalloc(&M->full_u, (size_t)M->tail_n + 8);
+   // 6. drop the global copies of the distributed levels
+   if (rc == HDK_OK)
+   {
+      for (int l = 0; l < tail_level; l++)
+      {
+         AmgLevel &Lg = Mg->lev[(size_t)l];
+         if (Lg.owns_A) { destroy_local(Lg.A); Lg.A = nullptr; Lg.owns_A = false; }
+         destroy_local(Lg.P); Lg.P = nullptr;
+         destroy_local(Lg.R); Lg.R = nullptr;
+         csr_free(Lg.S); csr_free(Lg.L);
+         dfree(Lg.cf); Lg.cf = nullptr; dfree(Lg.measure); Lg.measure = nullptr; dfree(Lg.f2c); Lg.f2c = nullptr;
+         if (Lg.l1_up != Lg.l1_down) dfree(Lg.l1_up);
+         dfree(Lg.l1_down); Lg.l1_down = Lg.l1_up = nullptr;
+         dfree(Lg.u); dfree(Lg.f); dfree(Lg.t); Lg.u = Lg.f = Lg.t = nullptr;
+      }
+      HDK_CUDA(cudaStreamSynchronize(g.stream));
+   }
+   if (rc != HDK_OK) { hdk_amg_destroy(M); return rc; }
+   *out = M;
+   return HDK_OK;
+}
+
+int hdk_amg_setup(const hdk_csr *A0, const hdk_amg_params *prm, hdk_amg **out)
+{
+   HDK_TRY(require_init());
+   if (!A0 || !prm || !out) return set_error(HDK_ERR_INVALID, "hdk_amg_setup: null argument");
+   if (prm->interp_type != 6) return set_error(HDK_ERR_UNSUPPORTED, "interpolation type %d: only extended+i (6) has a device kernel", prm->interp_type);
+   if (prm->trunc_factor != 0.0) return set_error(HDK_ERR_UNSUPPORTED, "interpolation trunc_factor != 0 is not supported on the device path");
+   g_timing = getenv("HDK_SETUP_TIMING") && atoi(getenv("HDK_SETUP_TIMING")) == 1;
+   if (g.nranks > 1) return setup_distributed(A0, prm, out);
+   return setup_serial(A0, prm, out, false);
+}
+
+int hdk_amg_num_levels(const hdk_amg *M) { return M ? M->nlev + (M->tail ? M->tail->nlev - M->tail_level : 0) : 0; }
 double hdk_amg_operator_complexity(const hdk_amg *M) { return M ? M->op_complexity : 0.0; }
 double hdk_amg_vcycle_bytes(const hdk_amg *M) { return M ? M->vcycle_bytes : 0.0; }
 
 int hdk_amg_level_info(const hdk_amg *M, int level, int64_t *rows, int64_t *nnz_A, int64_t *nnz_P)
 {
+   if (M && M->tail && level >= M->nlev) return hdk_amg_level_info(M->tail, level, rows, nnz_A, nnz_P);
    if (!M || level < 0 || level >= M->nlev) return set_error(HDK_ERR_INVALID, "level out of range");
    const AmgLevel &L = M->lev[(size_t)level];
    if (rows) *rows = L.n;

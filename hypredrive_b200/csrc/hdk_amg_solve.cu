@@ -98,35 +98,56 @@ static int coarse_solve(hdk_amg_s *M, int l, const double *f, double *u, double 
    return HDK_OK;
 }
 
-// One V-cycle.  Level-0 vectors are the caller's (f, u); u is also used as scratch.
-int amg_cycle(hdk_amg_s *M, const double *f0, double *u0, bool zero_guess, int fin, double *fin_out)
+// One V-cycle over levels [l0, nlev) of M.  Level-l0 vectors are the caller's (f, u); u is also
+// used as scratch.  With a replicated tail (N > 1) every level of M is a "fine" level and the
+// coarsest stage is: sum the restricted right-hand side over ranks, run the serial tail cycle.
+int amg_cycle(hdk_amg_s *M, const double *f0, double *u0, bool zero_guess, int fin, double *fin_out, int l0)
 {
-   const int            nl = M->nlev, Lc = nl - 1;
+   const int             nl = M->nlev;
+   const bool            has_tail = (M->tail != nullptr);
+   const int             nfine = has_tail ? nl : nl - 1; // levels [l0, nfine) smooth + restrict
    const hdk_amg_params &p = M->prm;
-   std::vector<double *> cur((size_t)nl), alt((size_t)nl);
-   std::vector<const double *> rhs((size_t)nl);
+   std::vector<double *> cur((size_t)nl + 1, nullptr), alt((size_t)nl + 1, nullptr);
+   std::vector<const double *> rhs((size_t)nl + 1, nullptr);
    bool                  fin_done = false;
-   // level-0 buffer parity so that the result lands in u0 without a copy (default sweeps)
+   if (has_tail && nl == 0)
    {
-      AmgLevel &L0 = M->lev[0];
+      // the whole hierarchy is replicated: gather the right-hand side, cycle, take my slice
+      HDK_TRY(vec_fill(M->full_f, 0.0, M->tail_n));
+      HDK_TRY(vec_copy(M->full_f + M->tail_off, f0, M->tail_cnt));
+      HDK_TRY(allreduce_dev(M->full_f, (int)M->tail_n));
+      if (!zero_guess)
+      {
+         HDK_TRY(vec_fill(M->full_u, 0.0, M->tail_n));
+         HDK_TRY(vec_copy(M->full_u + M->tail_off, u0, M->tail_cnt));
+         HDK_TRY(allreduce_dev(M->full_u, (int)M->tail_n));
+      }
+      HDK_TRY(amg_cycle(M->tail, M->full_f, M->full_u, zero_guess, FIN_NONE, nullptr, M->tail_level));
+      HDK_TRY(vec_copy(u0, M->full_u + M->tail_off, M->tail_cnt));
+      if (fin != FIN_NONE) HDK_TRY(vec_dot_dev(f0, u0, M->tail_cnt, fin, fin_out));
+      return HDK_OK;
+   }
+   // level-l0 buffer parity so that the result lands in u0 without a copy (default sweeps)
+   {
+      AmgLevel &L0 = M->lev[(size_t)l0];
       int       oop;
-      if (nl == 1) oop = 0;
+      if (nfine <= l0) oop = 0;
       else
       {
          int down_oop = zero_guess && is_jacobi(p.relax_down) ? (p.sweeps_down > 0 ? p.sweeps_down - 1 : 0) : p.sweeps_down;
          oop          = down_oop + p.sweeps_up;
       }
       bool start_in_u0 = zero_guess ? (oop % 2 == 0) : true;
-      cur[0] = start_in_u0 ? u0 : L0.t;
-      alt[0] = start_in_u0 ? L0.t : u0;
-      rhs[0] = f0;
+      cur[(size_t)l0] = start_in_u0 ? u0 : L0.t;
+      alt[(size_t)l0] = start_in_u0 ? L0.t : u0;
+      rhs[(size_t)l0] = f0;
    }
-   for (int l = 1; l < nl; l++) { cur[(size_t)l] = M->lev[(size_t)l].u; alt[(size_t)l] = M->lev[(size_t)l].t; rhs[(size_t)l] = M->lev[(size_t)l].f; }
+   for (int l = l0 + 1; l < nl; l++) { cur[(size_t)l] = M->lev[(size_t)l].u; alt[(size_t)l] = M->lev[(size_t)l].t; rhs[(size_t)l] = M->lev[(size_t)l].f; }
 
-   for (int l = 0; l < Lc; l++)
+   for (int l = l0; l < nfine; l++)
    {
       AmgLevel &L = M->lev[(size_t)l];
-      bool      zg = (l > 0) || zero_guess;
+      bool      zg = (l > l0) || zero_guess;
       for (int s = 0; s < p.sweeps_down; s++)
       {
          if (s == 0 && zg && is_jacobi(p.relax_down))
@@ -142,61 +163,69 @@ int amg_cycle(hdk_amg_s *M, const double *f0, double *u0, bool zero_guess, int f
       }
       if (p.sweeps_down == 0 && zg) HDK_TRY(vec_fill(cur[(size_t)l], 0.0, L.n));
       // residual into the spare buffer, restrict to the next level
-      SpmvArgs a;
       if (p.sweeps_down == 0 && zg)
       {
          HDK_TRY(vec_copy(alt[(size_t)l], rhs[(size_t)l], L.n));
       }
       else
       {
+         SpmvArgs a;
          a.x = cur[(size_t)l]; a.y = alt[(size_t)l]; a.b = rhs[(size_t)l];
          HDK_TRY(parcsr_matvec(*L.A, SPMV_RESIDUAL, a));
       }
       SpmvArgs rr;
-      rr.x = alt[(size_t)l]; rr.y = M->lev[(size_t)l + 1].f;
-      HDK_TRY(parcsr_matvec(*L.R, SPMV_SET, rr));
-   }
-   // coarsest level
-   {
-      double *res;
-      bool    zg = (Lc > 0) || zero_guess;
-      if (nl == 1 && !(M->ge_inv && M->ge_n == M->lev[0].n))
-      {
-         // single-level hierarchy without a dense factor: smoother sweeps on the caller's vectors
-         HDK_TRY(coarse_solve(M, 0, rhs[0], cur[0], alt[0], zg, &res));
-         if (res != u0) HDK_TRY(vec_copy(u0, res, M->lev[0].n));
-      }
+      rr.x = alt[(size_t)l];
+      if (l + 1 < nl) rr.y = M->lev[(size_t)l + 1].f;
       else
       {
-         HDK_TRY(coarse_solve(M, Lc, rhs[(size_t)Lc], cur[(size_t)Lc], alt[(size_t)Lc], zg, &res));
-         if (res != cur[(size_t)Lc]) std::swap(cur[(size_t)Lc], alt[(size_t)Lc]);
-         if (nl == 1 && res != u0) HDK_TRY(vec_copy(u0, res, M->lev[0].n));
+         // first replicated level: my rows of the coarse right-hand side go into the full vector
+         HDK_TRY(vec_fill(M->full_f, 0.0, M->tail_n));
+         rr.y = M->full_f + M->tail_off;
       }
+      HDK_TRY(parcsr_matvec(*L.R, SPMV_SET, rr));
    }
-   for (int l = Lc - 1; l >= 0; l--)
+   // coarsest stage
+   const double *coarse_sol = nullptr; // solution feeding the prolongation of level nfine-1
+   if (has_tail)
+   {
+      HDK_TRY(allreduce_dev(M->full_f, (int)M->tail_n));
+      HDK_TRY(amg_cycle(M->tail, M->full_f, M->full_u, true, FIN_NONE, nullptr, M->tail_level));
+      coarse_sol = M->full_u;
+   }
+   else
+   {
+      const int Lc = nl - 1;
+      double   *res;
+      bool      zg = (Lc > l0) || zero_guess;
+      HDK_TRY(coarse_solve(M, Lc, rhs[(size_t)Lc], cur[(size_t)Lc], alt[(size_t)Lc], zg, &res));
+      if (res != cur[(size_t)Lc]) std::swap(cur[(size_t)Lc], alt[(size_t)Lc]);
+      coarse_sol = cur[(size_t)Lc];
+   }
+   for (int l = nfine - 1; l >= l0; l--)
    {
       AmgLevel &L = M->lev[(size_t)l];
       // u += P e_c
       SpmvArgs a;
-      a.x = cur[(size_t)l + 1]; a.y = cur[(size_t)l];
+      a.x = (l + 1 < nl) ? cur[(size_t)l + 1] : coarse_sol;
+      a.y = cur[(size_t)l];
       HDK_TRY(parcsr_matvec(*L.P, SPMV_ADD, a));
       for (int s = 0; s < p.sweeps_up; s++)
       {
-         bool last = (l == 0 && s == p.sweeps_up - 1);
+         bool last = (l == l0 && s == p.sweeps_up - 1);
          int  f_   = (last && fin != FIN_NONE) ? fin : FIN_NONE;
          HDK_TRY(relax_sweep(M, l, p.relax_up, L.l1_up, rhs[(size_t)l], cur[(size_t)l], alt[(size_t)l], f_, fin_out));
          std::swap(cur[(size_t)l], alt[(size_t)l]);
          if (f_ != FIN_NONE) fin_done = true;
       }
    }
-   if (cur[0] != u0) HDK_TRY(vec_copy(u0, cur[0], M->lev[0].n));
-   if (fin != FIN_NONE && !fin_done) HDK_TRY(vec_dot_dev(f0, u0, M->lev[0].n, fin, fin_out));
+   if (cur[(size_t)l0] != u0) HDK_TRY(vec_copy(u0, cur[(size_t)l0], M->lev[(size_t)l0].n));
+   if (fin != FIN_NONE && !fin_done) HDK_TRY(vec_dot_dev(f0, u0, M->lev[(size_t)l0].n, fin, fin_out));
    return HDK_OK;
 }
 
 int amg_precond(hdk_amg_s *M, const double *r, double *z, int fin, double *fin_out)
 {
-   return amg_cycle(M, r, z, true, fin, fin_out);
+   return amg_cycle(M, r, z, true, fin, fin_out, 0);
 }
 
 } // namespace hdk
@@ -216,7 +245,7 @@ int hdk_amg_vcycle(hdk_amg *M, const double *f_d, double *u_d)
 {
    HDK_TRY(require_init());
    if (!M) return set_error(HDK_ERR_INVALID, "null hierarchy");
-   return amg_cycle(M, f_d, u_d, false, FIN_NONE, nullptr);
+   return amg_cycle(M, f_d, u_d, false, FIN_NONE, nullptr, 0);
 }
 
 // CUDA-event timing of one hot kernel, `reps` back-to-back launches (bench.py roofline leg)

@@ -24,6 +24,7 @@ struct NcclApi
    int (*AllGather)(const void *, void *, size_t, int, ncclComm_p, cudaStream_t) = nullptr;
    int (*Send)(const void *, size_t, int, int, ncclComm_p, cudaStream_t) = nullptr;
    int (*Recv)(void *, size_t, int, int, ncclComm_p, cudaStream_t) = nullptr;
+   int (*Broadcast)(const void *, void *, size_t, int, int, ncclComm_p, cudaStream_t) = nullptr;
    int (*GroupStart)() = nullptr;
    int (*GroupEnd)() = nullptr;
    const char *(*GetErrorString)(int) = nullptr;
@@ -47,7 +48,7 @@ static int nccl_load()
    if (!nccl.field) return set_error(HDK_ERR_COMM, "NCCL symbol %s missing", name)
    LD(GetUniqueId, "ncclGetUniqueId"); LD(CommInitRank, "ncclCommInitRank");
    LD(CommDestroy, "ncclCommDestroy"); LD(AllReduce, "ncclAllReduce"); LD(AllGather, "ncclAllGather");
-   LD(Send, "ncclSend"); LD(Recv, "ncclRecv"); LD(GroupStart, "ncclGroupStart");
+   LD(Broadcast, "ncclBroadcast"); LD(Send, "ncclSend"); LD(Recv, "ncclRecv"); LD(GroupStart, "ncclGroupStart");
    LD(GroupEnd, "ncclGroupEnd"); LD(GetErrorString, "ncclGetErrorString");
 #undef LD
    return HDK_OK;
@@ -65,6 +66,13 @@ int allreduce_dev(double *buf_d, int count)
 {
    if (g.nranks <= 1) return HDK_OK;
    HDK_NCCL(nccl.AllReduce(buf_d, buf_d, (size_t)count, NCCL_FLOAT64, NCCL_SUM, (ncclComm_p)g.nccl, g.stream));
+   return HDK_OK;
+}
+
+int bcast_bytes(void *buf_d, size_t bytes, int root)
+{
+   if (g.nranks <= 1 || bytes == 0) return HDK_OK;
+   HDK_NCCL(nccl.Broadcast(buf_d, buf_d, bytes, 0 /* ncclInt8 */, root, (ncclComm_p)g.nccl, g.stream));
    return HDK_OK;
 }
 
@@ -121,12 +129,15 @@ int build_halo_plan(hdk_csr_s &A, int64_t *uniq, int n_halo)
    if (g.nranks <= 1)
       return set_error(HDK_ERR_INVALID, "matrix has %d off-rank columns but the communicator has one rank", n_halo);
    std::vector<int64_t> starts;
-   HDK_TRY(allgather_i64_host(A.row_start, starts));
-   starts.push_back(A.global_rows);
+   HDK_TRY(allgather_i64_host(A.col_start, starts)); // partition of the COLUMN space
+   starts.push_back(A.global_cols);
    A.row_starts = starts;
    std::vector<int64_t> ids((size_t)n_halo);
-   HDK_CUDA(cudaMemcpyAsync(ids.data(), uniq, sizeof(int64_t) * (size_t)n_halo, cudaMemcpyDeviceToHost, g.stream));
-   HDK_CUDA(cudaStreamSynchronize(g.stream));
+   if (n_halo > 0)
+   {
+      HDK_CUDA(cudaMemcpyAsync(ids.data(), uniq, sizeof(int64_t) * (size_t)n_halo, cudaMemcpyDeviceToHost, g.stream));
+      HDK_CUDA(cudaStreamSynchronize(g.stream));
+   }
    std::vector<int> want((size_t)g.nranks, 0);
    for (int i = 0; i < n_halo; i++)
    {
@@ -160,7 +171,7 @@ int build_halo_plan(hdk_csr_s &A, int64_t *uniq, int n_halo)
    HDK_NCCL(nccl.GroupEnd());
    if (soff > 0)
    {
-      k_ids_to_local<<<cdiv(soff, 256), 256, 0, g.stream>>>(req, soff, A.row_start, H.send_idx);
+      k_ids_to_local<<<cdiv(soff, 256), 256, 0, g.stream>>>(req, soff, A.col_start, H.send_idx);
       HDK_LAUNCH_CHECK();
    }
    dfree(req);

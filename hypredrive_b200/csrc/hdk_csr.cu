@@ -28,7 +28,7 @@ __global__ void k_split_count(const int64_t *indptr, const int64_t *cols, int nr
 // (hypre IJ assembly / hypre_CSRMatrixReorder semantics: a swap, not a rotation)
 __global__ void k_split_fill(const int64_t *indptr, const int64_t *cols, const double *vals, int nrows,
                              int64_t rs, int64_t re, const int *rp_d, int *col_d, double *val_d,
-                             const int *rp_o, int64_t *gcol_o, double *val_o)
+                             const int *rp_o, int64_t *gcol_o, double *val_o, int square)
 {
    int r = blockIdx.x * blockDim.x + threadIdx.x;
    if (r >= nrows) return;
@@ -41,7 +41,7 @@ __global__ void k_split_fill(const int64_t *indptr, const int64_t *cols, const d
       if (c >= rs && c <= re)
       {
          int lc = (int)(c - rs);
-         if (lc == r && dpos < 0) dpos = pd;
+         if (square && lc == r && dpos < 0) dpos = pd;
          col_d[pd] = lc; val_d[pd] = vals[k]; pd++;
       }
       else { gcol_o[po] = c; val_o[po] = vals[k]; po++; }
@@ -78,8 +78,32 @@ int exclusive_scan_int(const int *in, int *out, int n)
 
 int build_halo_plan(hdk_csr_s &A, int64_t *gcol_sorted_unique, int n_halo); // hdk_comm.cu
 
-static int parcsr_from_device(int64_t rs, int64_t re, int64_t grows, const int64_t *indptr,
-                              const int64_t *cols, const double *vals, hdk_csr_s **out)
+// copy of the caller's rows with global columns, diagonal entry swapped to the front: kept at
+// N > 1 so that the multi-rank setup can reassemble the global operator in its original order
+__global__ void k_orig_diag_first(const int64_t *indptr, int64_t *cols, double *vals, int nrows, int64_t rs)
+{
+   int r = blockIdx.x * blockDim.x + threadIdx.x;
+   if (r >= nrows) return;
+   int64_t b = indptr[r], e = indptr[r + 1], me = rs + r;
+   for (int64_t k = b; k < e; k++)
+      if (cols[k] == me)
+      {
+         if (k != b)
+         {
+            int64_t tc = cols[b]; double tv = vals[b];
+            cols[b] = cols[k]; vals[b] = vals[k];
+            cols[k] = tc; vals[k] = tv;
+         }
+         break;
+      }
+}
+
+// Build the rank-local ParCSR block pair from rows [rs,re] with global columns.  Columns in
+// [cs,ce] (this rank's share of the column space) go to the diag block.  `distributed`: the
+// matrix is one slab of a matrix spread over all ranks (collective: every rank must call).
+int parcsr_build(int64_t rs, int64_t re, int64_t cs, int64_t ce, int64_t grows, int64_t gcols, bool square,
+                 bool distributed, bool keep_orig, const int64_t *indptr, const int64_t *cols, const double *vals,
+                 hdk_csr_s **out)
 {
    if (re < rs) return set_error(HDK_ERR_INVALID, "empty local row range [%lld,%lld]", (long long)rs, (long long)re);
    int64_t n64 = re - rs + 1;
@@ -87,12 +111,13 @@ static int parcsr_from_device(int64_t rs, int64_t re, int64_t grows, const int64
    int        n = (int)n64;
    hdk_csr_s *A = new hdk_csr_s();
    A->row_start = rs; A->row_end = re; A->global_rows = grows;
+   A->col_start = cs; A->col_end = ce; A->global_cols = gcols;
    int *cnt_d, *cnt_o, *rp_d, *rp_o;
    HDK_TRY(dalloc(&cnt_d, (size_t)n + 1));
    HDK_TRY(dalloc(&cnt_o, (size_t)n + 1));
    HDK_TRY(dalloc(&rp_d, (size_t)n + 1));
    HDK_TRY(dalloc(&rp_o, (size_t)n + 1));
-   k_split_count<<<cdiv(n + 1, 256), 256, 0, g.stream>>>(indptr, cols, n, rs, re, cnt_d, cnt_o);
+   k_split_count<<<cdiv(n + 1, 256), 256, 0, g.stream>>>(indptr, cols, n, cs, ce, cnt_d, cnt_o);
    HDK_LAUNCH_CHECK();
    HDK_TRY(exclusive_scan_int(cnt_d, rp_d, n + 1));
    HDK_TRY(exclusive_scan_int(cnt_o, rp_o, n + 1));
@@ -102,20 +127,21 @@ static int parcsr_from_device(int64_t rs, int64_t re, int64_t grows, const int64
    HDK_CUDA(cudaStreamSynchronize(g.stream));
    dfree(cnt_d); dfree(cnt_o);
    int nh_guess = tot[1];
-   HDK_TRY(csr_alloc(A->diag, n, n, tot[0]));
+   HDK_TRY(csr_alloc(A->diag, n, (int)(ce - cs + 1), tot[0]));
    HDK_TRY(csr_alloc(A->offd, n, 0, nh_guess));
    dfree(A->diag.rowptr); A->diag.rowptr = rp_d;
    dfree(A->offd.rowptr); A->offd.rowptr = rp_o;
    int64_t *gcol_o;
    HDK_TRY(dalloc(&gcol_o, (size_t)tot[1] + 1));
-   k_split_fill<<<cdiv(n, 256), 256, 0, g.stream>>>(indptr, cols, vals, n, rs, re, rp_d, A->diag.col,
-                                                    A->diag.val, rp_o, gcol_o, A->offd.val);
+   k_split_fill<<<cdiv(n, 256), 256, 0, g.stream>>>(indptr, cols, vals, n, cs, ce, rp_d, A->diag.col,
+                                                    A->diag.val, rp_o, gcol_o, A->offd.val, square ? 1 : 0);
    HDK_LAUNCH_CHECK();
    int n_halo = 0;
+   int64_t *uniq = nullptr;
    if (tot[1] > 0)
    {
       // sorted unique global ids of the off-rank columns -> col_map_offd
-      int64_t *sorted, *uniq;
+      int64_t *sorted;
       int     *nsel;
       HDK_TRY(dalloc(&sorted, (size_t)tot[1]));
       HDK_TRY(dalloc(&uniq, (size_t)tot[1]));
@@ -133,15 +159,20 @@ static int parcsr_from_device(int64_t rs, int64_t re, int64_t grows, const int64
       HDK_LAUNCH_CHECK();
       dfree(tmp); dfree(sorted); dfree(nsel);
       A->offd.ncols = n_halo;
-      int rc = build_halo_plan(*A, uniq, n_halo);
+   }
+   if (distributed && g.nranks > 1)
+   {
+      int rc = build_halo_plan(*A, uniq, n_halo); // collective, also with n_halo == 0
       if (rc != HDK_OK) return rc;
    }
+   else if (tot[1] > 0)
+      return set_error(HDK_ERR_INVALID, "matrix has %d off-rank columns but is not distributed", n_halo);
    dfree(gcol_o);
    HDK_TRY(csr_analyze(A->diag));
    if (A->offd.nnz > 0) HDK_TRY(csr_analyze(A->offd));
    // global nnz
    double loc = (double)tot[0] + (double)tot[1];
-   if (g.nranks > 1)
+   if (distributed && g.nranks > 1)
    {
       HDK_CUDA(cudaMemcpyAsync(g.dscal + S_TMP0, &loc, sizeof(double), cudaMemcpyHostToDevice, g.stream));
       HDK_TRY(allreduce_dev(g.dscal + S_TMP0, 1));
@@ -149,8 +180,27 @@ static int parcsr_from_device(int64_t rs, int64_t re, int64_t grows, const int64
       HDK_CUDA(cudaStreamSynchronize(g.stream));
    }
    A->global_nnz = (int64_t)loc;
+   if (keep_orig && distributed && g.nranks > 1)
+   {
+      int64_t nnz = (int64_t)tot[0] + tot[1];
+      HDK_TRY(dalloc(&A->orig_indptr, (size_t)n + 1));
+      HDK_TRY(dalloc(&A->orig_cols, (size_t)nnz + 1));
+      HDK_TRY(dalloc(&A->orig_vals, (size_t)nnz + 1));
+      HDK_CUDA(cudaMemcpyAsync(A->orig_indptr, indptr, sizeof(int64_t) * ((size_t)n + 1), cudaMemcpyDeviceToDevice, g.stream));
+      HDK_CUDA(cudaMemcpyAsync(A->orig_cols, cols, sizeof(int64_t) * (size_t)nnz, cudaMemcpyDeviceToDevice, g.stream));
+      HDK_CUDA(cudaMemcpyAsync(A->orig_vals, vals, sizeof(double) * (size_t)nnz, cudaMemcpyDeviceToDevice, g.stream));
+      k_orig_diag_first<<<cdiv(n, 256), 256, 0, g.stream>>>(A->orig_indptr, A->orig_cols, A->orig_vals, n, rs);
+      HDK_LAUNCH_CHECK();
+      A->orig_nnz = nnz;
+   }
    *out = A;
    return HDK_OK;
+}
+
+static int parcsr_from_device(int64_t rs, int64_t re, int64_t grows, const int64_t *indptr, const int64_t *cols,
+                              const double *vals, hdk_csr_s **out)
+{
+   return parcsr_build(rs, re, rs, re, grows, grows, true, true, true, indptr, cols, vals, out);
 }
 
 // ---- y = op(A) x with halo exchange: diag kernel overlaps the exchange, offd kernel follows
@@ -160,8 +210,9 @@ __global__ void k_offd_correct(const int *rowptr, const int *col, const double *
 
 int parcsr_matvec(const hdk_csr_s &A, int mode, SpmvArgs a)
 {
-   bool has_offd = (A.offd.nnz > 0 && g.nranks > 1);
-   if (!has_offd) return spmv_launch(A.diag, mode, a);
+   // p2p exchange partners must match: a rank takes part when it sends OR receives
+   bool exch = g.nranks > 1 && (A.halo.n_send > 0 || A.halo.n_halo > 0);
+   if (!exch) return spmv_launch(A.diag, mode, a);
    // start the exchange, run the diag block (no fused dot: the result is not final yet)
    HDK_TRY(halo_exchange_begin(A, a.x));
    SpmvArgs ad = a;
@@ -169,10 +220,13 @@ int parcsr_matvec(const hdk_csr_s &A, int mode, SpmvArgs a)
    HDK_TRY(spmv_launch(A.diag, mode, ad));
    HDK_TRY(halo_exchange_end(A));
    // offd contribution: y_i += sign * sum_o (linear correction of the diag-only epilogue)
-   int grid = cdiv(A.offd.nrows, 256);
-   k_offd_correct<<<grid, 256, 0, g.stream>>>(A.offd.rowptr, A.offd.col, A.offd.val, A.offd.nrows,
-                                              A.halo.x_halo, a.y, a.d, a.w, mode, a.alpha);
-   HDK_LAUNCH_CHECK();
+   if (A.offd.nnz > 0)
+   {
+      int grid = cdiv(A.offd.nrows, 256);
+      k_offd_correct<<<grid, 256, 0, g.stream>>>(A.offd.rowptr, A.offd.col, A.offd.val, A.offd.nrows,
+                                                 A.halo.x_halo, a.y, a.d, a.w, mode, a.alpha);
+      HDK_LAUNCH_CHECK();
+   }
    if (a.fin != FIN_NONE && a.dotv)
    {
       HDK_TRY(vec_dot_dev(a.dotv, a.y, A.diag.nrows, a.fin, a.fin_out));
@@ -397,6 +451,7 @@ int hdk_csr_destroy(hdk_csr *A)
    {
       csr_free(A->diag); csr_free(A->offd);
       dfree(A->halo.col_map); dfree(A->halo.send_idx); dfree(A->halo.send_buf); dfree(A->halo.x_halo);
+      dfree(A->orig_indptr); dfree(A->orig_cols); dfree(A->orig_vals);
    }
    delete A;
    return HDK_OK;

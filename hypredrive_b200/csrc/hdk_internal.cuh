@@ -181,6 +181,10 @@ struct HaloPlan
 struct hdk_csr_s
 {
    int64_t       row_start = 0, row_end = -1, global_rows = 0, global_nnz = 0;
+   int64_t       col_start = 0, col_end = -1, global_cols = 0; // this rank's share of the column space
+   int64_t      *orig_indptr = nullptr, *orig_cols = nullptr;  // N > 1: caller's rows, global columns
+   double       *orig_vals = nullptr;
+   int64_t       orig_nnz = 0;
    hdk::DevCSR   diag, offd;
    hdk::HaloPlan halo;
    std::vector<int64_t> row_starts; // partition (nranks+1), host
@@ -188,6 +192,11 @@ struct hdk_csr_s
 
 namespace hdk {
 int parcsr_matvec(const hdk_csr_s &A, int mode, SpmvArgs a); // halo exchange + diag + offd
+int parcsr_build(int64_t rs, int64_t re, int64_t cs, int64_t ce, int64_t grows, int64_t gcols, bool square,
+                 bool distributed, bool keep_orig, const int64_t *indptr, const int64_t *cols, const double *vals,
+                 hdk_csr_s **out);
+int bcast_bytes(void *buf_d, size_t bytes, int root);                 // NCCL broadcast on the compute stream
+int allgather_i64_host(int64_t mine, std::vector<int64_t> &all);
 int halo_exchange_begin(const hdk_csr_s &A, const double *x);
 int halo_exchange_end(const hdk_csr_s &A);
 
