@@ -291,15 +291,15 @@ def ours(args):
     peak, peak_src = measured_peaks()
     roof = None
     extra_kernels = {}
+    ms, by = C.c_double(), C.c_double()
+    names = {0: "spmv", 1: "l1_jacobi_fused", 2: "residual", 3: "pcg_xr_update", 4: "vcycle"}
+    for kid, name in names.items():          # collective at N > 1 (halo exchange inside): every rank runs it
+        hdk.check(hdk.lib().hdk_time_kernel(hA, hM, kid, 20, C.byref(ms), C.byref(by)))
+        extra_kernels[name] = {"ms": ms.value, "GBps": by.value / ms.value / 1e6, "bytes": by.value}
     if rank == 0:
-        ms, by = C.c_double(), C.c_double()
-        names = {0: "spmv", 1: "l1_jacobi_fused", 2: "residual", 3: "pcg_xr_update", 4: "vcycle"}
-        for kid, name in names.items():
-            hdk.check(hdk.lib().hdk_time_kernel(hA, hM, kid, 20, C.byref(ms), C.byref(by)))
-            extra_kernels[name] = {"ms": ms.value, "GBps": by.value / ms.value / 1e6, "bytes": by.value}
         k0 = extra_kernels["spmv"]
         roof = {"bound": "hbm", "achieved": k0["GBps"], "peak": peak, "unit": "GB/s", "frac": k0["GBps"] / peak,
-                "traffic": None, "kernel": "k_spmv_stream<SET> (fine level, y = A x)", "peak_source": peak_src,
+                "traffic": None, "kernel": "k_spmv_tma<SET> (fine level, y = A x, per GPU)", "peak_source": peak_src,
                 "algorithmic_bytes": k0["bytes"], "ms": k0["ms"]}
     if dist is not None:
         dist.barrier()

@@ -78,6 +78,13 @@ int exclusive_scan_int(const int *in, int *out, int n)
 
 int build_halo_plan(hdk_csr_s &A, int64_t *gcol_sorted_unique, int n_halo); // hdk_comm.cu
 
+// rows with at least one off-rank entry (hypre keeps the same list as offd "rownnz")
+__global__ void k_offd_rows(const int *rowptr, int nrows, int *list, int *count)
+{
+   int r = blockIdx.x * blockDim.x + threadIdx.x;
+   if (r < nrows && rowptr[r + 1] > rowptr[r]) list[atomicAdd(count, 1)] = r;
+}
+
 // copy of the caller's rows with global columns, diagonal entry swapped to the front: kept at
 // N > 1 so that the multi-rank setup can reassemble the global operator in its original order
 __global__ void k_orig_diag_first(const int64_t *indptr, int64_t *cols, double *vals, int nrows, int64_t rs)
@@ -169,7 +176,16 @@ int parcsr_build(int64_t rs, int64_t re, int64_t cs, int64_t ce, int64_t grows, 
       return set_error(HDK_ERR_INVALID, "matrix has %d off-rank columns but is not distributed", n_halo);
    dfree(gcol_o);
    HDK_TRY(csr_analyze(A->diag));
-   if (A->offd.nnz > 0) HDK_TRY(csr_analyze(A->offd));
+   if (A->offd.nnz > 0)
+   {
+      int *cnt = reinterpret_cast<int *>(g.dscal + S_TMP2);
+      HDK_TRY(dalloc(&A->offd_rows, (size_t)(A->offd.nnz < n ? A->offd.nnz : n) + 1));
+      HDK_CUDA(cudaMemsetAsync(cnt, 0, sizeof(int), g.stream));
+      k_offd_rows<<<cdiv(n, 256), 256, 0, g.stream>>>(A->offd.rowptr, n, A->offd_rows, cnt);
+      HDK_LAUNCH_CHECK();
+      HDK_CUDA(cudaMemcpyAsync(&A->n_offd_rows, cnt, sizeof(int), cudaMemcpyDeviceToHost, g.stream));
+      HDK_CUDA(cudaStreamSynchronize(g.stream));
+   }
    // global nnz
    double loc = (double)tot[0] + (double)tot[1];
    if (distributed && g.nranks > 1)
@@ -204,7 +220,7 @@ static int parcsr_from_device(int64_t rs, int64_t re, int64_t grows, const int64
 }
 
 // ---- y = op(A) x with halo exchange: diag kernel overlaps the exchange, offd kernel follows
-__global__ void k_offd_correct(const int *rowptr, const int *col, const double *val, int nrows,
+__global__ void k_offd_correct(const int *rows, const int *rowptr, const int *col, const double *val, int nrows,
                                const double *xh, double *y, const double *d, double w, int mode,
                                double alpha);
 
@@ -222,8 +238,8 @@ int parcsr_matvec(const hdk_csr_s &A, int mode, SpmvArgs a)
    // offd contribution: y_i += sign * sum_o (linear correction of the diag-only epilogue)
    if (A.offd.nnz > 0)
    {
-      int grid = cdiv(A.offd.nrows, 256);
-      k_offd_correct<<<grid, 256, 0, g.stream>>>(A.offd.rowptr, A.offd.col, A.offd.val, A.offd.nrows,
+      int grid = cdiv(A.n_offd_rows, 128);
+      k_offd_correct<<<grid, 128, 0, g.stream>>>(A.offd_rows, A.offd.rowptr, A.offd.col, A.offd.val, A.n_offd_rows,
                                                  A.halo.x_halo, a.y, a.d, a.w, mode, a.alpha);
       HDK_LAUNCH_CHECK();
    }
@@ -234,14 +250,14 @@ int parcsr_matvec(const hdk_csr_s &A, int mode, SpmvArgs a)
    return HDK_OK;
 }
 
-__global__ void k_offd_correct(const int *rowptr, const int *col, const double *val, int nrows,
+__global__ void k_offd_correct(const int *rows, const int *rowptr, const int *col, const double *val, int nrows,
                                const double *xh, double *y, const double *d, double w, int mode,
                                double alpha)
 {
-   int r = blockIdx.x * blockDim.x + threadIdx.x;
-   if (r >= nrows) return;
+   int i = blockIdx.x * blockDim.x + threadIdx.x;
+   if (i >= nrows) return;
+   int r = rows[i];
    int s = rowptr[r], e = rowptr[r + 1];
-   if (s == e) return;
    double acc = 0.0;
    for (int k = s; k < e; k++) acc += val[k] * xh[col[k]];
    switch (mode)
@@ -451,7 +467,7 @@ int hdk_csr_destroy(hdk_csr *A)
    {
       csr_free(A->diag); csr_free(A->offd);
       dfree(A->halo.col_map); dfree(A->halo.send_idx); dfree(A->halo.send_buf); dfree(A->halo.x_halo);
-      dfree(A->orig_indptr); dfree(A->orig_cols); dfree(A->orig_vals);
+      dfree(A->orig_indptr); dfree(A->orig_cols); dfree(A->orig_vals); dfree(A->offd_rows);
    }
    delete A;
    return HDK_OK;

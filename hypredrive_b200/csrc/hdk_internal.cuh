@@ -185,6 +185,8 @@ struct hdk_csr_s
    int64_t      *orig_indptr = nullptr, *orig_cols = nullptr;  // N > 1: caller's rows, global columns
    double       *orig_vals = nullptr;
    int64_t       orig_nnz = 0;
+   int          *offd_rows = nullptr; // rows with off-rank entries
+   int           n_offd_rows = 0;
    hdk::DevCSR   diag, offd;
    hdk::HaloPlan halo;
    std::vector<int64_t> row_starts; // partition (nranks+1), host

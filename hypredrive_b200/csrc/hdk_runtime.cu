@@ -62,7 +62,11 @@ int hdk_init(int device)
    HDK_CUDA(cudaGetDeviceProperties(&prop, device));
    g.sm_count = prop.multiProcessorCount;
    HDK_CUDA(cudaStreamCreateWithFlags(&g.stream, cudaStreamNonBlocking));
-   HDK_CUDA(cudaStreamCreateWithFlags(&g.comm_stream, cudaStreamNonBlocking));
+   // halo exchange stream: highest priority so NCCL's few CTAs are placed before the persistent
+   // SpMV grid that becomes runnable at the same moment (both wait for the pack kernel)
+   int prio_lo = 0, prio_hi = 0;
+   HDK_CUDA(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+   HDK_CUDA(cudaStreamCreateWithPriority(&g.comm_stream, cudaStreamNonBlocking, prio_hi));
    HDK_CUDA(cudaEventCreate(&g.ev_a));
    HDK_CUDA(cudaEventCreate(&g.ev_b));
    HDK_CUDA(cudaEventCreateWithFlags(&g.ev_scal, cudaEventDisableTiming));
