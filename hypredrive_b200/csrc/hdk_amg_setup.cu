@@ -148,6 +148,24 @@ __device__ __forceinline__ int hmap_insert(int2 *tab, int cap, int key, int val)
    }
 }
 
+// shared-memory table shared by the lanes of one warp: concurrent inserts of DISTINCT keys
+__device__ __forceinline__ int wt_find_or_insert(int *keys, int cap, int key, bool &isnew)
+{
+   unsigned h = hslot(key, cap), mask = (unsigned)cap - 1;
+   while (true)
+   {
+      int k = keys[h];
+      if (k == key) { isnew = false; return (int)h; }
+      if (k == -1)
+      {
+         int old = atomicCAS(keys + h, -1, key);
+         if (old == -1) { isnew = true; return (int)h; }
+         if (old == key) { isnew = false; return (int)h; }
+      }
+      h = (h + 1) & mask;
+   }
+}
+
 // =====================================================================================
 // strength of connection (hypre_BoomerAMGCreateS)
 // =====================================================================================
@@ -361,12 +379,12 @@ __global__ void k_cf_flag(const int *cf, int n, int *flag)
 // extended+i interpolation (hypre_BoomerAMGBuildExtPIInterp) + truncation
 // (hypre_BoomerAMGInterpTruncation with hypre_qsort2abs): one thread per row
 // =====================================================================================
-__global__ void k_interp_cap(const int *srp, const int *scol, const int *cf, int n, int *cap)
+__global__ void k_interp_cap(const int *srp, const int *scol, const int *cf, int n, int *cap, const int *slow)
 {
    int i = blockIdx.x * blockDim.x + threadIdx.x;
    if (i > n) return;
    int c = 0;
-   if (i < n && cf[i] < 0 && cf[i] != SF_PT)
+   if (i < n && slow[i] && cf[i] < 0 && cf[i] != SF_PT)
    {
       int ub = 0;
       for (int k = srp[i]; k < srp[i + 1]; k++)
@@ -381,10 +399,10 @@ __global__ void k_interp_cap(const int *srp, const int *scol, const int *cf, int
 }
 
 __global__ void k_interp_count(const int *srp, const int *scol, const int *cf, int row0, int row1,
-                               const int64_t *off, int *keys, int max_elmts, int *cnt, int *rowlen)
+                               const int64_t *off, int *keys, int max_elmts, int *cnt, int *rowlen, const int *slow)
 {
    int i = row0 + blockIdx.x * blockDim.x + threadIdx.x;
-   if (i >= row1) return;
+   if (i >= row1 || !slow[i]) return;
    int c = 0;
    if (cf[i] > 0) c = 1;
    else if (cf[i] != SF_PT)
@@ -407,12 +425,12 @@ __global__ void k_interp_count(const int *srp, const int *scol, const int *cf, i
    rowlen[i] = (max_elmts > 0 && c > max_elmts) ? max_elmts : c;
 }
 
-__global__ void k_interp_cap2(const int *srp, const int *cf, const int *cnt, int n, int *cap2)
+__global__ void k_interp_cap2(const int *srp, const int *cf, const int *cnt, int n, int *cap2, const int *slow)
 {
    int i = blockIdx.x * blockDim.x + threadIdx.x;
    if (i > n) return;
    int c = 0;
-   if (i < n && cf[i] < 0 && cf[i] != SF_PT) c = pow2ceil(2 * (cnt[i] + (srp[i + 1] - srp[i])));
+   if (i < n && slow[i] && cf[i] < 0 && cf[i] != SF_PT) c = pow2ceil(2 * (cnt[i] + (srp[i + 1] - srp[i])));
    cap2[i] = c;
 }
 
@@ -458,10 +476,10 @@ __device__ void qsort2abs_dev(int *v, double *w, int n)
 __global__ void k_interp_fill(const int *arp, const int *acol, const double *aval, const int *srp, const int *scol,
                               const int *cf, const int *f2c, int row0, int row1, const int *cnt,
                               const int64_t *hoff, int2 *htab, const int64_t *loff, int *lcol, double *lval,
-                              int max_elmts, const int *prp, int *pcol, double *pval)
+                              int max_elmts, const int *prp, int *pcol, double *pval, const int *slow)
 {
    int i = row0 + blockIdx.x * blockDim.x + threadIdx.x;
-   if (i >= row1) return;
+   if (i >= row1 || !slow[i]) return;
    int p0 = prp[i];
    if (cf[i] > 0) { pcol[p0] = f2c[i]; pval[p0] = 1.0; return; }
    if (cf[i] == SF_PT) return;
@@ -546,6 +564,189 @@ __global__ void k_interp_fill(const int *arp, const int *acol, const double *ava
    for (int k = 0; k < len; k++) { pcol[p0 + k] = f2c[lc[k]]; pval[p0 + k] = lv[k]; }
 }
 
+// ---- warp-per-row extended+i interpolation (shared-memory hash + candidate list) ----------
+// Same sequence of operations as the one-thread version (and the oracle): C-hat is discovered
+// in hypre's order (chunks of 32 candidates, slots assigned in lane order), the weight loop
+// runs sequentially over the row of A, lanes only parallelise the hash look-ups of the inner
+// loops, and every floating-point sum is accumulated in CSR order.
+constexpr int IW_CAP   = 256; // hash slots per warp: C-hat plus the strong F neighbours
+constexpr int IW_LIST  = 120; // longest C-hat handled here
+constexpr int IW_WARPS = 8;
+
+__device__ __forceinline__ int wt_find(const int *keys, const int *idx, int cap, int key)
+{
+   unsigned h = hslot(key, cap), mask = (unsigned)cap - 1;
+   while (true)
+   {
+      int k = keys[h];
+      if (k == key) return idx[h];
+      if (k == -1) return -1;
+      h = (h + 1) & mask;
+   }
+}
+
+template <bool FILL>
+__global__ void __launch_bounds__(32 * IW_WARPS) k_interp_warp(const int *arp, const int *acol, const double *aval,
+                                                               const int *srp, const int *scol, const int *cf,
+                                                               const int *f2c, int n, int max_elmts, int *cnt, int *rowlen,
+                                                               int *slow, const int *prp, int *pcol, double *pval, int force_slow)
+{
+   __shared__ int    s_keys[IW_WARPS][IW_CAP];
+   __shared__ int    s_idx[IW_WARPS][IW_CAP];
+   __shared__ int    s_lc[IW_WARPS][IW_LIST + 8];
+   __shared__ double s_lv[IW_WARPS][IW_LIST + 8];
+   const int      lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+   const unsigned FULL = 0xffffffffu, LT = (1u << lane) - 1u;
+   const int      i = blockIdx.x * IW_WARPS + wid;
+   if (i >= n) return;
+   const int ci = cf[i];
+   if (ci > 0)
+   {
+      if (lane == 0)
+      {
+         if (!FILL) { cnt[i] = 1; rowlen[i] = 1; slow[i] = 0; }
+         else { pcol[prp[i]] = f2c[i]; pval[prp[i]] = 1.0; }
+      }
+      return;
+   }
+   if (ci == SF_PT) { if (!FILL && lane == 0) { cnt[i] = 0; rowlen[i] = 0; slow[i] = 0; } return; }
+   if (FILL && slow[i]) return;
+   if (!FILL && force_slow) { if (lane == 0) { slow[i] = 1; cnt[i] = 0; rowlen[i] = 0; } return; }
+   int *keys = s_keys[wid], *idx = s_idx[wid], *lc = s_lc[wid];
+   double *lv = s_lv[wid];
+   for (int h = lane; h < IW_CAP; h += 32) keys[h] = -1;
+   __syncwarp();
+   int  nC = 0, nins = 0;
+   bool overflow = false;
+   // ---- discovery of C-hat_i; strong F neighbours are tagged with idx = -2
+   for (int jj = srp[i]; jj < srp[i + 1] && !overflow; jj++)
+   {
+      const int i1 = scol[jj], c1 = cf[i1];
+      if (c1 > 0)
+      {
+         bool isnew = false;
+         int  h = 0;
+         if (lane == 0) h = wt_find_or_insert(keys, IW_CAP, i1, isnew);
+         unsigned nm = __ballot_sync(FULL, lane == 0 && isnew);
+         if (nm)
+         {
+            if (nC >= IW_LIST) overflow = true;
+            else if (lane == 0) { idx[h] = nC; lc[nC] = i1; lv[nC] = 0.0; }
+            nC++; nins++;
+         }
+      }
+      else if (c1 != SF_PT)
+      {
+         if (lane == 0) { bool nw; int h = wt_find_or_insert(keys, IW_CAP, i1, nw); idx[h] = -2; }
+         nins++;
+         __syncwarp();
+         for (int base = srp[i1]; base < srp[i1 + 1] && !overflow; base += 32)
+         {
+            const int  kk = base + lane;
+            const int  k1 = kk < srp[i1 + 1] ? scol[kk] : -1;
+            const bool act = k1 >= 0 && cf[k1] > 0;
+            bool       isnew = false;
+            int        h = 0;
+            if (act) h = wt_find_or_insert(keys, IW_CAP, k1, isnew);
+            const unsigned nm = __ballot_sync(FULL, act && isnew);
+            const int      add = __popc(nm);
+            if (nC + add > IW_LIST || nins + add > (IW_CAP * 3) / 4) overflow = true;
+            else if (act && isnew) { int s = nC + __popc(nm & LT); idx[h] = s; lc[s] = k1; lv[s] = 0.0; }
+            nC += add; nins += add;
+            __syncwarp();
+         }
+      }
+      __syncwarp();
+   }
+   if (!FILL)
+   {
+      if (lane == 0)
+      {
+         slow[i]   = overflow ? 1 : 0;
+         cnt[i]    = overflow ? 0 : nC;
+         rowlen[i] = overflow ? 0 : ((max_elmts > 0 && nC > max_elmts) ? max_elmts : nC);
+      }
+      return;
+   }
+   // ---- weights: sequential over the row of A, lanes over the inner look-ups
+   double diagonal = aval[arp[i]];
+   for (int jj = arp[i] + 1; jj < arp[i + 1]; jj++)
+   {
+      const int    i1 = acol[jj];
+      const double a  = aval[jj];
+      const int    m  = wt_find(keys, idx, IW_CAP, i1);
+      if (m >= 0) { if (lane == 0) lv[m] = __dadd_rn(lv[m], a); }
+      else if (m == -2)
+      {
+         const double sgn = aval[arp[i1]] < 0 ? -1.0 : 1.0;
+         const int    b1 = arp[i1] + 1, e1 = arp[i1 + 1];
+         double       sum = 0.0;
+         for (int base = b1; base < e1; base += 32)
+         {
+            const int    j1 = base + lane;
+            const bool   v1 = j1 < e1;
+            const int    i2 = v1 ? acol[j1] : -1;
+            const double v  = v1 ? aval[j1] : 0.0;
+            const bool   q  = v1 && (sgn * v < 0) && (i2 == i || wt_find(keys, idx, IW_CAP, i2) >= 0);
+            unsigned     rem = __ballot_sync(FULL, q);
+            while (rem) { int src = __ffs(rem) - 1; sum = __dadd_rn(sum, __shfl_sync(FULL, v, src)); rem &= rem - 1u; }
+         }
+         if (sum != 0.0)
+         {
+            const double distribute = __ddiv_rn(a, sum);
+            for (int base = b1; base < e1; base += 32)
+            {
+               const int    j1 = base + lane;
+               const bool   v1 = j1 < e1;
+               const int    i2 = v1 ? acol[j1] : -1;
+               const double v  = v1 ? aval[j1] : 0.0;
+               const bool   neg = v1 && (sgn * v < 0);
+               const int    m2 = neg ? wt_find(keys, idx, IW_CAP, i2) : -1;
+               const double t  = __dmul_rn(distribute, v);
+               if (neg && m2 >= 0) lv[m2] = __dadd_rn(lv[m2], t);
+               const unsigned dm = __ballot_sync(FULL, neg && i2 == i);
+               if (dm) diagonal = __dadd_rn(diagonal, __shfl_sync(FULL, t, __ffs(dm) - 1));
+            }
+         }
+         else diagonal = __dadd_rn(diagonal, a);
+      }
+      else if (cf[i1] != SF_PT) diagonal = __dadd_rn(diagonal, a);
+      __syncwarp();
+   }
+   if (diagonal != 0.0)
+   {
+      const double nd = -diagonal;
+      for (int k = lane; k < nC; k += 32) lv[k] = __ddiv_rn(lv[k], nd);
+   }
+   __syncwarp();
+   int len = nC;
+   if (max_elmts > 0 && nC > max_elmts)
+   {
+      if (lane == 0)
+      {
+         double row_sum = 0.0, scale = 0.0;
+         for (int k = 0; k < nC; k++) row_sum = __dadd_rn(row_sum, lv[k]);
+         qsort2abs_dev(lc, lv, nC);
+         for (int k = 0; k < max_elmts; k++) scale = __dadd_rn(scale, lv[k]);
+         if (scale != 0.0 && scale != row_sum)
+         {
+            scale = __ddiv_rn(row_sum, scale);
+            for (int k = 0; k < max_elmts; k++) lv[k] = __dmul_rn(lv[k], scale);
+         }
+      }
+      len = max_elmts;
+      __syncwarp();
+   }
+   const int p0 = prp[i];
+   for (int k = lane; k < len; k += 32) { pcol[p0 + k] = f2c[lc[k]]; pval[p0 + k] = lv[k]; }
+}
+
+__global__ void k_mask_cnt(const int *cnt, const int *slow, int n, int *out)
+{
+   int i = blockIdx.x * blockDim.x + threadIdx.x;
+   if (i <= n) out[i] = (i < n && slow[i]) ? cnt[i] : 0;
+}
+
 __global__ void k_cf_reset_sf(int *cf, int n)
 {
    int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -562,8 +763,16 @@ static int build_interp(const DevCSR &A, const DevCSR &S, int *cf, const int *f2
    HDK_TRY(dalloc(&rowlen, (size_t)n + 1));
    HDK_TRY(dalloc(&prp, (size_t)n + 1));
    HDK_TRY(dalloc(&off, (size_t)n + 1));
-   // pass 1: |C-hat_i| with hash sets sized from an upper bound, chunked to bound scratch
-   k_interp_cap<<<cdiv(n + 1, 256), 256, 0, g.stream>>>(S.rowptr, S.col, cf, n, cap);
+   int *slow;
+   HDK_TRY(dalloc(&slow, (size_t)n + 1));
+   // short rows (fine stencil levels): one thread per row beats one warp per row
+   const int force_slow = ((double)A.nnz / (n > 0 ? n : 1)) <= 10.0 ? 1 : 0;
+   // pass 1a: |C-hat_i| by the warp kernel (shared-memory hash); rows it cannot hold are flagged
+   k_interp_warp<false><<<cdiv(n, IW_WARPS), 32 * IW_WARPS, 0, g.stream>>>(A.rowptr, A.col, A.val, S.rowptr, S.col, cf, f2c, n,
+                                                                          max_elmts, cnt, rowlen, slow, nullptr, nullptr, nullptr, force_slow);
+   HDK_LAUNCH_CHECK();
+   // pass 1b: flagged rows, one thread per row, hash sets in global scratch (chunked)
+   k_interp_cap<<<cdiv(n + 1, 256), 256, 0, g.stream>>>(S.rowptr, S.col, cf, n, cap, slow);
    HDK_LAUNCH_CHECK();
    HDK_TRY(exclusive_scan_i64(cap, off, n + 1));
    std::vector<int> bounds;
@@ -577,7 +786,7 @@ static int build_interp(const DevCSR &A, const DevCSR &S, int *cf, const int *f2
          int r0 = bounds[c], r1 = bounds[c + 1];
          if (r1 <= r0) continue;
          HDK_CUDA(cudaMemsetAsync(keys, 0xFF, sizeof(int) * ((size_t)maxsz + 4), g.stream));
-         k_interp_count<<<cdiv(r1 - r0, 128), 128, 0, g.stream>>>(S.rowptr, S.col, cf, r0, r1, off, keys, max_elmts, cnt, rowlen);
+         k_interp_count<<<cdiv(r1 - r0, 128), 128, 0, g.stream>>>(S.rowptr, S.col, cf, r0, r1, off, keys, max_elmts, cnt, rowlen, slow);
          HDK_LAUNCH_CHECK();
       }
       dfree(keys);
@@ -597,10 +806,15 @@ static int build_interp(const DevCSR &A, const DevCSR &S, int *cf, const int *f2
    // pass 2: weights.  hash maps sized from the exact counts, candidate lists in scratch
    int64_t *loff;
    HDK_TRY(dalloc(&loff, (size_t)n + 1));
-   k_interp_cap2<<<cdiv(n + 1, 256), 256, 0, g.stream>>>(S.rowptr, cf, cnt, n, cap);
+   k_interp_warp<true><<<cdiv(n, IW_WARPS), 32 * IW_WARPS, 0, g.stream>>>(A.rowptr, A.col, A.val, S.rowptr, S.col, cf, f2c, n,
+                                                                         max_elmts, cnt, rowlen, slow, prp, P.col, P.val, force_slow);
+   HDK_LAUNCH_CHECK();
+   k_interp_cap2<<<cdiv(n + 1, 256), 256, 0, g.stream>>>(S.rowptr, cf, cnt, n, cap, slow);
    HDK_LAUNCH_CHECK();
    HDK_TRY(exclusive_scan_i64(cap, off, n + 1));
-   HDK_TRY(exclusive_scan_i64(cnt, loff, n + 1));
+   k_mask_cnt<<<cdiv(n + 1, 256), 256, 0, g.stream>>>(cnt, slow, n, rowlen); // candidate lists only for the fallback rows
+   HDK_LAUNCH_CHECK();
+   HDK_TRY(exclusive_scan_i64(rowlen, loff, n + 1));
    HDK_TRY(plan_chunks(off, n, bounds, maxsz));
    {
       int64_t maxl = 0;
@@ -624,14 +838,14 @@ static int build_interp(const DevCSR &A, const DevCSR &S, int *cf, const int *f2
          if (r1 <= r0) continue;
          HDK_CUDA(cudaMemsetAsync(htab, 0xFF, sizeof(int2) * ((size_t)maxsz + 4), g.stream));
          k_interp_fill<<<cdiv(r1 - r0, 128), 128, 0, g.stream>>>(A.rowptr, A.col, A.val, S.rowptr, S.col, cf, f2c, r0, r1,
-                                                                cnt, off, htab, loff, lcol, lval, max_elmts, prp, P.col, P.val);
+                                                                cnt, off, htab, loff, lcol, lval, max_elmts, prp, P.col, P.val, slow);
          HDK_LAUNCH_CHECK();
       }
       dfree(htab); dfree(lcol); dfree(lval);
    }
    k_cf_reset_sf<<<cdiv(n, 256), 256, 0, g.stream>>>(cf, n);
    HDK_LAUNCH_CHECK();
-   dfree(cap); dfree(cnt); dfree(rowlen); dfree(off); dfree(loff);
+   dfree(cap); dfree(cnt); dfree(rowlen); dfree(off); dfree(loff); dfree(slow);
    return HDK_OK;
 }
 
@@ -701,6 +915,124 @@ static int csr_transpose(const DevCSR &A, DevCSR &T)
 // hash accumulators in scratch; row = diagonal first, then columns in discovery order of
 // (i1 in R_ic) x (i2 in A_i1) x (i3 in P_i2); value = sum (r*a)*p in that order.
 // =====================================================================================
+// ---- warp-per-row Galerkin product with shared-memory hash accumulators -------------------
+// A warp walks the product stream of one coarse row in hypre's loop order, 32 products at a
+// time.  Lanes that hit the same column in one chunk are grouped with match.any; the group
+// leader inserts / looks up the column (new columns get slots in lane order = discovery
+// order) and adds the group's products in lane order, so both the column order and every
+// floating-point sum equal the sequential loop bit for bit.
+constexpr int RW_CAP   = 512;  // hash slots per warp
+constexpr int RW_LIMIT = 320;  // longest row handled here; longer rows fall back to k_rap_count/fill
+constexpr int RW_WARPS = 8;
+
+template <bool FILL, int CAP>
+__global__ void __launch_bounds__(32 * RW_WARPS) k_rap_warp(const int *rrp, const int *rcol, const double *rval,
+                                                            const int *arp, const int *acol, const double *aval,
+                                                            const int *prp, const int *pcol, const double *pval,
+                                                            int nc, int *cnt, const int *crp, int *ccol, double *cval)
+{
+   extern __shared__ __align__(16) unsigned char rw_smem[];
+   const int      lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+   const unsigned FULL = 0xffffffffu;
+   const int      ic = blockIdx.x * RW_WARPS + wid;
+   if (ic >= nc) return;
+   if (FILL && cnt[ic] > RW_LIMIT) return;
+   int    *keys = reinterpret_cast<int *>(rw_smem) + (size_t)wid * CAP;
+   int    *idx  = reinterpret_cast<int *>(rw_smem) + (size_t)RW_WARPS * CAP + (size_t)wid * CAP;
+   double *vals = reinterpret_cast<double *>(rw_smem + (size_t)2 * RW_WARPS * CAP * sizeof(int)) + (size_t)wid * CAP;
+   for (int h = lane; h < CAP; h += 32) keys[h] = -1;
+   __syncwarp();
+   int  count = 1;
+   bool overflow = false;
+   if (lane == 0)
+   {
+      bool nw;
+      int  h = wt_find_or_insert(keys, CAP, ic, nw);
+      if (FILL) { idx[h] = 0; vals[h] = 0.0; }
+   }
+   __syncwarp();
+   for (int j1 = rrp[ic]; j1 < rrp[ic + 1] && !overflow; j1++)
+   {
+      const int    i1 = rcol[j1];
+      const double r  = FILL ? rval[j1] : 0.0;
+      const int    a0 = arp[i1], a1 = arp[i1 + 1];
+      for (int base = a0; base < a1 && !overflow; base += 32)
+      {
+         const int  j2 = base + lane;
+         const bool v2 = j2 < a1;
+         int        i2 = v2 ? acol[j2] : 0;
+         double     ra = (FILL && v2) ? __dmul_rn(r, aval[j2]) : 0.0;
+         int        ps = v2 ? prp[i2] : 0;
+         int        pl = v2 ? prp[i2 + 1] - ps : 0;
+         int        incl = pl;
+#pragma unroll
+         for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(FULL, incl, o); if (lane >= o) incl += t; }
+         const int excl = incl - pl, Tc = __shfl_sync(FULL, incl, 31);
+         for (int q0 = 0; q0 < Tc; q0 += 32)
+         {
+            const int  q = q0 + lane;
+            const bool act = q < Tc;
+            int lo = 0, hi = 31; // smallest m with incl[m] > q
+#pragma unroll
+            for (int s = 0; s < 5; s++)
+            {
+               int mid = (lo + hi) >> 1;
+               int v   = __shfl_sync(FULL, incl, mid);
+               if (v > q) hi = mid; else lo = mid + 1;
+            }
+            const int    m   = lo;
+            const int    j3  = q - __shfl_sync(FULL, excl, m);
+            const int    psm = __shfl_sync(FULL, ps, m);
+            const double ram = __shfl_sync(FULL, ra, m);
+            const int    key = act ? pcol[psm + j3] : (-2 - lane);
+            const double rap = (FILL && act) ? __dmul_rn(ram, pval[psm + j3]) : 0.0;
+            const unsigned grp = __match_any_sync(FULL, key);
+            const bool leader = act && (lane == __ffs(grp) - 1);
+            bool isnew = false;
+            int  h = 0;
+            if (leader) h = wt_find_or_insert(keys, CAP, key, isnew);
+            const unsigned newmask = __ballot_sync(FULL, leader && isnew);
+            if (FILL && leader && isnew) idx[h] = count + __popc(newmask & ((1u << lane) - 1u));
+            count += __popc(newmask);
+            if (count > RW_LIMIT) overflow = true;
+            if (FILL)
+            {
+               const int maxc = (int)__reduce_max_sync(FULL, leader ? (unsigned)__popc(grp) : 0u);
+               double    acc = 0.0;
+               bool      first = true;
+               unsigned  rem = leader ? grp : 0u;
+               for (int s = 0; s < maxc; s++)
+               {
+                  int    src = rem ? (__ffs(rem) - 1) : lane;
+                  double v   = __shfl_sync(FULL, rap, src);
+                  if (rem)
+                  {
+                     if (first) { acc = isnew ? v : __dadd_rn(vals[h], v); first = false; }
+                     else acc = __dadd_rn(acc, v);
+                     rem &= rem - 1u;
+                  }
+               }
+               if (leader) vals[h] = acc;
+            }
+            __syncwarp();
+            if (overflow) break;
+         }
+      }
+   }
+   if (!FILL) { if (lane == 0) cnt[ic] = overflow ? -1 : count; return; }
+   const int b = crp[ic];
+   for (int h = lane; h < CAP; h += 32)
+      if (keys[h] >= 0) { int s = idx[h]; ccol[b + s] = keys[h]; cval[b + s] = vals[h]; }
+}
+
+__global__ void k_max_int(const int *v, int n, int *out)
+{
+   int i = blockIdx.x * blockDim.x + threadIdx.x;
+   int m = i < n ? v[i] : 0;
+   for (int o = 16; o > 0; o >>= 1) { int t = __shfl_down_sync(0xffffffffu, m, o); m = t > m ? t : m; }
+   if ((threadIdx.x & 31) == 0 && m > 0) atomicMax(out, m);
+}
+
 __global__ void k_rap_q(const int *arp, const int *acol, const int *prp, int n, int *q)
 {
    int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -709,11 +1041,11 @@ __global__ void k_rap_q(const int *arp, const int *acol, const int *prp, int n, 
    for (int k = arp[i]; k < arp[i + 1]; k++) { int j = acol[k]; s += prp[j + 1] - prp[j]; }
    q[i] = s;
 }
-__global__ void k_rap_cap(const int *rrp, const int *rcol, const int *q, int nc, int *cap)
+__global__ void k_rap_cap(const int *rrp, const int *rcol, const int *q, int nc, int *cap, const int *cnt)
 {
    int ic = blockIdx.x * blockDim.x + threadIdx.x;
    if (ic > nc) return;
-   if (ic == nc) { cap[ic] = 0; return; }
+   if (ic == nc || cnt[ic] != -1) { cap[ic] = 0; return; } // only rows the warp kernel gave up on
    long long ub = 1;
    for (int k = rrp[ic]; k < rrp[ic + 1]; k++) ub += q[rcol[k]];
    if (ub > nc) ub = nc;
@@ -726,6 +1058,7 @@ __global__ void k_rap_count(const int *rrp, const int *rcol, const int *arp, con
    if (ic >= row1) return;
    int *tab = keys + (off[ic] - off[row0]);
    int  cap = (int)(off[ic + 1] - off[ic]);
+   if (cap == 0) return;
    int  c   = 1;
    hset_insert(tab, cap, ic);
    for (int j1 = rrp[ic]; j1 < rrp[ic + 1]; j1++)
@@ -744,7 +1077,7 @@ __global__ void k_rap_cap2(const int *cnt, int nc, int *cap2)
 {
    int ic = blockIdx.x * blockDim.x + threadIdx.x;
    if (ic > nc) return;
-   cap2[ic] = ic < nc ? pow2ceil(2 * cnt[ic]) : 0;
+   cap2[ic] = (ic < nc && cnt[ic] > RW_LIMIT) ? pow2ceil(2 * cnt[ic]) : 0; // rows too long for the warp kernel
 }
 __global__ void k_rap_fill(const int *rrp, const int *rcol, const double *rval, const int *arp, const int *acol,
                            const double *aval, const int *prp, const int *pcol, const double *pval, int row0,
@@ -754,6 +1087,7 @@ __global__ void k_rap_fill(const int *rrp, const int *rcol, const double *rval, 
    if (ic >= row1) return;
    int2 *tab = htab + (off[ic] - off[row0]);
    int   cap = (int)(off[ic + 1] - off[ic]);
+   if (cap == 0) return;
    int   b = crp[ic], c = b;
    hmap_insert(tab, cap, ic, c);
    ccol[c] = ic; cval[c] = 0.0; c++;
@@ -779,6 +1113,7 @@ __global__ void k_rap_fill(const int *rrp, const int *rcol, const double *rval, 
 
 static int build_rap(const DevCSR &R, const DevCSR &A, const DevCSR &P, DevCSR &C)
 {
+   stage_mark(nullptr, -1);
    int nc = R.nrows, n = A.nrows;
    int *q, *cap, *cnt, *crp;
    int64_t *off;
@@ -789,7 +1124,13 @@ static int build_rap(const DevCSR &R, const DevCSR &A, const DevCSR &P, DevCSR &
    HDK_TRY(dalloc(&off, (size_t)nc + 1));
    k_rap_q<<<cdiv(n, 256), 256, 0, g.stream>>>(A.rowptr, A.col, P.rowptr, n, q);
    HDK_LAUNCH_CHECK();
-   k_rap_cap<<<cdiv(nc + 1, 256), 256, 0, g.stream>>>(R.rowptr, R.col, q, nc, cap);
+   // pass 1a: exact row lengths by the warp kernel (rows longer than RW_LIMIT are flagged -1)
+   k_rap_warp<false, RW_CAP><<<cdiv(nc, RW_WARPS), 32 * RW_WARPS, (size_t)RW_WARPS * RW_CAP * sizeof(int), g.stream>>>(
+      R.rowptr, R.col, R.val, A.rowptr, A.col, A.val, P.rowptr, P.col, P.val, nc, cnt, nullptr, nullptr, nullptr);
+   HDK_LAUNCH_CHECK();
+   stage_mark("  rap.warp1", -1);
+   // pass 1b: flagged rows through the one-thread-per-row kernel with hash sets in global scratch
+   k_rap_cap<<<cdiv(nc + 1, 256), 256, 0, g.stream>>>(R.rowptr, R.col, q, nc, cap, cnt);
    HDK_LAUNCH_CHECK();
    HDK_TRY(exclusive_scan_i64(cap, off, nc + 1));
    std::vector<int> bounds;
@@ -808,6 +1149,7 @@ static int build_rap(const DevCSR &R, const DevCSR &A, const DevCSR &P, DevCSR &
       }
       dfree(keys);
    }
+   stage_mark("  rap.thr1", -1);
    HDK_CUDA(cudaMemsetAsync(cnt + nc, 0, sizeof(int), g.stream));
    HDK_TRY(exclusive_scan_int(cnt, crp, nc + 1));
    int nnzC = 0;
@@ -819,6 +1161,26 @@ static int build_rap(const DevCSR &R, const DevCSR &A, const DevCSR &P, DevCSR &
    HDK_TRY(dalloc(&C.val, (size_t)nnzC + 8));
    HDK_CUDA(cudaMemsetAsync(C.col + nnzC, 0, sizeof(int) * 8, g.stream));
    HDK_CUDA(cudaMemsetAsync(C.val + nnzC, 0, sizeof(double) * 8, g.stream));
+   {
+      // small tables (more resident warps) when every row of the level is short
+      int *dmax = reinterpret_cast<int *>(g.dscal + S_TMP3), hmax = 0;
+      HDK_CUDA(cudaMemsetAsync(dmax, 0, sizeof(int), g.stream));
+      k_max_int<<<cdiv(nc, 256), 256, 0, g.stream>>>(cnt, nc, dmax);
+      HDK_LAUNCH_CHECK();
+      HDK_CUDA(cudaMemcpyAsync(&hmax, dmax, sizeof(int), cudaMemcpyDeviceToHost, g.stream));
+      HDK_CUDA(cudaStreamSynchronize(g.stream));
+      static bool attr = false;
+      size_t      smem = (size_t)RW_WARPS * RW_CAP * (2 * sizeof(int) + sizeof(double));
+      if (!attr) { HDK_CUDA(cudaFuncSetAttribute(k_rap_warp<true, RW_CAP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = true; }
+      if (hmax <= 80)
+         k_rap_warp<true, 128><<<cdiv(nc, RW_WARPS), 32 * RW_WARPS, (size_t)RW_WARPS * 128 * 16, g.stream>>>(
+            R.rowptr, R.col, R.val, A.rowptr, A.col, A.val, P.rowptr, P.col, P.val, nc, cnt, crp, C.col, C.val);
+      else
+         k_rap_warp<true, RW_CAP><<<cdiv(nc, RW_WARPS), 32 * RW_WARPS, smem, g.stream>>>(
+            R.rowptr, R.col, R.val, A.rowptr, A.col, A.val, P.rowptr, P.col, P.val, nc, cnt, crp, C.col, C.val);
+      HDK_LAUNCH_CHECK();
+      stage_mark("  rap.warp2", -1);
+   }
    k_rap_cap2<<<cdiv(nc + 1, 256), 256, 0, g.stream>>>(cnt, nc, cap);
    HDK_LAUNCH_CHECK();
    HDK_TRY(exclusive_scan_i64(cap, off, nc + 1));
