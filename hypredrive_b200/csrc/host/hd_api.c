@@ -336,6 +336,9 @@ uint32_t HYPREDRV_PreconPresetRegister(const char *name, const char *yaml_text, 
 }
 
 /* ---- linear system ------------------------------------------------------------------- */
+static uint32_t read_vector_into(HYPREDRV_t h, const char *fname, double **dst);
+static uint32_t alloc_vec(double **p, int64_t n);
+
 static void build_timer_add(HYPREDRV_t h, double t0)
 {
    hdk_sync();
@@ -450,8 +453,15 @@ uint32_t HYPREDRV_LinearSystemSetRHS(HYPREDRV_t h, HYPRE_Vector vec)
    int mode = h->args ? h->args->ls.rhs_mode : 2;
    if (mode == 2)
    {
+      if (h->args && h->args->ls.rhs_filename[0])
+      {
+         double   t0 = hd_wtime();
+         uint32_t e = read_vector_into(h, h->args->ls.rhs_filename, &h->b_d);
+         if (!e) build_timer_add(h, t0);
+         return e;
+      }
       if (h->b_d) return hd_err_get(); /* e.g. installed together with a device stencil */
-      return fail(HYPREDRV_ERROR_FILE_NOT_FOUND, "%s", "rhs_mode 'file': reading IJ vectors from disk is not implemented on the B200 path");
+      return fail(HYPREDRV_ERROR_FILE_NOT_FOUND, "%s", "rhs_mode 'file' but linear_system.rhs_filename is empty");
    }
    double t0 = hd_wtime();
    if (alloc_vec(&h->b_d, h->n)) return hd_err_get();
@@ -492,7 +502,12 @@ uint32_t HYPREDRV_LinearSystemSetInitialGuess(HYPREDRV_t h, HYPRE_Vector vec)
       if (mode == 1) rc = hdk_vec_fill(h->x0_d, 1.0, h->n);
       else if (mode == 3) rc = hdk_vec_random(h->x0_d, h->n, h->row_start, 2023);
       else if (mode == 4) rc = hdk_vec_copy(h->x0_d, h->x_d, h->n);
-      else if (mode == 2) return fail(HYPREDRV_ERROR_FILE_NOT_FOUND, "%s", "init_guess_mode 'file' is not implemented on the B200 path");
+      else if (mode == 2)
+      {
+         if (!h->args->ls.x0_filename[0]) return fail(HYPREDRV_ERROR_FILE_NOT_FOUND, "%s", "init_guess_mode 'file' but linear_system.x0_filename is empty");
+         uint32_t e = read_vector_into(h, h->args->ls.x0_filename, &h->x0_d);
+         if (e) return e;
+      }
       else rc = hdk_vec_fill(h->x0_d, 0.0, h->n);
    }
    if (!rc && (!h->args || h->args->ls.init_guess_mode != 4)) rc = hdk_vec_fill(h->x_d, 0.0, h->n);
@@ -541,13 +556,51 @@ uint32_t HYPREDRV_LinearSystemBuild(HYPREDRV_t h)
    return HYPREDRV_LinearSystemSetPrecMatrix(h, NULL);
 }
 
+static void join_path(char *out, size_t cap, const char *dir, const char *name)
+{
+   if (dir && dir[0] && name[0] != '/') snprintf(out, cap, "%s/%s", dir, name);
+   else snprintf(out, cap, "%s", name);
+}
+
 uint32_t HYPREDRV_LinearSystemReadMatrix(HYPREDRV_t h)
 {
+   /* reference src/HYPREDRV.c:1940 -> linsys.c:946-977: IJ parts "<name>.%05d[.bin]" */
    CHECK_ARGS(h);
-   return fail(HYPREDRV_ERROR_FILE_NOT_FOUND,
-               "reading '%s' from disk: the IJ file readers are a 'next' row of the scope table (SURVEY.md 8f-1); "
-               "use SetMatrixFromCSR / SetMatrix / SetStencil",
-               h->args->ls.matrix_filename);
+   if (!h->args->ls.matrix_filename[0]) return fail(HYPREDRV_ERROR_FILE_NOT_FOUND, "%s", "linear_system.matrix_filename is empty");
+   char path[2048];
+   join_path(path, sizeof(path), h->args->ls.dirname, h->args->ls.matrix_filename);
+   double         t0 = hd_wtime();
+   HYPRE_IJMatrix ij = NULL;
+   if (hd_read_ij_matrix(path, h->rank, &ij)) return hd_err_get();
+   if (hd_ij_matrix_flatten(ij)) { HYPRE_IJMatrixDestroy(ij); return fail(HYPREDRV_ERROR_ALLOCATION, NULL, NULL); }
+   uint32_t e = HYPREDRV_LinearSystemSetMatrixFromCSR(h, ij->ilower, ij->iupper, (const HYPRE_BigInt *)ij->indptr, ij->cols, ij->vals);
+   HYPRE_IJMatrixDestroy(ij);
+   if (e) return e;
+   h->pending_build += hd_wtime() - t0 - 0.0; /* file parsing counts as LS build time */
+   if (h->rank == 0)
+   {
+      int64_t lr, gr, ln, gn;
+      hdk_csr_info(h->A, &lr, &gr, &ln, &gn);
+      printf("====================================================================================\n");
+      printf("Solving linear system #%d with %lld rows and %lld nonzeros...\n", h->stats->ls_id + 1, (long long)gr, (long long)gn);
+      printf("====================================================================================\n");
+      fflush(stdout);
+   }
+   h->stats->ls_id++;
+   return hd_err_get();
+}
+
+static uint32_t read_vector_into(HYPREDRV_t h, const char *fname, double **dst)
+{
+   char path[2048];
+   join_path(path, sizeof(path), h->args->ls.dirname, fname);
+   HYPRE_IJVector v = NULL;
+   if (hd_read_ij_vector(path, h->rank, &v)) return hd_err_get();
+   if (v->n != h->n) { HYPRE_IJVectorDestroy(v); return fail(HYPREDRV_ERROR_FILE_UNEXPECTED_ENTRY, "vector file %s does not match the matrix row range", path); }
+   if (alloc_vec(dst, h->n)) { HYPRE_IJVectorDestroy(v); return hd_err_get(); }
+   int rc = hdk_vec_h2d(*dst, v->data, h->n);
+   HYPRE_IJVectorDestroy(v);
+   return rc ? hdk_fail(rc) : hd_err_get();
 }
 
 uint32_t HYPREDRV_LinearSystemGetSolutionValues(HYPREDRV_t h, HYPRE_Complex **sol_data)

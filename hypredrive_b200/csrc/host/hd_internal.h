@@ -164,4 +164,8 @@ struct hypre_IJVector_struct
 #define HD_IJVEC_MAGIC 0x494a5645u
 int hd_ij_matrix_flatten(struct hypre_IJMatrix_struct *A);
 
+/* ---------------------------------------------------------------- file readers (hd_io.c) */
+int hd_read_ij_matrix(const char *prefix, int rank, HYPRE_IJMatrix *out);
+int hd_read_ij_vector(const char *prefix, int rank, HYPRE_IJVector *out);
+
 #endif
