@@ -152,7 +152,8 @@ done:
    return rc;
 }
 
-int hdk_gmres(const hdk_csr *A, hdk_amg *M, const double *b, double *x, hdk_krylov *k)
+// flexible: hypre krylov/flexgmres.c -- keep z_j = M^{-1} p_j and form x += sum_j y_j z_j
+static int gmres_impl(const hdk_csr *A, hdk_amg *M, const double *b, double *x, hdk_krylov *k, bool flexible)
 {
    HDK_TRY(require_init());
    if (!A || !b || !x || !k) return set_error(HDK_ERR_INVALID, "hdk_gmres: null argument");
@@ -163,6 +164,8 @@ int hdk_gmres(const hdk_csr *A, hdk_amg *M, const double *b, double *x, hdk_kryl
    double *r = nullptr, *w = nullptr;
    int     rc = HDK_OK;
    for (int j = 0; j <= kd; j++) if ((rc = dalloc(&p[(size_t)j], (size_t)n + 8))) return rc;
+   std::vector<double *> z(flexible ? (size_t)kd + 1 : 0, nullptr);
+   for (size_t j = 0; j < z.size(); j++) if ((rc = dalloc(&z[j], (size_t)n + 8))) return rc;
    HDK_TRY(dalloc(&r, (size_t)n + 8));
    HDK_TRY(dalloc(&w, (size_t)n + 8));
    std::vector<double> c((size_t)kd + 1, 0.0), s((size_t)kd + 1, 0.0), rs((size_t)kd + 2, 0.0);
@@ -207,11 +210,12 @@ int hdk_gmres(const hdk_csr *A, hdk_amg *M, const double *b, double *x, hdk_kryl
          while (i < kd && iter < k->max_iter)
          {
             i++; iter++;
-            // r = M^{-1} p[i-1] ; p[i] = A r
-            if (M) { if ((rc = amg_precond(M, p[(size_t)i - 1], r, FIN_NONE, nullptr))) goto done; }
-            else if ((rc = vec_copy(r, p[(size_t)i - 1], n))) goto done;
+            // zz = M^{-1} p[i-1] ; p[i] = A zz
+            double *zz = flexible ? z[(size_t)i - 1] : r;
+            if (M) { if ((rc = amg_precond(M, p[(size_t)i - 1], zz, FIN_NONE, nullptr))) goto done; }
+            else if ((rc = vec_copy(zz, p[(size_t)i - 1], n))) goto done;
             SpmvArgs a;
-            a.x = r; a.y = p[(size_t)i];
+            a.x = zz; a.y = p[(size_t)i];
             if ((rc = parcsr_matvec(*A, SPMV_SET, a))) goto done;
             // modified Gram-Schmidt: coefficients stay on the device (S_H0 + j)
             for (int j = 0; j < i; j++)
@@ -256,12 +260,19 @@ int hdk_gmres(const hdk_csr *A, hdk_amg *M, const double *b, double *x, hdk_kryl
             t += rs[(size_t)kk];
             rs[(size_t)kk] = t / HH(kk, kk);
          }
-         if ((rc = vec_copy(w, p[(size_t)i - 1], n))) goto done;
-         if ((rc = vec_scale(rs[(size_t)i - 1], w, n))) goto done;
-         for (int j = i - 2; j >= 0; j--) if ((rc = vec_axpy(rs[(size_t)j], p[(size_t)j], w, n))) goto done;
-         if (M) { if ((rc = amg_precond(M, w, r, FIN_NONE, nullptr))) goto done; }
-         else if ((rc = vec_copy(r, w, n))) goto done;
-         if ((rc = vec_axpy(1.0, r, x, n))) goto done;
+         if (flexible)
+         {
+            for (int j = i - 1; j >= 0; j--) if ((rc = vec_axpy(rs[(size_t)j], z[(size_t)j], x, n))) goto done;
+         }
+         else
+         {
+            if ((rc = vec_copy(w, p[(size_t)i - 1], n))) goto done;
+            if ((rc = vec_scale(rs[(size_t)i - 1], w, n))) goto done;
+            for (int j = i - 2; j >= 0; j--) if ((rc = vec_axpy(rs[(size_t)j], p[(size_t)j], w, n))) goto done;
+            if (M) { if ((rc = amg_precond(M, w, r, FIN_NONE, nullptr))) goto done; }
+            else if ((rc = vec_copy(r, w, n))) goto done;
+            if ((rc = vec_axpy(1.0, r, x, n))) goto done;
+         }
          if (r_norm <= eps && iter >= k->min_iter)
          {
             if (k->skip_real_res_check) { k->converged = 1; break; }
@@ -302,7 +313,87 @@ done:
    cudaEventElapsedTime(&ms, g.ev_a, g.ev_b);
    k->solve_ms = ms;
    for (auto q : p) dfree(q);
+   for (auto q : z) dfree(q);
    dfree(r); dfree(w);
+   return rc;
+}
+
+int hdk_gmres(const hdk_csr *A, hdk_amg *M, const double *b, double *x, hdk_krylov *k) { return gmres_impl(A, M, b, x, k, false); }
+int hdk_fgmres(const hdk_csr *A, hdk_amg *M, const double *b, double *x, hdk_krylov *k) { return gmres_impl(A, M, b, x, k, true); }
+
+// hypre krylov/bicgstab.c (hypre_BiCGSTABSolve), right-preconditioned (reference
+// src/internal/solver.c:241-252, options src/internal/bicgstab.c)
+int hdk_bicgstab(const hdk_csr *A, hdk_amg *M, const double *b, double *x, hdk_krylov *k)
+{
+   HDK_TRY(require_init());
+   if (!A || !b || !x || !k) return set_error(HDK_ERR_INVALID, "hdk_bicgstab: null argument");
+   const int64_t n = A->diag.nrows;
+   const double  epsmac = 1.e-128;
+   k->iters = 0; k->converged = 0; k->rel_res_norm = 0.0; k->solve_ms = 0.0;
+   double *v[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+   for (int j = 0; j < 6; j++) HDK_TRY(dalloc(&v[j], (size_t)n + 8));
+   double *r0 = v[0], *r = v[1], *p = v[2], *vv = v[3], *q = v[4], *s = v[5];
+   int     rc = HDK_OK, iter = 0;
+   double  d = 0, b_norm = 0, r_norm = 0, res = 0;
+   HDK_CUDA(cudaEventRecord(g.ev_a, g.stream));
+   auto prec = [&](const double *in, double *out) -> int {
+      if (M) return amg_precond(M, in, out, FIN_NONE, nullptr);
+      return vec_copy(out, in, n);
+   };
+   auto mv = [&](const double *in, double *out) -> int { SpmvArgs a; a.x = in; a.y = out; return parcsr_matvec(*A, SPMV_SET, a); };
+   do
+   {
+      if ((rc = vec_dot_host(b, b, n, &d))) break;
+      b_norm = sqrt(d);
+      SpmvArgs a;
+      a.x = x; a.y = r0; a.b = b;
+      if ((rc = parcsr_matvec(*A, SPMV_RESIDUAL, a))) break;
+      if ((rc = vec_copy(r, r0, n)) || (rc = vec_copy(p, r0, n))) break;
+      if ((rc = vec_dot_host(r, r, n, &d))) break;
+      r_norm = sqrt(d);
+      double den = b_norm > 0.0 ? b_norm : r_norm, eps = k->rel_tol * den;
+      if (k->abs_tol > eps) eps = k->abs_tol;
+      res = d; // <r0, r>
+      while (iter < k->max_iter && res != 0.0)
+      {
+         if (r_norm == 0.0) { k->converged = 1; break; }
+         iter++;
+         double temp, gn, gd;
+         if ((rc = prec(p, vv)) || (rc = mv(vv, q)) || (rc = vec_dot_host(r0, q, n, &temp))) break;
+         if (fabs(temp) < epsmac) break;
+         double alpha = res / temp;
+         if ((rc = vec_axpy(alpha, vv, x, n)) || (rc = vec_axpy(-alpha, q, r, n))) break;
+         if ((rc = prec(r, vv)) || (rc = mv(vv, s))) break;
+         if ((rc = vec_dot_host(r, s, n, &gn)) || (rc = vec_dot_host(s, s, n, &gd))) break;
+         double gamma = (gn == 0.0 && gd == 0.0) ? 0.0 : gn / gd;
+         if ((rc = vec_axpy(gamma, vv, x, n)) || (rc = vec_axpy(-gamma, s, r, n))) break;
+         if ((rc = vec_dot_host(r, r, n, &d))) break;
+         r_norm = sqrt(d);
+         if (r_norm <= eps && iter >= k->min_iter)
+         {
+            SpmvArgs t;
+            t.x = x; t.y = r; t.b = b;
+            if ((rc = parcsr_matvec(*A, SPMV_RESIDUAL, t)) || (rc = vec_dot_host(r, r, n, &d))) break;
+            r_norm = sqrt(d);
+            if (r_norm <= eps) { k->converged = 1; break; }
+         }
+         if (fabs(res) < epsmac) break;
+         double beta = 1.0 / res;
+         if ((rc = vec_dot_host(r0, r, n, &res))) break;
+         beta *= res;
+         if ((rc = vec_axpy(-gamma, q, p, n))) break;
+         if (fabs(gamma) < epsmac) break;
+         if ((rc = vec_scale(beta * alpha / gamma, p, n)) || (rc = vec_axpy(1.0, r, p, n))) break;
+      }
+   } while (0);
+   k->iters        = iter;
+   k->rel_res_norm = b_norm > 0.0 ? r_norm / b_norm : r_norm;
+   cudaEventRecord(g.ev_b, g.stream);
+   cudaEventSynchronize(g.ev_b);
+   float ms = 0.f;
+   cudaEventElapsedTime(&ms, g.ev_a, g.ev_b);
+   k->solve_ms = ms;
+   for (int j = 0; j < 6; j++) dfree(v[j]);
    return rc;
 }
 

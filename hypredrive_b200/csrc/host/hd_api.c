@@ -814,7 +814,9 @@ uint32_t HYPREDRV_LinearSolverApply(HYPREDRV_t h)
       k.max_iter = h->args->gmres.max_iter; k.rel_tol = h->args->gmres.relative_tol; k.abs_tol = h->args->gmres.absolute_tol;
       k.krylov_dim = h->args->gmres.krylov_dim; k.min_iter = h->args->gmres.min_iter;
       k.skip_real_res_check = h->args->gmres.skip_real_res_check;
-      rc = hdk_gmres(h->A, h->precon, h->b_d, h->x_d, &k);
+      if (h->args->solver_method == HD_SOLVER_FGMRES) rc = hdk_fgmres(h->A, h->precon, h->b_d, h->x_d, &k);
+      else if (h->args->solver_method == HD_SOLVER_BICGSTAB) rc = hdk_bicgstab(h->A, h->precon, h->b_d, h->x_d, &k);
+      else rc = hdk_gmres(h->A, h->precon, h->b_d, h->x_d, &k);
    }
    if (rc) { hdk_vec_free(r); return hdk_fail(rc); }
    h->iters = k.iters; h->converged = k.converged; h->final_res = k.rel_res_norm; h->solve_time = 1e-3 * k.solve_ms;

@@ -89,6 +89,16 @@ static const hd_field f_gmres[] = {
    FI(hd_gmres_args, logging), FI(hd_gmres_args, print_level), FD(hd_gmres_args, relative_tol),
    FD(hd_gmres_args, absolute_tol), FD(hd_gmres_args, conv_fac_tol), FEND};
 
+/* fgmres (src/internal/fgmres.c:14-21) and bicgstab (src/internal/bicgstab.c:14-22) share the
+ * gmres option record: their keys are subsets of it */
+static const hd_field f_fgmres[] = {
+   FI(hd_gmres_args, min_iter), FI(hd_gmres_args, max_iter), FI(hd_gmres_args, krylov_dim), FI(hd_gmres_args, logging),
+   FI(hd_gmres_args, print_level), FD(hd_gmres_args, relative_tol), FD(hd_gmres_args, absolute_tol), FEND};
+static const hd_field f_bicgstab[] = {
+   FI(hd_gmres_args, min_iter), FI(hd_gmres_args, max_iter), FI(hd_gmres_args, stop_crit), FI(hd_gmres_args, logging),
+   FI(hd_gmres_args, print_level), FD(hd_gmres_args, relative_tol), FD(hd_gmres_args, absolute_tol),
+   FD(hd_gmres_args, conv_fac_tol), FEND};
+
 static const hd_field f_amg[] = {FI(hd_amg_args, max_iter), FI(hd_amg_args, print_level), FD(hd_amg_args, tolerance), FEND};
 static const hd_field f_amg_int[] = {
    FM(hd_amg_args, prolongation_type, map_interp), FM(hd_amg_args, restriction_type, map_restr), FI(hd_amg_args, max_nnz_row),
@@ -298,8 +308,10 @@ static int set_solver_method(hd_args *a, const char *name)
 {
    if (!strcmp(name, "pcg")) { a->solver_method = HD_SOLVER_PCG; return 0; }
    if (!strcmp(name, "gmres")) { a->solver_method = HD_SOLVER_GMRES; return 0; }
+   if (!strcmp(name, "fgmres")) { a->solver_method = HD_SOLVER_FGMRES; return 0; }
+   if (!strcmp(name, "bicgstab")) { a->solver_method = HD_SOLVER_BICGSTAB; return 0; }
    hd_err_set(HYPREDRV_ERROR_INVALID_SOLVER);
-   hd_err_msg("solver '%s' is outside the B200 hot path (supported: pcg, gmres)", name);
+   hd_err_msg("unknown solver '%s' (supported: pcg, gmres, fgmres, bicgstab)", name);
    return 1;
 }
 
@@ -323,6 +335,7 @@ static int parse_solver_node(hd_args *a, hd_node *n)
       if (!n->val[0]) { hd_err_set(HYPREDRV_ERROR_MISSING_SOLVER); hd_err_msg("empty solver section"); return 1; }
       if (set_solver_method(a, n->val)) { n->invalid = 2; return 1; }
       hd_pcg_defaults(&a->pcg); hd_gmres_defaults(&a->gmres);
+      if (a->solver_method == HD_SOLVER_BICGSTAB) a->gmres.max_iter = 100;
       a->pcg.print_level = 0; a->gmres.print_level = 0;
       return 0;
    }
@@ -337,7 +350,13 @@ static int parse_solver_node(hd_args *a, hd_node *n)
    if (set_solver_method(a, method->key)) { method->invalid = 1; return 1; }
    method->used = 1;
    if (a->solver_method == HD_SOLVER_PCG) { hd_pcg_defaults(&a->pcg); apply_fields(method, f_pcg, &a->pcg, "solver:pcg", NULL); }
-   else { hd_gmres_defaults(&a->gmres); apply_fields(method, f_gmres, &a->gmres, "solver:gmres", NULL); }
+   else
+   {
+      hd_gmres_defaults(&a->gmres);
+      if (a->solver_method == HD_SOLVER_GMRES) apply_fields(method, f_gmres, &a->gmres, "solver:gmres", NULL);
+      else if (a->solver_method == HD_SOLVER_FGMRES) apply_fields(method, f_fgmres, &a->gmres, "solver:fgmres", NULL);
+      else { a->gmres.max_iter = 100; apply_fields(method, f_bicgstab, &a->gmres, "solver:bicgstab", NULL); }
+   }
    return 0;
 }
 

@@ -42,7 +42,7 @@ int      hd_yaml_override(hd_node *root, const char *path, const char *value);
 void     hd_yaml_print(const hd_node *root, FILE *fp);
 
 /* ---------------------------------------------------------------- options (hd_args.c) */
-typedef enum { HD_SOLVER_PCG = 0, HD_SOLVER_GMRES = 1 } hd_solver_t;
+typedef enum { HD_SOLVER_PCG = 0, HD_SOLVER_GMRES = 1, HD_SOLVER_FGMRES = 2, HD_SOLVER_BICGSTAB = 3 } hd_solver_t;
 typedef enum { HD_PRECON_AMG = 0, HD_PRECON_NONE = 1 } hd_precon_t;
 
 typedef struct

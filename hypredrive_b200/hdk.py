@@ -85,6 +85,8 @@ def lib():
         L.hdk_amg_get_l1.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
         L.hdk_pcg.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(Krylov)]
         L.hdk_gmres.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(Krylov)]
+        L.hdk_fgmres.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(Krylov)]
+        L.hdk_bicgstab.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(Krylov)]
         L.hdk_time_kernel.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_double),
                                       C.POINTER(C.c_double)]
         L.hdk_comm_unique_id.argtypes = [C.c_void_p]
@@ -318,6 +320,18 @@ def gmres(A: DCsr, b: DVec, x: DVec, M: DAmg | None = None, max_iter=300, rel_to
     k = Krylov(max_iter=max_iter, rel_tol=rel_tol, abs_tol=abs_tol, krylov_dim=krylov_dim,
                skip_real_res_check=skip_real_res_check)
     check(lib().hdk_gmres(A.h, M.h if M is not None else None, b.p, x.p, C.byref(k)))
+    return dict(iters=k.iters, converged=bool(k.converged), rel_res_norm=k.rel_res_norm, solve_ms=k.solve_ms)
+
+
+def fgmres(A: DCsr, b: DVec, x: DVec, M: DAmg | None = None, max_iter=300, rel_tol=1e-6, abs_tol=0.0, krylov_dim=30):
+    k = Krylov(max_iter=max_iter, rel_tol=rel_tol, abs_tol=abs_tol, krylov_dim=krylov_dim)
+    check(lib().hdk_fgmres(A.h, M.h if M is not None else None, b.p, x.p, C.byref(k)))
+    return dict(iters=k.iters, converged=bool(k.converged), rel_res_norm=k.rel_res_norm, solve_ms=k.solve_ms)
+
+
+def bicgstab(A: DCsr, b: DVec, x: DVec, M: DAmg | None = None, max_iter=100, rel_tol=1e-6, abs_tol=0.0):
+    k = Krylov(max_iter=max_iter, rel_tol=rel_tol, abs_tol=abs_tol)
+    check(lib().hdk_bicgstab(A.h, M.h if M is not None else None, b.p, x.p, C.byref(k)))
     return dict(iters=k.iters, converged=bool(k.converged), rel_res_norm=k.rel_res_norm, solve_ms=k.solve_ms)
 
 

@@ -173,6 +173,9 @@ typedef struct
 int hdk_pcg(const hdk_csr *A, hdk_amg *M /* NULL: none */, const double *b_d, double *x_d,
             hdk_krylov *k);
 int hdk_gmres(const hdk_csr *A, hdk_amg *M, const double *b_d, double *x_d, hdk_krylov *k);
+/* "next" row 8f-3: the other Krylov callers of the same kernels (reference src/internal/solver.c:229-252) */
+int hdk_fgmres(const hdk_csr *A, hdk_amg *M, const double *b_d, double *x_d, hdk_krylov *k);
+int hdk_bicgstab(const hdk_csr *A, hdk_amg *M, const double *b_d, double *x_d, hdk_krylov *k);
 
 /* ---- measurement helpers: average kernel time in ms over `reps` back-to-back launches of
  * one hot kernel on the compute stream, CUDA-event timed (bench.py roofline leg).

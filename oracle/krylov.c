@@ -76,13 +76,21 @@ int opcg(const ocsr *A, oamg *M, const double *b, double *x, okrylov *k)
    return 0;
 }
 
-int ogmres(const ocsr *A, oamg *M, const double *b, double *x, okrylov *k)
+/* flexible != 0: hypre krylov/flexgmres.c -- the preconditioned directions z_j = M^{-1} p_j are
+ * stored and the correction is x += sum_j y_j z_j (no extra preconditioner application). */
+static int gmres_impl(const ocsr *A, oamg *M, const double *b, double *x, okrylov *k, int flexible)
 {
    int      n = A->nrows, kd = k->krylov_dim > 0 ? k->krylov_dim : 30;
    double  *r = (double *)calloc((size_t)n + 1, sizeof(double));
    double  *w = (double *)calloc((size_t)n + 1, sizeof(double));
    double **p = (double **)malloc(sizeof(double *) * (size_t)(kd + 1));
    for (int j = 0; j <= kd; j++) p[j] = (double *)calloc((size_t)n + 1, sizeof(double));
+   double **z = NULL;
+   if (flexible)
+   {
+      z = (double **)malloc(sizeof(double *) * (size_t)(kd + 1));
+      for (int j = 0; j <= kd; j++) z[j] = (double *)calloc((size_t)n + 1, sizeof(double));
+   }
    double  *c = (double *)calloc((size_t)kd + 1, sizeof(double));
    double  *s = (double *)calloc((size_t)kd + 1, sizeof(double));
    double  *rs = (double *)calloc((size_t)kd + 2, sizeof(double));
@@ -116,8 +124,9 @@ int ogmres(const ocsr *A, oamg *M, const double *b, double *x, okrylov *k)
       while (i < kd && iter < k->max_iter)
       {
          i++; iter++;
-         precond(M, n, p[i - 1], r);
-         ocsr_matvec(1.0, A, r, 0.0, p[i]);
+         double *zz = flexible ? z[i - 1] : r;
+         precond(M, n, p[i - 1], zz);
+         ocsr_matvec(1.0, A, zz, 0.0, p[i]);
          for (int j = 0; j < i; j++)
          {
             HH(j, i - 1) = ovec_dot(n, p[j], p[i]);
@@ -155,10 +164,17 @@ int ogmres(const ocsr *A, oamg *M, const double *b, double *x, okrylov *k)
          t += rs[kk];
          rs[kk] = t / HH(kk, kk);
       }
-      for (int j = 0; j < n; j++) w[j] = rs[i - 1] * p[i - 1][j];
-      for (int j = i - 2; j >= 0; j--) axpy(n, rs[j], p[j], w);
-      precond(M, n, w, r);
-      axpy(n, 1.0, r, x);
+      if (flexible)
+      {
+         for (int j = i - 1; j >= 0; j--) axpy(n, rs[j], z[j], x);
+      }
+      else
+      {
+         for (int j = 0; j < n; j++) w[j] = rs[i - 1] * p[i - 1][j];
+         for (int j = i - 2; j >= 0; j--) axpy(n, rs[j], p[j], w);
+         precond(M, n, w, r);
+         axpy(n, 1.0, r, x);
+      }
       if (r_norm <= eps)
       {
          if (k->skip_real_res_check) { k->converged = 1; break; }
@@ -188,7 +204,72 @@ int ogmres(const ocsr *A, oamg *M, const double *b, double *x, okrylov *k)
    k->iters        = iter;
    k->rel_res_norm = b_norm > 0.0 ? r_norm / b_norm : r_norm;
    for (int j = 0; j <= kd; j++) free(p[j]);
+   if (z) { for (int j = 0; j <= kd; j++) free(z[j]); free(z); }
    free(p); free(c); free(s); free(rs); free(hh); free(r); free(w);
 #undef HH
+   return 0;
+}
+
+int ogmres(const ocsr *A, oamg *M, const double *b, double *x, okrylov *k) { return gmres_impl(A, M, b, x, k, 0); }
+int ofgmres(const ocsr *A, oamg *M, const double *b, double *x, okrylov *k) { return gmres_impl(A, M, b, x, k, 1); }
+
+/* hypre krylov/bicgstab.c (hypre_BiCGSTABSolve), right-preconditioned, stop_crit 0. */
+int obicgstab(const ocsr *A, oamg *M, const double *b, double *x, okrylov *k)
+{
+   int     n = A->nrows;
+   double *r0 = (double *)calloc((size_t)n + 1, sizeof(double)), *r = (double *)calloc((size_t)n + 1, sizeof(double));
+   double *p = (double *)calloc((size_t)n + 1, sizeof(double)), *v = (double *)calloc((size_t)n + 1, sizeof(double));
+   double *q = (double *)calloc((size_t)n + 1, sizeof(double)), *s = (double *)calloc((size_t)n + 1, sizeof(double));
+   const double epsmac = 1.e-128;
+   k->iters = 0; k->converged = 0;
+   double b_norm = sqrt(ovec_dot(n, b, b));
+   ocsr_residual(A, x, b, r0);
+   memcpy(r, r0, sizeof(double) * (size_t)n);
+   memcpy(p, r0, sizeof(double) * (size_t)n);
+   double r_norm = sqrt(ovec_dot(n, r, r));
+   double den = b_norm > 0.0 ? b_norm : r_norm;
+   double eps = k->rel_tol * den;
+   if (k->abs_tol > eps) eps = k->abs_tol;
+   if (k->hist) k->hist[0] = r_norm;
+   int    iter = 0;
+   double res = ovec_dot(n, r0, r);
+   while (iter < k->max_iter && res != 0.0)
+   {
+      if (r_norm == 0.0) { k->converged = 1; break; }
+      iter++;
+      precond(M, n, p, v);
+      ocsr_matvec(1.0, A, v, 0.0, q);
+      double temp = ovec_dot(n, r0, q);
+      if (fabs(temp) < epsmac) break;
+      double alpha = res / temp;
+      axpy(n, alpha, v, x);
+      axpy(n, -alpha, q, r);
+      precond(M, n, r, v);
+      ocsr_matvec(1.0, A, v, 0.0, s);
+      double gn = ovec_dot(n, r, s), gd = ovec_dot(n, s, s);
+      double gamma = (gn == 0.0 && gd == 0.0) ? 0.0 : gn / gd;
+      axpy(n, gamma, v, x);
+      axpy(n, -gamma, s, r);
+      r_norm = sqrt(ovec_dot(n, r, r));
+      if (k->hist) k->hist[iter] = r_norm;
+      if (r_norm <= eps)
+      {
+         ocsr_residual(A, x, b, r);
+         r_norm = sqrt(ovec_dot(n, r, r));
+         if (r_norm <= eps) { k->converged = 1; break; }
+      }
+      if (fabs(res) < epsmac) break;
+      double beta = 1.0 / res;
+      res = ovec_dot(n, r0, r);
+      beta *= res;
+      axpy(n, -gamma, q, p);
+      if (fabs(gamma) < epsmac) break;
+      double sc = beta * alpha / gamma;
+      for (int j = 0; j < n; j++) p[j] *= sc;
+      axpy(n, 1.0, r, p);
+   }
+   k->iters = iter;
+   k->rel_res_norm = b_norm > 0.0 ? r_norm / b_norm : r_norm;
+   free(r0); free(r); free(p); free(v); free(q); free(s);
    return 0;
 }

@@ -127,6 +127,8 @@ typedef struct
 
 int opcg(const ocsr *A, oamg *M, const double *b, double *x, okrylov *k);
 int ogmres(const ocsr *A, oamg *M, const double *b, double *x, okrylov *k);
+int ofgmres(const ocsr *A, oamg *M, const double *b, double *x, okrylov *k);
+int obicgstab(const ocsr *A, oamg *M, const double *b, double *x, okrylov *k);
 
 /* ---- gen.c ---- */
 ocsr *ogen_laplace7(int nx, int ny, int nz, double cx, double cy, double cz);

@@ -99,6 +99,8 @@ def lib():
         L.oamg_precond.argtypes = [C.POINTER(OAMG), PD, PD]
         L.opcg.argtypes = [PO, C.POINTER(OAMG), PD, PD, C.POINTER(Krylov)]
         L.ogmres.argtypes = [PO, C.POINTER(OAMG), PD, PD, C.POINTER(Krylov)]
+        L.ofgmres.argtypes = [PO, C.POINTER(OAMG), PD, PD, C.POINTER(Krylov)]
+        L.obicgstab.argtypes = [PO, C.POINTER(OAMG), PD, PD, C.POINTER(Krylov)]
         for g in ("ogen_laplace7", "ogen_laplace27"):
             getattr(L, g).restype = PO
             getattr(L, g).argtypes = [C.c_int] * 3 + [C.c_double] * 3
@@ -271,6 +273,14 @@ def gmres(A, b, x0=None, M: Hierarchy | None = None, max_iter=300, rel_tol=1e-6,
           krylov_dim=30, skip_real_res_check=0):
     return _krylov(lib().ogmres, A, b, x0, M, max_iter, rel_tol, abs_tol, krylov_dim,
                    skip_real_res_check)
+
+
+def fgmres(A, b, x0=None, M: Hierarchy | None = None, max_iter=300, rel_tol=1e-6, abs_tol=0.0, krylov_dim=30):
+    return _krylov(lib().ofgmres, A, b, x0, M, max_iter, rel_tol, abs_tol, krylov_dim, 0)
+
+
+def bicgstab(A, b, x0=None, M: Hierarchy | None = None, max_iter=100, rel_tol=1e-6, abs_tol=0.0):
+    return _krylov(lib().obicgstab, A, b, x0, M, max_iter, rel_tol, abs_tol, 0, 0)
 
 
 def strength(A, theta=0.25, max_row_sum=0.9):

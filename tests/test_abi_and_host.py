@@ -80,7 +80,7 @@ def test_yaml_errors_set_the_reference_error_bits():
         ("solver:\n  pcg:\n    max_itr: 5\npreconditioner: amg\n", INVALID_KEY),
         ("solver:\n  pcg:\n    max_iter: many\npreconditioner: amg\n", INVALID_VAL),
         ("solver: pcg\npreconditioner:\n  amg:\n    coarsening:\n      type: banana\n", INVALID_VAL),
-        ("solver: bicgstab\npreconditioner: amg\n", INVALID_SOLVER),
+        ("solver: lgmres\npreconditioner: amg\n", INVALID_SOLVER),
         ("solver: pcg\npreconditioner: mgr\n", INVALID_PRECON),
         ("solver: pcg\n\tpreconditioner: amg\n", 0x41),                           # tab indentation
         ("solver:\n  pcg:\n   max_iter: 5\npreconditioner: amg\n", 0x4),          # inconsistent indent

@@ -195,3 +195,10 @@ def test_unsupported_requests_fail_loudly(gpu):
         hd.solve((indptr, cols, data), rhs, options=opts, row_start=0, row_end=15)
     res = hd.solve((indptr, cols, data), rhs, options=dict(BASE, preconditioner="jacobi"), row_start=0, row_end=15)
     assert res.converged
+
+
+@pytest.mark.parametrize("solver", ["fgmres", "bicgstab"])
+def test_api_fgmres_bicgstab(gpu, solver):
+    A, b = O.gen("convdif", 20, 8, 8, c=(1e-3, 1.0, 0.1))
+    res = hd.solve(A, b, options={"solver": {solver: {"relative_tol": 1.0e-8, "max_iter": 60}}, "preconditioner": "amg"})
+    assert res.converged and np.linalg.norm(b - A @ res.x) <= 1e-8 * np.linalg.norm(b) * 1.0001

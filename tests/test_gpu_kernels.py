@@ -213,3 +213,17 @@ def test_known_answer_systems(gpu):
         info = gpu.pcg(dA, db, dx, M, rel_tol=1e-8)
         assert info["converged"]
         assert np.allclose(dx.get(), sol, atol=1e-6)
+
+
+@pytest.mark.parametrize("solver", ["fgmres", "bicgstab"])
+def test_other_krylov_callers_match_oracle(gpu, solver):
+    """FGMRES and BiCGSTAB over the same kernels (reference src/internal/solver.c:229-252)."""
+    A, b = O.gen("convdif", 24, 8, 8, c=(1e-3, 1.0, 0.1))
+    n = A.shape[0]
+    H, dA, M = _compare_hierarchy(gpu, A)
+    db, dx = gpu.DVec(n, b), gpu.DVec(n)
+    info = getattr(gpu, solver)(dA, db, dx, M, rel_tol=1e-9, max_iter=100)
+    xr, ir = getattr(O, solver)(A, b, M=H, rel_tol=1e-9, max_iter=100)
+    assert info["converged"] and abs(info["iters"] - ir["iters"]) <= 1
+    assert np.linalg.norm(dx.get() - xr) <= 1e-8 * np.linalg.norm(xr)
+    assert np.linalg.norm(b - A @ dx.get()) <= 1e-9 * np.linalg.norm(b) * 1.0001

@@ -96,3 +96,14 @@ def test_hierarchy_invariants():
         assert np.array_equal(Ac.indices[Ac.indptr[:-1]], np.arange(Ac.shape[0]))  # diagonal first
         Pc = P[cf == 1]
         assert np.allclose(Pc.data, 1.0) and Pc.nnz == Ac.shape[0]
+
+
+def test_fgmres_bicgstab_against_scipy():
+    A, b = O.gen("convdif", 24, 8, 8, c=(1e-3, 1.0, 0.1))
+    H = O.Hierarchy(A, O.default_params(True))
+    xs = spla.spsolve(A.tocsc(), b)
+    xg, ig = O.gmres(A, b, M=H, rel_tol=1e-10)
+    for fn in (O.fgmres, O.bicgstab):
+        x, info = fn(A, b, M=H, rel_tol=1e-10, max_iter=100)
+        assert info["converged"] and np.linalg.norm(x - xs) <= 1e-8 * np.linalg.norm(xs)
+    assert O.fgmres(A, b, M=H, rel_tol=1e-10)[1]["iters"] == ig["iters"]   # fixed preconditioner: FGMRES == GMRES
