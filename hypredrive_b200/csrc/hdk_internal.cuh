@@ -90,13 +90,19 @@ struct DevCSR
    int    *col = nullptr;
    double *val = nullptr;
    // SpMV analysis (row-length statistics -> kernel choice)
-   int     kind = 0;          // 0 stream, 1 vector (warp per row)
+   int     kind = 0;          // 0 stream, 1 vector (warp per row), 2 sliced-ELL
    int     max_row = 0;
    double  avg_row = 0.0;
    int     tgt = 0, cap = 0;  // stream kernel: non-zeros per CTA, shared-memory entries per stage
    int     lpr = 1;           // stream kernel: lanes per row (1, 2, 4, 8)
    int     nblk = 0;          // stream kernel: number of nnz-balanced row blocks
    int    *blk_row = nullptr; // nblk+1 first rows
+   // sliced-ELL copy (kind 2): slices of 32 rows stored column-major, see hdk_spmv.cu
+   int     nslice = 0;
+   int    *sl_off = nullptr;  // nslice+1 prefix sums of slice widths (units of 32 entries)
+   int    *sl_meta = nullptr; // nslice*32: (row length << 5) | row offset inside the slice
+   int    *sl_col = nullptr;
+   double *sl_val = nullptr;
    bool    owns = true;
 };
 

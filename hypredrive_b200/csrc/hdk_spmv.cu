@@ -16,6 +16,7 @@
 //    bit-identical to the CPU oracle.  HBM sees only perfectly contiguous bulk reads.
 //  * VECTOR (longer rows): one warp per row, shuffle reduction.
 #include "hdk_internal.cuh"
+#include "hdk_amg.cuh"
 #include <stdlib.h>
 #include <map>
 
@@ -36,6 +37,10 @@ struct SpmvDev
    int           nrows, fin;
    double       *fin_out, *scal, *partials;
    unsigned     *ticket;
+   // sliced-ELL operands (kind 2)
+   const int    *sl_off, *sl_meta, *sl_col;
+   const double *sl_val;
+   int           nslice;
 };
 
 // ---- PTX helpers: mbarrier + 1-D bulk tensor-memory-accelerator copies -------------------
@@ -307,6 +312,183 @@ __global__ void __launch_bounds__(ST, 4) k_spmv_tma(SpmvDev a, int nblk, int cap
    }
 }
 
+// ---------------------------------------------------------------------------------------
+// Sliced-ELL kernel for the irregular operators of the hierarchy (coarse A, P, R).
+// Slices of 32 consecutive rows are stored column-major (entry k of the 32 rows is one
+// contiguous 256-byte / 128-byte segment), rows ordered by decreasing length inside the slice
+// so that the active lanes of every column load are a prefix.  One warp owns a slice, one lane
+// a row: val / col loads are perfectly coalesced streaming loads straight from HBM (no
+// shared-memory staging, no bank conflicts), the x gathers of a warp instruction touch the
+// same stencil position of 32 neighbouring rows, and every row is accumulated sequentially in
+// its stored order with separately rounded multiply and add.
+// ---------------------------------------------------------------------------------------
+constexpr int SELL_T = 256;
+
+template <int MODE>
+__device__ __forceinline__ double row_epilogue(const SpmvDev &a, const RowOps &o, double acc)
+{
+   if (MODE == SPMV_SET || MODE == SPMV_ADD || MODE == SPMV_RESIDUAL) return acc;
+   if (MODE == SPMV_AXPBY)
+      return (a.beta == 0.0) ? __dmul_rn(a.alpha, acc) : __dadd_rn(__dmul_rn(a.alpha, acc), __dmul_rn(a.beta, o.yo));
+   if (MODE == SPMV_JACOBI)
+      return (o.d != 0.0) ? __dadd_rn(o.xo, __ddiv_rn(__dmul_rn(a.w, acc), o.d)) : o.xo;
+   return (o.d != 0.0) ? __ddiv_rn(__dmul_rn(a.w, acc), o.d) : 0.0;
+}
+
+template <int MODE, bool DOT>
+__global__ void __launch_bounds__(SELL_T) k_spmv_sell(SpmvDev a)
+{
+   constexpr bool SUB = (MODE == SPMV_RESIDUAL || MODE == SPMV_JACOBI || MODE == SPMV_JACOBI_R);
+   __shared__ double red[SELL_T / 32];
+   __shared__ int    flag;
+   const int lane = threadIdx.x & 31;
+   const int wpb  = SELL_T / 32;
+   double    dacc = 0.0;
+   for (int s = blockIdx.x * wpb + (threadIdx.x >> 5); s < a.nslice; s += gridDim.x * wpb)
+   {
+      const int  meta  = __ldg(a.sl_meta + (size_t)s * 32 + lane);
+      const int  len   = meta >> 5;
+      const int  r     = s * 32 + (meta & 31);
+      const bool valid = r < a.nrows;
+      const size_t base = (size_t)__ldg(a.sl_off + s) * 32 + lane;
+      RowOps o;
+      o.b = o.d = o.xo = o.yo = o.dv = 0.0;
+      if (valid)
+      {
+         if (SUB) o.b = a.b[r];
+         if (MODE == SPMV_JACOBI || MODE == SPMV_JACOBI_R) o.d = a.d[r];
+         if (MODE == SPMV_JACOBI) o.xo = a.x[r];
+         if (MODE == SPMV_ADD || MODE == SPMV_AXPBY) o.yo = a.y[r];
+         if (DOT) o.dv = a.dotv[r];
+      }
+      double        acc = SUB ? o.b : ((MODE == SPMV_ADD) ? o.yo : 0.0);
+      const int    *cp  = a.sl_col + base;
+      const double *vp  = a.sl_val + base;
+      int           k   = 0;
+      for (; k + 4 <= len; k += 4)
+      {
+         int    c0 = __ldcs(cp + (size_t)k * 32), c1 = __ldcs(cp + (size_t)(k + 1) * 32);
+         int    c2 = __ldcs(cp + (size_t)(k + 2) * 32), c3 = __ldcs(cp + (size_t)(k + 3) * 32);
+         double v0 = __ldcs(vp + (size_t)k * 32), v1 = __ldcs(vp + (size_t)(k + 1) * 32);
+         double v2 = __ldcs(vp + (size_t)(k + 2) * 32), v3 = __ldcs(vp + (size_t)(k + 3) * 32);
+         double x0 = __ldg(a.x + c0), x1 = __ldg(a.x + c1), x2 = __ldg(a.x + c2), x3 = __ldg(a.x + c3);
+         double p0 = __dmul_rn(v0, x0), p1 = __dmul_rn(v1, x1), p2 = __dmul_rn(v2, x2), p3 = __dmul_rn(v3, x3);
+         if (SUB) { acc = __dadd_rn(acc, -p0); acc = __dadd_rn(acc, -p1); acc = __dadd_rn(acc, -p2); acc = __dadd_rn(acc, -p3); }
+         else { acc = __dadd_rn(acc, p0); acc = __dadd_rn(acc, p1); acc = __dadd_rn(acc, p2); acc = __dadd_rn(acc, p3); }
+      }
+      if (k < len)
+      {
+         const bool h1 = k + 1 < len, h2 = k + 2 < len;
+         int    c0 = __ldcs(cp + (size_t)k * 32);
+         int    c1 = h1 ? __ldcs(cp + (size_t)(k + 1) * 32) : c0;
+         int    c2 = h2 ? __ldcs(cp + (size_t)(k + 2) * 32) : c0;
+         double v0 = __ldcs(vp + (size_t)k * 32);
+         double v1 = h1 ? __ldcs(vp + (size_t)(k + 1) * 32) : 0.0;
+         double v2 = h2 ? __ldcs(vp + (size_t)(k + 2) * 32) : 0.0;
+         double x0 = __ldg(a.x + c0), x1 = __ldg(a.x + c1), x2 = __ldg(a.x + c2);
+         double p0 = __dmul_rn(v0, x0);
+         acc       = __dadd_rn(acc, SUB ? -p0 : p0);
+         if (h1) { double p1 = __dmul_rn(v1, x1); acc = __dadd_rn(acc, SUB ? -p1 : p1); }
+         if (h2) { double p2 = __dmul_rn(v2, x2); acc = __dadd_rn(acc, SUB ? -p2 : p2); }
+      }
+      if (valid)
+      {
+         double yn = row_epilogue<MODE>(a, o, acc);
+         a.y[r]    = yn;
+         if (DOT) dacc += o.dv * yn;
+      }
+   }
+   if (DOT)
+   {
+      double bs = block_sum<SELL_T>(dacc, red);
+      __syncthreads();
+      grid_finish<SELL_T>(bs, a.partials, a.ticket, a.fin, a.fin_out, a.scal, red, &flag);
+   }
+}
+
+// slice metadata: lanes ranked by decreasing row length (ties by row), slice width = longest row
+__global__ void k_sell_meta(const int *rowptr, int nrows, int nslice, int *meta, int *width, int *max_slice_nnz)
+{
+   const int lane = threadIdx.x & 31;
+   const int s    = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+   if (s >= nslice) return;
+   const int r   = s * 32 + lane;
+   const int len = (r < nrows) ? rowptr[r + 1] - rowptr[r] : 0;
+   const int key = (r < nrows) ? len : -1;
+   int       rank = 0, w = 0;
+   for (int j = 0; j < 32; ++j)
+   {
+      int kj = __shfl_sync(0xffffffffu, key, j);
+      rank += (kj > key) || (kj == key && j < lane);
+      w = kj > w ? kj : w;
+   }
+   meta[(size_t)s * 32 + rank] = (len << 5) | lane;
+   if (lane == 0)
+   {
+      width[s] = w;
+      int hi   = s * 32 + 32;
+      if (hi > nrows) hi = nrows;
+      atomicMax(max_slice_nnz, rowptr[hi] - rowptr[s * 32]);
+   }
+}
+
+// copy CSR rows into the slices through shared memory (coalesced on both sides); with `sort`
+// the entries of a row after a leading diagonal are ordered by column, which lines up the
+// gathers of neighbouring rows
+template <bool SORT>
+__global__ void k_sell_fill(const int *rowptr, const int *col, const double *val, int nrows, int nslice, const int *sl_off,
+                            const int *meta, int *scol, double *sval, int cap)
+{
+   extern __shared__ __align__(16) unsigned char sm_raw[];
+   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+   double   *vs = reinterpret_cast<double *>(sm_raw) + (size_t)w * cap;
+   int      *cs = reinterpret_cast<int *>(sm_raw + (size_t)nw * cap * sizeof(double)) + (size_t)w * cap;
+   const int s  = blockIdx.x * nw + w;
+   if (s >= nslice) return;
+   int hi = s * 32 + 32;
+   if (hi > nrows) hi = nrows;
+   const int k0 = rowptr[s * 32], k1 = rowptr[hi];
+   for (int k = k0 + lane; k < k1; k += 32) { cs[k - k0] = col[k]; vs[k - k0] = val[k]; }
+   __syncwarp();
+   const int m = meta[(size_t)s * 32 + lane], len = m >> 5, r = s * 32 + (m & 31);
+   if (r >= nrows || len == 0) return;
+   const int rs = rowptr[r] - k0;
+   if (SORT)
+   {
+      const int b = rs + ((cs[rs] == r) ? 1 : 0), e = rs + len;
+      for (int k = b + 1; k < e; ++k)
+      {
+         int    c = cs[k];
+         double v = vs[k];
+         int    j = k - 1;
+         while (j >= b && cs[j] > c) { cs[j + 1] = cs[j]; vs[j + 1] = vs[j]; --j; }
+         cs[j + 1] = c; vs[j + 1] = v;
+      }
+   }
+   const size_t base = (size_t)sl_off[s] * 32 + lane;
+   for (int k = 0; k < len; ++k)
+   {
+      scol[base + (size_t)k * 32] = cs[rs + k];
+      sval[base + (size_t)k * 32] = vs[rs + k];
+   }
+}
+
+template <int MODE, bool DOT>
+static int launch_sell(const DevCSR &A, const SpmvDev &d)
+{
+   static int occ = 0;
+   if (!occ)
+   {
+      HDK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_spmv_sell<MODE, DOT>, SELL_T, 0));
+      if (occ < 1) occ = 1;
+   }
+   int grid = cdiv(A.nslice, SELL_T / 32);
+   int cap  = g.sm_count * occ;
+   if (grid > cap) grid = cap;
+   k_spmv_sell<MODE, DOT><<<grid, SELL_T, 0, g.stream>>>(d);
+   return HDK_OK;
+}
+
 // one warp per row; lanes stride the row with scalar loads (rows here are long, so each warp
 // reads whole 128-byte lines).  Summation order differs from the oracle (tolerance parity).
 template <int MODE, bool DOT>
@@ -390,6 +572,10 @@ static int launch_mode(const DevCSR &A, const SpmvDev &d, bool dot)
          default: if (dot) HDK_TRY((launch_tma<MODE, true, 1>(A, d))); else HDK_TRY((launch_tma<MODE, false, 1>(A, d))); break;
       }
    }
+   else if (A.kind == 2)
+   {
+      if (dot) HDK_TRY((launch_sell<MODE, true>(A, d))); else HDK_TRY((launch_sell<MODE, false>(A, d)));
+   }
    else
    {
       int grid = cdiv(A.nrows, ST / 32);
@@ -412,6 +598,7 @@ int spmv_launch(const DevCSR &A, int mode, const SpmvArgs &s)
    d.w = s.w; d.alpha = s.alpha; d.beta = s.beta;
    d.nrows = A.nrows; d.fin = s.fin; d.fin_out = s.fin_out;
    d.scal = g.dscal; d.partials = g.partials; d.ticket = g.counters;
+   d.sl_off = A.sl_off; d.sl_meta = A.sl_meta; d.sl_col = A.sl_col; d.sl_val = A.sl_val; d.nslice = A.nslice;
    bool dot = (s.fin != FIN_NONE && s.dotv != nullptr);
    switch (mode)
    {
@@ -455,9 +642,64 @@ __global__ void k_blk_rows(const int *rowptr, int nrows, int nblk, int tgt, int 
    blk_row[b] = lo;
 }
 
+static void sell_free(DevCSR &A)
+{
+   dfree(A.sl_off); dfree(A.sl_meta); dfree(A.sl_col); dfree(A.sl_val);
+   A.sl_off = A.sl_meta = A.sl_col = nullptr; A.sl_val = nullptr; A.nslice = 0;
+}
+
+// build the sliced-ELL copy; leaves A.kind untouched (and no copy) when the layout does not pay:
+// too much padding or slices that do not fit the staging buffer of the fill kernel
+static int sell_build(DevCSR &A)
+{
+   static int sort = -1;
+   if (sort < 0) { const char *e = getenv("HDK_SELL_SORT"); sort = e ? atoi(e) : 1; }
+   const int ns = cdiv(A.nrows, 32);
+   int      *width = nullptr, *dmax = reinterpret_cast<int *>(g.dscal + S_TMP3);
+   HDK_TRY(dalloc(&A.sl_meta, (size_t)ns * 32));
+   HDK_TRY(dalloc(&A.sl_off, (size_t)ns + 1));
+   HDK_TRY(dalloc(&width, (size_t)ns + 1));
+   HDK_CUDA(cudaMemsetAsync(width + ns, 0, sizeof(int), g.stream));
+   HDK_CUDA(cudaMemsetAsync(dmax, 0, sizeof(int), g.stream));
+   k_sell_meta<<<cdiv(ns, 8), 256, 0, g.stream>>>(A.rowptr, A.nrows, ns, A.sl_meta, width, dmax);
+   HDK_LAUNCH_CHECK();
+   HDK_TRY(exclusive_scan_int(width, A.sl_off, ns + 1));
+   int h[2] = {0, 0};
+   HDK_CUDA(cudaMemcpyAsync(&h[0], A.sl_off + ns, sizeof(int), cudaMemcpyDeviceToHost, g.stream));
+   HDK_CUDA(cudaMemcpyAsync(&h[1], dmax, sizeof(int), cudaMemcpyDeviceToHost, g.stream));
+   HDK_CUDA(cudaStreamSynchronize(g.stream));
+   dfree(width);
+   const int64_t padded = (int64_t)h[0] * 32;
+   const int     cap    = (h[1] + 3) & ~3;
+   int           nw     = 4;
+   while (nw > 1 && (size_t)nw * cap * 12 > 200 * 1024) nw >>= 1;
+   if (padded > 3 * (int64_t)A.nnz + 4096 || (size_t)nw * cap * 12 > 200 * 1024) { sell_free(A); return HDK_OK; }
+   HDK_TRY(dalloc(&A.sl_col, (size_t)padded + 32));
+   HDK_TRY(dalloc(&A.sl_val, (size_t)padded + 32));
+   const size_t smem = (size_t)nw * cap * 12;
+   const bool   do_sort = sort && A.nrows == A.ncols;
+   if (do_sort)
+   {
+      HDK_CUDA(cudaFuncSetAttribute(k_sell_fill<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      k_sell_fill<true><<<cdiv(ns, nw), nw * 32, smem, g.stream>>>(A.rowptr, A.col, A.val, A.nrows, ns, A.sl_off, A.sl_meta,
+                                                                    A.sl_col, A.sl_val, cap);
+   }
+   else
+   {
+      HDK_CUDA(cudaFuncSetAttribute(k_sell_fill<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      k_sell_fill<false><<<cdiv(ns, nw), nw * 32, smem, g.stream>>>(A.rowptr, A.col, A.val, A.nrows, ns, A.sl_off, A.sl_meta,
+                                                                     A.sl_col, A.sl_val, cap);
+   }
+   HDK_LAUNCH_CHECK();
+   A.nslice = ns;
+   A.kind   = 2;
+   return HDK_OK;
+}
+
 int csr_analyze(DevCSR &A)
 {
    if (A.blk_row) { dfree(A.blk_row); A.blk_row = nullptr; }
+   sell_free(A);
    A.nblk = 0; A.kind = 0; A.max_row = 0; A.avg_row = 0.0;
    if (A.nrows <= 0) return HDK_OK;
    int *dmax = reinterpret_cast<int *>(g.dscal + S_TMP3);
@@ -472,6 +714,13 @@ int csr_analyze(DevCSR &A)
    A.max_row = hmax;
    A.avg_row = (double)A.nnz / (double)A.nrows;
    A.kind    = (hmax <= S_MAXR) ? 0 : 1;
+   if (A.kind == 0 && A.val)
+   {
+      // irregular operators (long or uneven rows) go to the sliced-ELL kernel
+      static double sell_min = -1.0;
+      if (sell_min < 0) { const char *e = getenv("HDK_SELL_MIN_AVG"); sell_min = e ? atof(e) : 12.0; }
+      if (A.avg_row > sell_min) HDK_TRY(sell_build(A));
+   }
    if (A.kind == 0)
    {
       // non-zeros per block: about one row per thread (`mult` x 256 rows), 64-aligned
@@ -518,6 +767,7 @@ void csr_free(DevCSR &A)
 {
    if (A.owns) { dfree(A.rowptr); dfree(A.col); dfree(A.val); }
    dfree(A.blk_row);
+   sell_free(A);
    A = DevCSR();
 }
 

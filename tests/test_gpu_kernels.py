@@ -59,7 +59,23 @@ def test_spmv_ragged_and_empty_rows(gpu):
     dA.matvec(dx, dy, alpha=2.0, beta=0.0)
     ref = 2.0 * (A @ x)
     assert np.allclose(dy.get(), ref, rtol=1e-13, atol=1e-13)
-    assert dA.spmv_kind()["kind"] == 0
+    assert dA.spmv_kind()["kind"] == 2                     # uneven rows, average > 12: sliced-ELL kernel
+    # short ragged rows stay on the bulk-copy stream kernel; one lane per row = scipy's order
+    B = _random_csr(4999, 8, max_len=12)
+    dB = gpu.DCsr.from_scipy(B)
+    assert dB.spmv_kind()["kind"] == 0
+    xb = np.random.default_rng(3).standard_normal(4999)
+    dxb, dyb, dbb = gpu.DVec(4999, xb), gpu.DVec(4999), gpu.DVec(4999, xb[::-1].copy())
+    dB.matvec(dxb, dyb)
+    assert np.allclose(dyb.get(), B @ xb, rtol=1e-13, atol=1e-13)
+    # every fused epilogue of the sliced-ELL kernel on a row count that is not a multiple of 32
+    b = np.random.default_rng(4).standard_normal(5000)
+    db, dr = gpu.DVec(5000, b), gpu.DVec(5000)
+    dA.residual(dx, db, dr)
+    assert np.allclose(dr.get(), b - A @ x, rtol=1e-12, atol=1e-12)
+    dy2 = gpu.DVec(5000, b)
+    dA.matvec(dx, dy2, alpha=-0.5, beta=3.0)
+    assert np.allclose(dy2.get(), -0.5 * (A @ x) + 3.0 * b, rtol=1e-12, atol=1e-12)
 
 
 def test_spmv_long_rows_vector_kernel(gpu):
