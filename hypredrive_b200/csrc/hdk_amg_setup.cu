@@ -1362,23 +1362,6 @@ static int build_dense_inverse(const DevCSR &A, double **inv)
    return HDK_OK;
 }
 
-// sort the off-diagonal entries of every row by column (diagonal stays first): improves the
-// coalescing of the x gathers across consecutive coarse rows in the solve phase
-__global__ void k_sort_rows(const int *rp, int *col, double *val, int n)
-{
-   int i = blockIdx.x * blockDim.x + threadIdx.x;
-   if (i >= n) return;
-   int b = rp[i] + 1, e = rp[i + 1];
-   for (int k = b + 1; k < e; k++)
-   {
-      int    c = col[k];
-      double v = val[k];
-      int    j = k - 1;
-      while (j >= b && col[j] > c) { col[j + 1] = col[j]; val[j + 1] = val[j]; j--; }
-      col[j + 1] = c; val[j + 1] = v;
-   }
-}
-
 // wrap a rank-local DevCSR as a ParCSR object with an empty offd block
 static hdk_csr_s *wrap_local(DevCSR &D, int64_t grows)
 {
@@ -1530,6 +1513,7 @@ static int setup_serial(const hdk_csr_s *A0, const hdk_amg_params *prm, hdk_amg_
       stage_mark("rap", level);
       if ((rc = csr_analyze(P))) break;
       if ((rc = csr_analyze(R))) break;
+      C.coarse_op = true;
       if ((rc = csr_analyze(C))) break;
       stage_mark("analyze", level);
       nnz_sum += C.nnz;
@@ -1541,16 +1525,6 @@ static int setup_serial(const hdk_csr_s *A0, const hdk_amg_params *prm, hdk_amg_
       level++;
       if (level == prm->max_levels - 1 || nc <= prm->max_coarse_size) more = false;
       if (!M->keep_debug) csr_free(M->lev[(size_t)level - 1].S);
-   }
-   if (rc == HDK_OK && getenv("HDK_SORT_COARSE") && atoi(getenv("HDK_SORT_COARSE")) == 1)
-   {
-      for (int l = 1; l <= level && rc == HDK_OK; l++)
-      {
-         DevCSR &D = M->lev[(size_t)l].A->diag;
-         k_sort_rows<<<cdiv(D.nrows, 128), 128, 0, g.stream>>>(D.rowptr, D.col, D.val, D.nrows);
-         g.launches++;
-         rc = csr_analyze(D);
-      }
    }
    if (rc == HDK_OK)
    {

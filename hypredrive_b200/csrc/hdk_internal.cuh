@@ -103,12 +103,14 @@ struct DevCSR
    int    *sl_meta = nullptr; // nslice*32: (row length << 5) | row offset inside the slice
    int    *sl_col = nullptr;
    double *sl_val = nullptr;
+   bool    coarse_op = false; // Galerkin operator of the hierarchy: its stored column order may be changed
    bool    owns = true;
 };
 
 int  csr_alloc(DevCSR &A, int nrows, int ncols, int nnz, bool values = true);
 void csr_free(DevCSR &A);
 int  csr_analyze(DevCSR &A);
+int  tune_set(const char *key, double value);
 
 // epilogue selectors of the fused SpMV family (see hdk_spmv.cu)
 enum SpmvMode

@@ -152,6 +152,12 @@ int hdk_copy_h2d(void *dst_d, const void *src_h, size_t bytes)
 
 } // extern "C"
 
+extern "C" int hdk_tune(const char *key, double value)
+{
+   if (!key) return hdk::set_error(HDK_ERR_INVALID, "hdk_tune: null key");
+   return hdk::tune_set(key, value);
+}
+
 // cudaProfilerStart/Stop bracket for `ncu --profile-from-start off` (bench.py HDK_PROFILE_RANGE=1)
 #include <cuda_profiler_api.h>
 extern "C" int hdk_profiler_range(int start)

@@ -18,6 +18,7 @@
 #include "hdk_internal.cuh"
 #include "hdk_amg.cuh"
 #include <stdlib.h>
+#include <string.h>
 #include <map>
 
 namespace hdk {
@@ -26,6 +27,44 @@ constexpr int ST       = 256;   // threads per CTA
 constexpr int S_TGT_LO = 1024;  // non-zeros per block: bounds
 constexpr int S_TGT_HI = 8192;
 constexpr int S_MAXR   = 1024;  // longest row the stream kernel accepts
+
+// kernel-selection tunables: defaults, overridden by environment variables at first use and by
+// hdk_tune() at any time (they apply to matrices analysed afterwards)
+struct Tune
+{
+   double rows_mult     = 1.0;      // HDK_SPMV_ROWS_MULT   rows per thread of a stream-kernel block
+   double tgt_max       = 3072;     // HDK_SPMV_TGT_MAX     non-zeros per stream-kernel block (cap)
+   double lpr           = 0;        // HDK_SPMV_LPR         force lanes per row (0 = by row length)
+   double sell_min_rows = 200000;   // HDK_SELL_MIN_ROWS    sliced-ELL for matrices with at least this many rows
+   double sell_min_avg  = 0.0;      // HDK_SELL_MIN_AVG     ... and more than this many non-zeros per row
+   double sell_sort     = 1;        // HDK_SELL_SORT        sort the columns of coarse operators in the slices
+   bool   env_read      = false;
+};
+static Tune tune;
+static const struct { const char *key, *env; double Tune::*field; } tune_keys[] = {
+   {"spmv_rows_mult", "HDK_SPMV_ROWS_MULT", &Tune::rows_mult}, {"spmv_tgt_max", "HDK_SPMV_TGT_MAX", &Tune::tgt_max},
+   {"spmv_lpr", "HDK_SPMV_LPR", &Tune::lpr},                   {"sell_min_rows", "HDK_SELL_MIN_ROWS", &Tune::sell_min_rows},
+   {"sell_min_avg", "HDK_SELL_MIN_AVG", &Tune::sell_min_avg},  {"sell_sort", "HDK_SELL_SORT", &Tune::sell_sort}};
+static Tune &tunables()
+{
+   if (!tune.env_read)
+   {
+      tune.env_read = true;
+      for (const auto &k : tune_keys)
+      {
+         const char *e = getenv(k.env);
+         if (e && *e) tune.*(k.field) = atof(e);
+      }
+   }
+   return tune;
+}
+int tune_set(const char *key, double value)
+{
+   Tune &t = tunables();
+   for (const auto &k : tune_keys)
+      if (!strcmp(key, k.key)) { t.*(k.field) = value; return HDK_OK; }
+   return set_error(HDK_ERR_INVALID, "unknown tunable '%s'", key);
+}
 
 struct SpmvDev
 {
@@ -364,32 +403,31 @@ __global__ void __launch_bounds__(SELL_T) k_spmv_sell(SpmvDev a)
       double        acc = SUB ? o.b : ((MODE == SPMV_ADD) ? o.yo : 0.0);
       const int    *cp  = a.sl_col + base;
       const double *vp  = a.sl_val + base;
-      int           k   = 0;
-      for (; k + 4 <= len; k += 4)
+      // software pipeline: the val / col loads of group k+1 are in flight while the gathers of
+      // group k complete, so every lane keeps 8 streaming loads + 4 gathers outstanding
+      int    c0 = 0, c1 = 0, c2 = 0, c3 = 0;
+      double v0 = 0.0, v1 = 0.0, v2 = 0.0, v3 = 0.0;
+      if (0 < len) { c0 = __ldcs(cp); v0 = __ldcs(vp); }
+      if (1 < len) { c1 = __ldcs(cp + 32); v1 = __ldcs(vp + 32); }
+      if (2 < len) { c2 = __ldcs(cp + 64); v2 = __ldcs(vp + 64); }
+      if (3 < len) { c3 = __ldcs(cp + 96); v3 = __ldcs(vp + 96); }
+      for (int k = 0; k < len; k += 4)
       {
-         int    c0 = __ldcs(cp + (size_t)k * 32), c1 = __ldcs(cp + (size_t)(k + 1) * 32);
-         int    c2 = __ldcs(cp + (size_t)(k + 2) * 32), c3 = __ldcs(cp + (size_t)(k + 3) * 32);
-         double v0 = __ldcs(vp + (size_t)k * 32), v1 = __ldcs(vp + (size_t)(k + 1) * 32);
-         double v2 = __ldcs(vp + (size_t)(k + 2) * 32), v3 = __ldcs(vp + (size_t)(k + 3) * 32);
-         double x0 = __ldg(a.x + c0), x1 = __ldg(a.x + c1), x2 = __ldg(a.x + c2), x3 = __ldg(a.x + c3);
-         double p0 = __dmul_rn(v0, x0), p1 = __dmul_rn(v1, x1), p2 = __dmul_rn(v2, x2), p3 = __dmul_rn(v3, x3);
-         if (SUB) { acc = __dadd_rn(acc, -p0); acc = __dadd_rn(acc, -p1); acc = __dadd_rn(acc, -p2); acc = __dadd_rn(acc, -p3); }
-         else { acc = __dadd_rn(acc, p0); acc = __dadd_rn(acc, p1); acc = __dadd_rn(acc, p2); acc = __dadd_rn(acc, p3); }
-      }
-      if (k < len)
-      {
-         const bool h1 = k + 1 < len, h2 = k + 2 < len;
-         int    c0 = __ldcs(cp + (size_t)k * 32);
-         int    c1 = h1 ? __ldcs(cp + (size_t)(k + 1) * 32) : c0;
-         int    c2 = h2 ? __ldcs(cp + (size_t)(k + 2) * 32) : c0;
-         double v0 = __ldcs(vp + (size_t)k * 32);
-         double v1 = h1 ? __ldcs(vp + (size_t)(k + 1) * 32) : 0.0;
-         double v2 = h2 ? __ldcs(vp + (size_t)(k + 2) * 32) : 0.0;
-         double x0 = __ldg(a.x + c0), x1 = __ldg(a.x + c1), x2 = __ldg(a.x + c2);
-         double p0 = __dmul_rn(v0, x0);
-         acc       = __dadd_rn(acc, SUB ? -p0 : p0);
-         if (h1) { double p1 = __dmul_rn(v1, x1); acc = __dadd_rn(acc, SUB ? -p1 : p1); }
-         if (h2) { double p2 = __dmul_rn(v2, x2); acc = __dadd_rn(acc, SUB ? -p2 : p2); }
+         const double x0 = __ldg(a.x + c0), x1 = __ldg(a.x + c1), x2 = __ldg(a.x + c2), x3 = __ldg(a.x + c3);
+         const size_t q  = (size_t)(k + 4) * 32;
+         int          n0 = 0, n1 = 0, n2 = 0, n3 = 0;
+         double       w0 = 0.0, w1 = 0.0, w2 = 0.0, w3 = 0.0;
+         if (k + 4 < len) { n0 = __ldcs(cp + q); w0 = __ldcs(vp + q); }
+         if (k + 5 < len) { n1 = __ldcs(cp + q + 32); w1 = __ldcs(vp + q + 32); }
+         if (k + 6 < len) { n2 = __ldcs(cp + q + 64); w2 = __ldcs(vp + q + 64); }
+         if (k + 7 < len) { n3 = __ldcs(cp + q + 96); w3 = __ldcs(vp + q + 96); }
+         const double p0 = __dmul_rn(v0, x0), p1 = __dmul_rn(v1, x1), p2 = __dmul_rn(v2, x2), p3 = __dmul_rn(v3, x3);
+         acc = __dadd_rn(acc, SUB ? -p0 : p0);
+         if (k + 1 < len) acc = __dadd_rn(acc, SUB ? -p1 : p1);
+         if (k + 2 < len) acc = __dadd_rn(acc, SUB ? -p2 : p2);
+         if (k + 3 < len) acc = __dadd_rn(acc, SUB ? -p3 : p3);
+         c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+         v0 = w0; v1 = w1; v2 = w2; v3 = w3;
       }
       if (valid)
       {
@@ -652,8 +690,7 @@ static void sell_free(DevCSR &A)
 // too much padding or slices that do not fit the staging buffer of the fill kernel
 static int sell_build(DevCSR &A)
 {
-   static int sort = -1;
-   if (sort < 0) { const char *e = getenv("HDK_SELL_SORT"); sort = e ? atoi(e) : 1; }
+   const bool sort = tunables().sell_sort != 0.0 && A.coarse_op;
    const int ns = cdiv(A.nrows, 32);
    int      *width = nullptr, *dmax = reinterpret_cast<int *>(g.dscal + S_TMP3);
    HDK_TRY(dalloc(&A.sl_meta, (size_t)ns * 32));
@@ -716,21 +753,21 @@ int csr_analyze(DevCSR &A)
    A.kind    = (hmax <= S_MAXR) ? 0 : 1;
    if (A.kind == 0 && A.val)
    {
-      // irregular operators (long or uneven rows) go to the sliced-ELL kernel
-      static double sell_min = -1.0;
-      if (sell_min < 0) { const char *e = getenv("HDK_SELL_MIN_AVG"); sell_min = e ? atof(e) : 12.0; }
-      if (A.avg_row > sell_min) HDK_TRY(sell_build(A));
+      // large operators go to the sliced-ELL kernel; small ones are latency-bound and do better
+      // with several lanes per row in the stream kernel
+      const Tune &t = tunables();
+      if ((double)A.nrows >= t.sell_min_rows && A.avg_row > t.sell_min_avg) HDK_TRY(sell_build(A));
    }
    if (A.kind == 0)
    {
       // non-zeros per block: about one row per thread (`mult` x 256 rows), 64-aligned
-      static double mult = -1.0;
-      if (mult < 0) { const char *e = getenv("HDK_SPMV_ROWS_MULT"); mult = e ? atof(e) : 1.0; if (mult <= 0) mult = 1.0; }
-      static int thi = -1;
-      if (thi < 0) { const char *e = getenv("HDK_SPMV_TGT_MAX"); thi = e ? atoi(e) : 3072; if (thi < S_TGT_LO) thi = S_TGT_LO; if (thi > S_TGT_HI) thi = S_TGT_HI; }
+      const Tune &t = tunables();
+      double mult = t.rows_mult > 0 ? t.rows_mult : 1.0;
+      int    thi  = (int)t.tgt_max;
+      if (thi < S_TGT_LO) thi = S_TGT_LO;
+      if (thi > S_TGT_HI) thi = S_TGT_HI;
       // lanes per row from the average row length (1 keeps the exact sequential CSR order)
-      static int lpr_force = -1;
-      if (lpr_force < 0) { const char *e = getenv("HDK_SPMV_LPR"); lpr_force = e ? atoi(e) : 0; }
+      const int lpr_force = (int)t.lpr;
       int lpr = A.avg_row <= 12.0 ? 1 : (A.avg_row <= 24.0 ? 2 : (A.avg_row <= 56.0 ? 4 : 8));
       if (lpr_force == 1 || lpr_force == 2 || lpr_force == 4 || lpr_force == 8) lpr = lpr_force;
       A.lpr   = lpr;

@@ -341,6 +341,13 @@ def time_kernel(A: DCsr, M: DAmg | None, kernel: int, reps: int = 20):
     return ms.value, by.value
 
 
+def tune(key: str, value: float):
+    """Kernel-selection tunable (hdk_tune), e.g. tune("sell_min_rows", 0)."""
+    L = lib()
+    L.hdk_tune.argtypes = [C.c_char_p, C.c_double]
+    check(L.hdk_tune(key.encode(), float(value)))
+
+
 def launch_count_reset() -> int:
     return int(lib().hdk_launch_count_reset())
 

@@ -185,6 +185,10 @@ int hdk_time_kernel(const hdk_csr *A, hdk_amg *M, int kernel, int reps, double *
                     double *algorithmic_bytes);
 /* number of kernel launches issued by this library since the last call (and reset) */
 int64_t hdk_launch_count_reset(void);
+/* kernel-selection tunables for matrices analysed after the call (same names as the HDK_*
+ * environment variables, lower case without the prefix): spmv_rows_mult, spmv_tgt_max, spmv_lpr,
+ * sell_min_rows, sell_min_avg, sell_sort.  Unknown key -> HDK_ERR_INVALID. */
+int hdk_tune(const char *key, double value);
 /* cudaProfilerStart (1) / cudaProfilerStop (0) for `ncu --profile-from-start off` */
 int hdk_profiler_range(int start);
 

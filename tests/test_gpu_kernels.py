@@ -53,13 +53,20 @@ def test_spmv_bit_exact(gpu, kind, dims, c):
 
 def test_spmv_ragged_and_empty_rows(gpu):
     A = _random_csr(5000, 7)
-    dA = gpu.DCsr.from_scipy(A)
+    gpu.tune("sell_min_rows", 0)                           # force the sliced-ELL kernel on a small matrix
+    try:
+        dA = gpu.DCsr.from_scipy(A)
+    finally:
+        gpu.tune("sell_min_rows", 200000)
     x = np.random.default_rng(2).standard_normal(5000)
     dx, dy = gpu.DVec(5000, x), gpu.DVec(5000)
     dA.matvec(dx, dy, alpha=2.0, beta=0.0)
     ref = 2.0 * (A @ x)
     assert np.allclose(dy.get(), ref, rtol=1e-13, atol=1e-13)
-    assert dA.spmv_kind()["kind"] == 2                     # uneven rows, average > 12: sliced-ELL kernel
+    assert dA.spmv_kind()["kind"] == 2
+    # user matrices keep their stored order in the slices: one lane per row = the oracle's order
+    rp, cj, va = dA.diag_arrays()
+    assert np.array_equal(dy.get(), 2.0 * O.matvec(sp.csr_matrix((va, cj, rp), shape=A.shape), x))
     # short ragged rows stay on the bulk-copy stream kernel; one lane per row = scipy's order
     B = _random_csr(4999, 8, max_len=12)
     dB = gpu.DCsr.from_scipy(B)
@@ -187,6 +194,33 @@ def test_vcycle_and_pcg_parity(gpu, kind, dims, c):
     x = dx.get()
     assert np.linalg.norm(x - x_ref) <= 1e-8 * np.linalg.norm(x_ref)   # solution rel. diff <= 1e-8
     assert np.linalg.norm(b - A @ x) / np.linalg.norm(b) < (1e-8 if kind == "convdif" else 1e-6) * 1.0001
+
+
+@pytest.mark.parametrize("sort", [0, 1])
+def test_sliced_ell_levels_parity(gpu, sort):
+    """Every operator of the hierarchy (A, P, R on all levels) on the sliced-ELL kernel: the
+    hierarchy stays bit-identical to the oracle's (the slices are a copy); the V-cycle agrees
+    within rounding, with the stored column order and with coarse rows sorted by column."""
+    A, b = O.gen("lap7", 20, 18, 16)
+    gpu.tune("sell_min_rows", 0)
+    gpu.tune("sell_sort", sort)
+    try:
+        H, dA, M = _compare_hierarchy(gpu, A)
+        assert dA.spmv_kind()["kind"] == 2
+        n = A.shape[0]
+        r = np.random.default_rng(12).standard_normal(n)
+        dr, dz = gpu.DVec(n, r), gpu.DVec(n)
+        M.apply(dr, dz)
+        z_ref = H.precond(r)
+        assert np.allclose(dz.get(), z_ref, rtol=1e-11, atol=1e-13 * np.abs(z_ref).max())
+        db, dx = gpu.DVec(n, b), gpu.DVec(n)
+        info = gpu.pcg(dA, db, dx, M, rel_tol=1e-8, max_iter=100)
+        xo, io = O.pcg(A, b, M=H, rel_tol=1e-8, max_iter=100)
+        assert abs(info["iters"] - io["iters"]) <= 1 and info["converged"]
+        assert np.linalg.norm(dx.get() - xo) <= 1e-8 * np.linalg.norm(xo)
+    finally:
+        gpu.tune("sell_min_rows", 200000)
+        gpu.tune("sell_sort", 1)
 
 
 def test_pcg_without_preconditioner_and_zero_rhs(gpu):
