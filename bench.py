@@ -54,6 +54,10 @@ preconditioner:
       num_sweeps: 1
 """
 
+# dram__bytes_read.sum + dram__bytes_write.sum per launch of the fine-level SpMV at the bench
+# workload (256^3 7-point rows per GPU), from the `ncu --set full` capture summarised under
+# profiles/ (see profiles/README.md); None when no capture exists for the selected kernel
+NCU_TRAFFIC_BYTES = {"k_spmv_sell": None, "k_spmv_tma": 1.871e9}
 CPU_SAMPLE_EDGE = 160  # cube edge of the bounded CPU sample (about 10-30 s of work on ~8 cores)
 
 
@@ -286,7 +290,7 @@ def ours(args):
     e2e_value = n_glob * e2e_it / (e2e_wall / args.steps)
     clocks = sampler.stop() if sampler else None
 
-    # ---- roofline of the dominant kernel (fine-level SpMV stream kernel), live ------------
+    # ---- roofline of the dominant kernel (fine-level SpMV), live -----------------------------
     hA, hM = drv.device_handles()
     peak, peak_src = measured_peaks()
     roof = None
@@ -298,8 +302,12 @@ def ours(args):
         extra_kernels[name] = {"ms": ms.value, "GBps": by.value / ms.value / 1e6, "bytes": by.value}
     if rank == 0:
         k0 = extra_kernels["spmv"]
+        kk, ka, km = C.c_int(), C.c_double(), C.c_int()
+        hdk.check(hdk.lib().hdk_csr_spmv_kind(hA, C.byref(kk), C.byref(ka), C.byref(km)))
+        kname = {0: "k_spmv_tma", 1: "k_spmv_vector", 2: "k_spmv_sell"}.get(kk.value, "k_spmv")
         roof = {"bound": "hbm", "achieved": k0["GBps"], "peak": peak, "unit": "GB/s", "frac": k0["GBps"] / peak,
-                "traffic": None, "kernel": "k_spmv_tma<SET> (fine level, y = A x, per GPU)", "peak_source": peak_src,
+                "traffic": NCU_TRAFFIC_BYTES.get(kname), "kernel": kname + "<SET> (fine level, y = A x, per GPU)",
+                "peak_source": peak_src,
                 "algorithmic_bytes": k0["bytes"], "ms": k0["ms"]}
     if dist is not None:
         dist.barrier()

@@ -245,6 +245,18 @@ int hdk_vec_alloc(int64_t n, double **x_d)
    return vec_fill(*x_d, 0.0, n + 8);
 }
 int hdk_vec_free(double *x_d) { return hdk_free_device(x_d); }
+int hdk_host_alloc(size_t bytes, void **p_h)
+{
+   HDK_TRY(require_init());
+   if (!p_h) return set_error(HDK_ERR_INVALID, "hdk_host_alloc: null output");
+   HDK_CUDA(cudaHostAlloc(p_h, bytes ? bytes : 8, cudaHostAllocDefault));
+   return HDK_OK;
+}
+int hdk_host_free(void *p_h)
+{
+   if (p_h) HDK_CUDA(cudaFreeHost(p_h));
+   return HDK_OK;
+}
 int hdk_vec_h2d(double *x_d, const double *x_h, int64_t n) { return hdk_copy_h2d(x_d, x_h, sizeof(double) * (size_t)n); }
 int hdk_vec_d2h(double *x_h, const double *x_d, int64_t n) { return hdk_copy_d2h(x_h, x_d, sizeof(double) * (size_t)n); }
 int hdk_vec_fill(double *x_d, double v, int64_t n) { HDK_TRY(require_init()); return vec_fill(x_d, v, n); }

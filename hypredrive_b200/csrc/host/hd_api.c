@@ -143,8 +143,8 @@ static void free_system(HYPREDRV_t h)
    if (h->b_d) { hdk_vec_free(h->b_d); h->b_d = NULL; }
    if (h->x0_d) { hdk_vec_free(h->x0_d); h->x0_d = NULL; }
    if (h->x_d) { hdk_vec_free(h->x_d); h->x_d = NULL; }
-   free(h->x_host); h->x_host = NULL;
-   free(h->b_host); h->b_host = NULL;
+   hdk_host_free(h->x_host); h->x_host = NULL;
+   hdk_host_free(h->b_host); h->b_host = NULL;
 }
 
 uint32_t HYPREDRV_Destroy(HYPREDRV_t *hp)
@@ -609,8 +609,8 @@ uint32_t HYPREDRV_LinearSystemGetSolutionValues(HYPREDRV_t h, HYPRE_Complex **so
    CHECK_OBJ(h);
    if (!sol_data) return fail(HYPREDRV_ERROR_INVALID_VAL, "%s", "sol_data cannot be NULL");
    if (!h->x_d) return fail(HYPREDRV_ERROR_INVALID_VAL, "%s", "no solution vector is available");
-   if (!h->x_host) h->x_host = malloc(sizeof(double) * (size_t)(h->n > 0 ? h->n : 1));
-   int rc = hdk_vec_d2h(h->x_host, h->x_d, h->n);
+   int rc = h->x_host ? HDK_OK : hdk_host_alloc(sizeof(double) * (size_t)(h->n > 0 ? h->n : 1), (void **)&h->x_host);
+   if (!rc) rc = hdk_vec_d2h(h->x_host, h->x_d, h->n);
    if (rc) return hdk_fail(rc);
    *sol_data = h->x_host;
    return hd_err_get();
@@ -621,8 +621,8 @@ uint32_t HYPREDRV_LinearSystemGetRHSValues(HYPREDRV_t h, HYPRE_Complex **rhs_dat
    CHECK_OBJ(h);
    if (!rhs_data) return fail(HYPREDRV_ERROR_INVALID_VAL, "%s", "rhs_data cannot be NULL");
    if (!h->b_d) return fail(HYPREDRV_ERROR_INVALID_VAL, "%s", "no right-hand side is available");
-   if (!h->b_host) h->b_host = malloc(sizeof(double) * (size_t)(h->n > 0 ? h->n : 1));
-   int rc = hdk_vec_d2h(h->b_host, h->b_d, h->n);
+   int rc = h->b_host ? HDK_OK : hdk_host_alloc(sizeof(double) * (size_t)(h->n > 0 ? h->n : 1), (void **)&h->b_host);
+   if (!rc) rc = hdk_vec_d2h(h->b_host, h->b_d, h->n);
    if (rc) return hdk_fail(rc);
    *rhs_data = h->b_host;
    return hd_err_get();

@@ -53,6 +53,9 @@ int hdk_comm_sum_i64(int64_t local, int64_t *global);
 /* ---- device vectors (reference: HYPRE_IJVector / hypre_ParVector, src/internal/linsys.c:1412-1491) */
 int hdk_vec_alloc(int64_t n, double **x_d);
 int hdk_vec_free(double *x_d);
+/* page-locked host buffers for the library-owned host views of device vectors (full PCIe rate) */
+int hdk_host_alloc(size_t bytes, void **p_h);
+int hdk_host_free(void *p_h);
 int hdk_vec_h2d(double *x_d, const double *x_h, int64_t n);
 int hdk_vec_d2h(double *x_h, const double *x_d, int64_t n);
 int hdk_vec_fill(double *x_d, double value, int64_t n);
