@@ -41,6 +41,43 @@ static void stage_mark(const char *name, int level)
 
 static const int64_t SCRATCH_BUDGET = (int64_t)1 << 30; // hash slots per chunk (4-8 GB)
 
+// ---- work sharing of the replicated multi-rank setup --------------------------------------
+// While the global hierarchy is built on every rank (setup_distributed), the row-parallel
+// stages (interpolation, Galerkin product) compute only this rank's share of the rows of the
+// GLOBAL matrices and the ranks exchange their row segments (grouped NCCL broadcasts), so the
+// result on every rank is the same bit-identical global level at 1/nranks of the work.
+static bool g_share = false;
+static int  g_share_min_rows = 65536; // smaller levels: the exchange latency exceeds the saving
+static bool share_on(int n) { return g_share && g.nranks > 1 && n >= g_share_min_rows; }
+static void share_range(int n, int &lo, int &hi)
+{
+   lo = 0; hi = n;
+   if (!share_on(n)) return;
+   lo = (int)((int64_t)n * g.rank / g.nranks);
+   hi = (int)((int64_t)n * (g.rank + 1) / g.nranks);
+}
+// exchange a per-row array (elem bytes per row) computed for the shares of [0,n)
+static int share_rows(void *base, size_t elem, int n)
+{
+   if (!share_on(n)) return HDK_OK;
+   std::vector<int64_t> offs((size_t)g.nranks + 1);
+   for (int r = 0; r <= g.nranks; r++) offs[(size_t)r] = (int64_t)((int64_t)n * r / g.nranks) * (int64_t)elem;
+   return allgatherv_bytes(base, offs.data());
+}
+// exchange per-entry arrays of a CSR whose rows were computed by shares; rowptr is complete
+static int share_entries(const int *rowptr_d, int n, void *a, size_t ea, void *b, size_t eb)
+{
+   if (!share_on(n)) return HDK_OK;
+   std::vector<int>     bnd((size_t)g.nranks + 1);
+   std::vector<int64_t> offs((size_t)g.nranks + 1);
+   for (int r = 0; r <= g.nranks; r++)
+      HDK_CUDA(cudaMemcpyAsync(&bnd[(size_t)r], rowptr_d + (int64_t)n * r / g.nranks, sizeof(int), cudaMemcpyDeviceToHost, g.stream));
+   HDK_CUDA(cudaStreamSynchronize(g.stream));
+   if (a) { for (int r = 0; r <= g.nranks; r++) offs[(size_t)r] = (int64_t)bnd[(size_t)r] * (int64_t)ea; HDK_TRY(allgatherv_bytes(a, offs.data())); }
+   if (b) { for (int r = 0; r <= g.nranks; r++) offs[(size_t)r] = (int64_t)bnd[(size_t)r] * (int64_t)eb; HDK_TRY(allgatherv_bytes(b, offs.data())); }
+   return HDK_OK;
+}
+
 // =====================================================================================
 // small utilities
 // =====================================================================================
@@ -589,7 +626,8 @@ template <bool FILL>
 __global__ void __launch_bounds__(32 * IW_WARPS) k_interp_warp(const int *arp, const int *acol, const double *aval,
                                                                const int *srp, const int *scol, const int *cf,
                                                                const int *f2c, int n, int max_elmts, int *cnt, int *rowlen,
-                                                               int *slow, const int *prp, int *pcol, double *pval, int force_slow)
+                                                               int *slow, const int *prp, int *pcol, double *pval, int force_slow,
+                                                               int row_lo)
 {
    __shared__ int    s_keys[IW_WARPS][IW_CAP];
    __shared__ int    s_idx[IW_WARPS][IW_CAP];
@@ -597,7 +635,7 @@ __global__ void __launch_bounds__(32 * IW_WARPS) k_interp_warp(const int *arp, c
    __shared__ double s_lv[IW_WARPS][IW_LIST + 8];
    const int      lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
    const unsigned FULL = 0xffffffffu, LT = (1u << lane) - 1u;
-   const int      i = blockIdx.x * IW_WARPS + wid;
+   const int      i = row_lo + blockIdx.x * IW_WARPS + wid; // rows [row_lo, n)
    if (i >= n) return;
    const int ci = cf[i];
    if (ci > 0)
@@ -767,9 +805,19 @@ static int build_interp(const DevCSR &A, const DevCSR &S, int *cf, const int *f2
    HDK_TRY(dalloc(&slow, (size_t)n + 1));
    // short rows (fine stencil levels): one thread per row beats one warp per row
    const int force_slow = ((double)A.nnz / (n > 0 ? n : 1)) <= 10.0 ? 1 : 0;
+   // this rank's share of the rows (all of them unless the multi-rank setup shares the work);
+   // rows outside it keep slow = cnt = rowlen = 0, which every later kernel skips
+   int lo, hi;
+   share_range(n, lo, hi);
+   if (share_on(n))
+   {
+      HDK_CUDA(cudaMemsetAsync(slow, 0, sizeof(int) * ((size_t)n + 1), g.stream));
+      HDK_CUDA(cudaMemsetAsync(cnt, 0, sizeof(int) * ((size_t)n + 1), g.stream));
+      HDK_CUDA(cudaMemsetAsync(rowlen, 0, sizeof(int) * ((size_t)n + 1), g.stream));
+   }
    // pass 1a: |C-hat_i| by the warp kernel (shared-memory hash); rows it cannot hold are flagged
-   k_interp_warp<false><<<cdiv(n, IW_WARPS), 32 * IW_WARPS, 0, g.stream>>>(A.rowptr, A.col, A.val, S.rowptr, S.col, cf, f2c, n,
-                                                                          max_elmts, cnt, rowlen, slow, nullptr, nullptr, nullptr, force_slow);
+   k_interp_warp<false><<<cdiv(hi - lo, IW_WARPS), 32 * IW_WARPS, 0, g.stream>>>(A.rowptr, A.col, A.val, S.rowptr, S.col, cf, f2c, hi,
+                                                                                max_elmts, cnt, rowlen, slow, nullptr, nullptr, nullptr, force_slow, lo);
    HDK_LAUNCH_CHECK();
    // pass 1b: flagged rows, one thread per row, hash sets in global scratch (chunked)
    k_interp_cap<<<cdiv(n + 1, 256), 256, 0, g.stream>>>(S.rowptr, S.col, cf, n, cap, slow);
@@ -793,6 +841,7 @@ static int build_interp(const DevCSR &A, const DevCSR &S, int *cf, const int *f2
    }
    HDK_CUDA(cudaMemsetAsync(rowlen + n, 0, sizeof(int), g.stream));
    HDK_CUDA(cudaMemsetAsync(cnt + n, 0, sizeof(int), g.stream));
+   HDK_TRY(share_rows(rowlen, sizeof(int), n)); // row lengths of the other ranks' shares
    HDK_TRY(exclusive_scan_int(rowlen, prp, n + 1));
    int nnzP = 0;
    HDK_CUDA(cudaMemcpyAsync(&nnzP, prp + n, sizeof(int), cudaMemcpyDeviceToHost, g.stream));
@@ -806,8 +855,8 @@ static int build_interp(const DevCSR &A, const DevCSR &S, int *cf, const int *f2
    // pass 2: weights.  hash maps sized from the exact counts, candidate lists in scratch
    int64_t *loff;
    HDK_TRY(dalloc(&loff, (size_t)n + 1));
-   k_interp_warp<true><<<cdiv(n, IW_WARPS), 32 * IW_WARPS, 0, g.stream>>>(A.rowptr, A.col, A.val, S.rowptr, S.col, cf, f2c, n,
-                                                                         max_elmts, cnt, rowlen, slow, prp, P.col, P.val, force_slow);
+   k_interp_warp<true><<<cdiv(hi - lo, IW_WARPS), 32 * IW_WARPS, 0, g.stream>>>(A.rowptr, A.col, A.val, S.rowptr, S.col, cf, f2c, hi,
+                                                                               max_elmts, cnt, rowlen, slow, prp, P.col, P.val, force_slow, lo);
    HDK_LAUNCH_CHECK();
    k_interp_cap2<<<cdiv(n + 1, 256), 256, 0, g.stream>>>(S.rowptr, cf, cnt, n, cap, slow);
    HDK_LAUNCH_CHECK();
@@ -843,6 +892,7 @@ static int build_interp(const DevCSR &A, const DevCSR &S, int *cf, const int *f2
       }
       dfree(htab); dfree(lcol); dfree(lval);
    }
+   HDK_TRY(share_entries(prp, n, P.col, sizeof(int), P.val, sizeof(double)));
    k_cf_reset_sf<<<cdiv(n, 256), 256, 0, g.stream>>>(cf, n);
    HDK_LAUNCH_CHECK();
    dfree(cap); dfree(cnt); dfree(rowlen); dfree(off); dfree(loff); dfree(slow);
@@ -929,12 +979,13 @@ template <bool FILL, int CAP>
 __global__ void __launch_bounds__(32 * RW_WARPS) k_rap_warp(const int *rrp, const int *rcol, const double *rval,
                                                             const int *arp, const int *acol, const double *aval,
                                                             const int *prp, const int *pcol, const double *pval,
-                                                            int nc, int *cnt, const int *crp, int *ccol, double *cval)
+                                                            int nc, int *cnt, const int *crp, int *ccol, double *cval,
+                                                            int row_lo)
 {
    extern __shared__ __align__(16) unsigned char rw_smem[];
    const int      lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
    const unsigned FULL = 0xffffffffu;
-   const int      ic = blockIdx.x * RW_WARPS + wid;
+   const int      ic = row_lo + blockIdx.x * RW_WARPS + wid; // rows [row_lo, nc)
    if (ic >= nc) return;
    if (FILL && cnt[ic] > RW_LIMIT) return;
    int    *keys = reinterpret_cast<int *>(rw_smem) + (size_t)wid * CAP;
@@ -1073,11 +1124,11 @@ __global__ void k_rap_count(const int *rrp, const int *rcol, const int *arp, con
    }
    cnt[ic] = c;
 }
-__global__ void k_rap_cap2(const int *cnt, int nc, int *cap2)
+__global__ void k_rap_cap2(const int *cnt, int nc, int *cap2, int lo, int hi)
 {
    int ic = blockIdx.x * blockDim.x + threadIdx.x;
    if (ic > nc) return;
-   cap2[ic] = (ic < nc && cnt[ic] > RW_LIMIT) ? pow2ceil(2 * cnt[ic]) : 0; // rows too long for the warp kernel
+   cap2[ic] = (ic >= lo && ic < hi && cnt[ic] > RW_LIMIT) ? pow2ceil(2 * cnt[ic]) : 0; // rows too long for the warp kernel
 }
 __global__ void k_rap_fill(const int *rrp, const int *rcol, const double *rval, const int *arp, const int *acol,
                            const double *aval, const int *prp, const int *pcol, const double *pval, int row0,
@@ -1124,9 +1175,13 @@ static int build_rap(const DevCSR &R, const DevCSR &A, const DevCSR &P, DevCSR &
    HDK_TRY(dalloc(&off, (size_t)nc + 1));
    k_rap_q<<<cdiv(n, 256), 256, 0, g.stream>>>(A.rowptr, A.col, P.rowptr, n, q);
    HDK_LAUNCH_CHECK();
+   // this rank's share of the coarse rows (all of them unless the multi-rank setup shares the work)
+   int lo, hi;
+   share_range(nc, lo, hi);
+   if (share_on(nc)) HDK_CUDA(cudaMemsetAsync(cnt, 0, sizeof(int) * ((size_t)nc + 1), g.stream));
    // pass 1a: exact row lengths by the warp kernel (rows longer than RW_LIMIT are flagged -1)
-   k_rap_warp<false, RW_CAP><<<cdiv(nc, RW_WARPS), 32 * RW_WARPS, (size_t)RW_WARPS * RW_CAP * sizeof(int), g.stream>>>(
-      R.rowptr, R.col, R.val, A.rowptr, A.col, A.val, P.rowptr, P.col, P.val, nc, cnt, nullptr, nullptr, nullptr);
+   k_rap_warp<false, RW_CAP><<<cdiv(hi - lo, RW_WARPS), 32 * RW_WARPS, (size_t)RW_WARPS * RW_CAP * sizeof(int), g.stream>>>(
+      R.rowptr, R.col, R.val, A.rowptr, A.col, A.val, P.rowptr, P.col, P.val, hi, cnt, nullptr, nullptr, nullptr, lo);
    HDK_LAUNCH_CHECK();
    stage_mark("  rap.warp1", -1);
    // pass 1b: flagged rows through the one-thread-per-row kernel with hash sets in global scratch
@@ -1151,6 +1206,7 @@ static int build_rap(const DevCSR &R, const DevCSR &A, const DevCSR &P, DevCSR &
    }
    stage_mark("  rap.thr1", -1);
    HDK_CUDA(cudaMemsetAsync(cnt + nc, 0, sizeof(int), g.stream));
+   HDK_TRY(share_rows(cnt, sizeof(int), nc)); // row lengths of the other ranks' shares
    HDK_TRY(exclusive_scan_int(cnt, crp, nc + 1));
    int nnzC = 0;
    HDK_CUDA(cudaMemcpyAsync(&nnzC, crp + nc, sizeof(int), cudaMemcpyDeviceToHost, g.stream));
@@ -1173,15 +1229,15 @@ static int build_rap(const DevCSR &R, const DevCSR &A, const DevCSR &P, DevCSR &
       size_t      smem = (size_t)RW_WARPS * RW_CAP * (2 * sizeof(int) + sizeof(double));
       if (!attr) { HDK_CUDA(cudaFuncSetAttribute(k_rap_warp<true, RW_CAP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = true; }
       if (hmax <= 80)
-         k_rap_warp<true, 128><<<cdiv(nc, RW_WARPS), 32 * RW_WARPS, (size_t)RW_WARPS * 128 * 16, g.stream>>>(
-            R.rowptr, R.col, R.val, A.rowptr, A.col, A.val, P.rowptr, P.col, P.val, nc, cnt, crp, C.col, C.val);
+         k_rap_warp<true, 128><<<cdiv(hi - lo, RW_WARPS), 32 * RW_WARPS, (size_t)RW_WARPS * 128 * 16, g.stream>>>(
+            R.rowptr, R.col, R.val, A.rowptr, A.col, A.val, P.rowptr, P.col, P.val, hi, cnt, crp, C.col, C.val, lo);
       else
-         k_rap_warp<true, RW_CAP><<<cdiv(nc, RW_WARPS), 32 * RW_WARPS, smem, g.stream>>>(
-            R.rowptr, R.col, R.val, A.rowptr, A.col, A.val, P.rowptr, P.col, P.val, nc, cnt, crp, C.col, C.val);
+         k_rap_warp<true, RW_CAP><<<cdiv(hi - lo, RW_WARPS), 32 * RW_WARPS, smem, g.stream>>>(
+            R.rowptr, R.col, R.val, A.rowptr, A.col, A.val, P.rowptr, P.col, P.val, hi, cnt, crp, C.col, C.val, lo);
       HDK_LAUNCH_CHECK();
       stage_mark("  rap.warp2", -1);
    }
-   k_rap_cap2<<<cdiv(nc + 1, 256), 256, 0, g.stream>>>(cnt, nc, cap);
+   k_rap_cap2<<<cdiv(nc + 1, 256), 256, 0, g.stream>>>(cnt, nc, cap, lo, hi);
    HDK_LAUNCH_CHECK();
    HDK_TRY(exclusive_scan_i64(cap, off, nc + 1));
    HDK_TRY(plan_chunks(off, nc, bounds, maxsz));
@@ -1199,6 +1255,7 @@ static int build_rap(const DevCSR &R, const DevCSR &A, const DevCSR &P, DevCSR &
       }
       dfree(htab);
    }
+   HDK_TRY(share_entries(crp, nc, C.col, sizeof(int), C.val, sizeof(double)));
    dfree(q); dfree(cap); dfree(cnt); dfree(off);
    return HDK_OK;
 }
@@ -1423,7 +1480,7 @@ int hdk_amg_destroy(hdk_amg *M)
 
 // per-level solve data: smoother diagonals, work vectors, (two-stage GS) lower triangles, and the
 // algorithmic byte count of one V-cycle
-static int finalize_levels(hdk_amg_s *M, const hdk_amg_params *prm)
+static int finalize_levels(hdk_amg_s *M, const hdk_amg_params *prm, int64_t live_max_rows = -1)
 {
    int    rc = HDK_OK;
    double bytes = 0.0;
@@ -1431,6 +1488,7 @@ static int finalize_levels(hdk_amg_s *M, const hdk_amg_params *prm)
    {
       AmgLevel &L = M->lev[(size_t)l];
       int       n = L.n;
+      if (live_max_rows >= 0 && n > live_max_rows) continue; // global level that is only sliced, never cycled
       if ((rc = build_l1(*L.A, relax_l1_option(prm->relax_down), &L.l1_down))) break;
       if (relax_l1_option(prm->relax_up) == relax_l1_option(prm->relax_down)) L.l1_up = L.l1_down;
       else if ((rc = build_l1(*L.A, relax_l1_option(prm->relax_up), &L.l1_up))) break;
@@ -1460,7 +1518,10 @@ static int finalize_levels(hdk_amg_s *M, const hdk_amg_params *prm)
    return rc;
 }
 
-static int setup_serial(const hdk_csr_s *A0, const hdk_amg_params *prm, hdk_amg_s **out, bool keep_f2c)
+// live_max_rows >= 0: the hierarchy is the global one of a multi-rank setup; levels with more
+// rows are only sliced into slabs afterwards, so they get no SpMV analysis and no solve data
+static int setup_serial(const hdk_csr_s *A0, const hdk_amg_params *prm, hdk_amg_s **out, bool keep_f2c,
+                        int64_t live_max_rows = -1)
 {
    hdk_amg_s *M = new hdk_amg_s();
    M->prm       = *prm;
@@ -1511,10 +1572,16 @@ static int setup_serial(const hdk_csr_s *A0, const hdk_amg_params *prm, hdk_amg_
       stage_mark("transpose", level);
       if ((rc = build_rap(R, A.diag, P, C))) break;
       stage_mark("rap", level);
-      if ((rc = csr_analyze(P))) break;
-      if ((rc = csr_analyze(R))) break;
       C.coarse_op = true;
-      if ((rc = csr_analyze(C))) break;
+      if (live_max_rows < 0 || n <= live_max_rows)
+      {
+         if ((rc = csr_analyze(P))) break;
+         if ((rc = csr_analyze(R))) break;
+      }
+      if (live_max_rows < 0 || nc <= live_max_rows)
+      {
+         if ((rc = csr_analyze(C))) break;
+      }
       stage_mark("analyze", level);
       nnz_sum += C.nnz;
       L.P = wrap_local(P, n);
@@ -1530,7 +1597,7 @@ static int setup_serial(const hdk_csr_s *A0, const hdk_amg_params *prm, hdk_amg_
    {
       M->nlev = level + 1;
       M->op_complexity = nnz_sum / (nnz0 > 0 ? nnz0 : 1.0);
-      rc = finalize_levels(M, prm);
+      rc = finalize_levels(M, prm, live_max_rows);
    }
    if (rc == HDK_OK)
    {
@@ -1601,6 +1668,7 @@ static int slice_rows(const DevCSR &D, int r0, int r1, int64_t cs, int64_t ce, i
 static int setup_distributed(const hdk_csr_s *A0, const hdk_amg_params *prm, hdk_amg_s **out)
 {
    const int R = g.nranks, me = g.rank;
+   stage_mark(nullptr, -2);
    if (!A0->orig_indptr) return set_error(HDK_ERR_INVALID, "distributed setup needs the matrix to be built at N > 1");
    // 1. sizes and offsets of every rank's slab
    std::vector<int64_t> rows_all, nnz_all;
@@ -1632,18 +1700,23 @@ static int setup_distributed(const hdk_csr_s *A0, const hdk_amg_params *prm, hdk
       HDK_TRY(bcast_bytes(gcj + koff[(size_t)r], sizeof(int64_t) * (size_t)nnz_all[(size_t)r], r));
       HDK_TRY(bcast_bytes(gva + koff[(size_t)r], sizeof(double) * (size_t)nnz_all[(size_t)r], r));
    }
+   static int64_t rep_rows = -1;
+   if (rep_rows < 0) { const char *e = getenv("HDK_REPLICATE_ROWS"); rep_rows = e ? atoll(e) : 262144; }
    hdk_csr_s *G = nullptr;
-   int rc = parcsr_build(0, N - 1, 0, N - 1, N, N, true, false, false, gip, gcj, gva, &G);
+   int rc = parcsr_build(0, N - 1, 0, N - 1, N, N, true, false, false, gip, gcj, gva, &G, N <= rep_rows);
    dfree(gip); dfree(gcj); dfree(gva);
    if (rc) return rc;
    // 3. the global hierarchy (serial algorithm, identical on every rank)
+   stage_mark("gather A", -2);
    hdk_amg_s *Mg = nullptr;
-   rc = setup_serial(G, prm, &Mg, true);
+   g_share = !(getenv("HDK_SETUP_SHARE") && atoi(getenv("HDK_SETUP_SHARE")) == 0);
+   if (getenv("HDK_SHARE_MIN_ROWS")) g_share_min_rows = atoi(getenv("HDK_SHARE_MIN_ROWS"));
+   rc = setup_serial(G, prm, &Mg, true, rep_rows);
+   g_share = false;
    if (rc) { destroy_local(G); return rc; }
    Mg->lev[0].owns_A = true; // G belongs to the global hierarchy
+   stage_mark("global setup", -2);
    // 4. fine ranges of every rank on every level; first replicated level
-   static int64_t rep_rows = -1;
-   if (rep_rows < 0) { const char *e = getenv("HDK_REPLICATE_ROWS"); rep_rows = e ? atoll(e) : 262144; }
    const int nl = Mg->nlev;
    std::vector<std::vector<int64_t>> starts((size_t)nl); // starts[l][r], r = 0..R
    starts[0] = roff;
@@ -1698,6 +1771,7 @@ static int setup_distributed(const hdk_csr_s *A0, const hdk_amg_params *prm, hdk
       }
       if ((rc = slice_rows(Lg.R->diag, (int)cs, (int)ce, fs, fe - 1, nc, nf, false, true, &L.R))) break;
    }
+   stage_mark("slice", -2);
    if (rc == HDK_OK)
    {
       M->nlev = tail_level;
@@ -1735,6 +1809,7 @@ static int setup_distributed(const hdk_csr_s *A0, const hdk_amg_params *prm, hdk
       }
       HDK_CUDA(cudaStreamSynchronize(g.stream));
    }
+   stage_mark("finalize", -2);
    if (rc != HDK_OK) { hdk_amg_destroy(M); return rc; }
    *out = M;
    return HDK_OK;

@@ -76,6 +76,22 @@ int bcast_bytes(void *buf_d, size_t bytes, int root)
    return HDK_OK;
 }
 
+// in-place all-gather of variable-size segments: rank r owns bytes [offs[r], offs[r+1]) of base
+int allgatherv_bytes(void *base_d, const int64_t *offs)
+{
+   if (g.nranks <= 1) return HDK_OK;
+   char *b = static_cast<char *>(base_d);
+   HDK_NCCL(nccl.GroupStart());
+   for (int r = 0; r < g.nranks; r++)
+   {
+      size_t bytes = (size_t)(offs[r + 1] - offs[r]);
+      if (bytes == 0) continue;
+      HDK_NCCL(nccl.Broadcast(b + offs[r], b + offs[r], bytes, 0 /* ncclInt8 */, r, (ncclComm_p)g.nccl, g.stream));
+   }
+   HDK_NCCL(nccl.GroupEnd());
+   return HDK_OK;
+}
+
 int allreduce_max_dev(double *buf_d, int count)
 {
    if (g.nranks <= 1) return HDK_OK;

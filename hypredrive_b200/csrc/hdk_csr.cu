@@ -110,7 +110,7 @@ __global__ void k_orig_diag_first(const int64_t *indptr, int64_t *cols, double *
 // matrix is one slab of a matrix spread over all ranks (collective: every rank must call).
 int parcsr_build(int64_t rs, int64_t re, int64_t cs, int64_t ce, int64_t grows, int64_t gcols, bool square,
                  bool distributed, bool keep_orig, const int64_t *indptr, const int64_t *cols, const double *vals,
-                 hdk_csr_s **out)
+                 hdk_csr_s **out, bool analyze)
 {
    if (re < rs) return set_error(HDK_ERR_INVALID, "empty local row range [%lld,%lld]", (long long)rs, (long long)re);
    int64_t n64 = re - rs + 1;
@@ -175,7 +175,7 @@ int parcsr_build(int64_t rs, int64_t re, int64_t cs, int64_t ce, int64_t grows, 
    else if (tot[1] > 0)
       return set_error(HDK_ERR_INVALID, "matrix has %d off-rank columns but is not distributed", n_halo);
    dfree(gcol_o);
-   HDK_TRY(csr_analyze(A->diag));
+   if (analyze) HDK_TRY(csr_analyze(A->diag));
    if (A->offd.nnz > 0)
    {
       int *cnt = reinterpret_cast<int *>(g.dscal + S_TMP2);

@@ -19,11 +19,19 @@ def _run(world, args, env_extra=None):
     return subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=600)
 
 
-@pytest.mark.parametrize("kind,dims,rep", [("lap7", ("12", "11", "6"), "40"), ("lap7", ("16", "16", "10"), "262144"),
-                                           ("lap27", ("8", "8", "6"), "30"), ("convdif", ("16", "8", "6"), "40")])
-def test_two_rank_solve_matches_oracle(gpu, kind, dims, rep):
+@pytest.mark.parametrize("kind,dims,rep,share", [
+    ("lap7", ("12", "11", "6"), "40", "0"), ("lap7", ("16", "16", "10"), "262144", "0"),
+    ("lap27", ("8", "8", "6"), "30", "0"), ("convdif", ("16", "8", "6"), "40", "0"),
+    # replicated setup only (no work sharing between the ranks)
+    ("lap7", ("12", "11", "6"), "40", "off")])
+def test_two_rank_solve_matches_oracle(gpu, kind, dims, rep, share):
     if gpu.device_count() < 2:
         pytest.skip("needs two GPUs")
-    r = _run(2, [kind, *dims], {"HDK_REPLICATE_ROWS": rep})
+    env = {"HDK_REPLICATE_ROWS": rep}
+    if share == "off":
+        env["HDK_SETUP_SHARE"] = "0"
+    else:
+        env["HDK_SHARE_MIN_ROWS"] = share  # share the interpolation / RAP rows even on these tiny levels
+    r = _run(2, [kind, *dims], env)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert "ok=True" in r.stdout
