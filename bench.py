@@ -335,7 +335,10 @@ def ours(args):
             "e2e": {"value": e2e_value, "unit": "DOF*iters/s", "h2d_bytes_per_step": 8 * n_loc * world,
                     "d2h_bytes_per_step": 8 * n_loc * world, "ms_per_step": e2e_wall / args.steps * 1e3,
                     "iterations": e2e_it},
-            "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "kernels": extra_kernels,
+            "gpu_launches": int(launches),
+            "halo_exchange": {0: "none (1 rank)", 1: "nccl send/recv",
+                              2: "peer-memory stores (CUDA IPC)"}.get(int(hdk.lib().hdk_comm_halo_mode()), "?"),
+            "clocks": clocks, "roofline": roof, "kernels": extra_kernels,
             "cpu_baseline": cpu,
             "published_reference": {"what": "hypre CUDA driven by hypredrive, 8xB200, lap-7 256^3 (docs figure, +-10%)",
                                     "setup_s": 0.10, "solve_s": 0.076},

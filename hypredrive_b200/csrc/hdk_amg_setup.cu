@@ -1433,7 +1433,7 @@ static void destroy_local(hdk_csr_s *A)
 {
    if (!A) return;
    csr_free(A->diag); csr_free(A->offd);
-   dfree(A->halo.col_map); dfree(A->halo.send_idx); dfree(A->halo.send_buf); dfree(A->halo.x_halo);
+   halo_plan_free(A->halo);
    dfree(A->offd_rows);
    delete A;
 }

@@ -6,6 +6,7 @@
 #include "hdk_internal.cuh"
 #include <dlfcn.h>
 #include <algorithm>
+#include <map>
 
 namespace hdk {
 
@@ -61,6 +62,120 @@ static int nccl_load()
          return set_error(HDK_ERR_COMM, "%s:%d %s -> %s", __FILE__, __LINE__, #call,           \
                           nccl.GetErrorString ? nccl.GetErrorString(r__) : "nccl error");      \
    } while (0)
+
+// ------------------------------------------------------------------------------------------
+// Peer-memory arena: one cudaMalloc'ed block per rank, opened by every other rank through CUDA
+// IPC at communicator creation.  Halo plans carve their receive buffers and flag slots out of
+// it, so a neighbour can store into them directly over NVLink.
+// ------------------------------------------------------------------------------------------
+struct IpcState
+{
+   bool                on = false;
+   char               *base = nullptr;
+   size_t              size = 0;
+   std::vector<char *> peer;                 // peer[r] = rank r's arena in my address space
+   std::map<size_t, size_t>               free_; // offset -> bytes
+   std::vector<std::pair<size_t, size_t>> pending; // released, reusable after the next collective
+};
+static IpcState ipc;
+
+static void arena_release_now(size_t off, size_t bytes)
+{
+   auto it = ipc.free_.emplace(off, bytes).first;
+   auto nx = std::next(it);
+   if (nx != ipc.free_.end() && it->first + it->second == nx->first) { it->second += nx->second; ipc.free_.erase(nx); }
+   if (it != ipc.free_.begin())
+   {
+      auto pv = std::prev(it);
+      if (pv->first + pv->second == it->first) { pv->second += it->second; ipc.free_.erase(it); }
+   }
+}
+static void arena_collect()
+{
+   for (auto &p : ipc.pending) arena_release_now(p.first, p.second);
+   ipc.pending.clear();
+}
+static int64_t arena_alloc(size_t bytes)
+{
+   bytes = (bytes + 255) & ~(size_t)255;
+   for (auto it = ipc.free_.begin(); it != ipc.free_.end(); ++it)
+      if (it->second >= bytes)
+      {
+         size_t off = it->first, rest = it->second - bytes;
+         ipc.free_.erase(it);
+         if (rest) ipc.free_.emplace(off + bytes, rest);
+         return (int64_t)off;
+      }
+   return -1;
+}
+
+static int ipc_setup()
+{
+   const char *e = getenv("HDK_HALO_IPC");
+   if (e && atoi(e) == 0) return HDK_OK;
+   size_t mb = 256;
+   if (getenv("HDK_IPC_ARENA_MB")) mb = (size_t)atoll(getenv("HDK_IPC_ARENA_MB"));
+   int ok = 1;
+   cudaIpcMemHandle_t mine;
+   memset(&mine, 0, sizeof(mine));
+   if (cudaMalloc((void **)&ipc.base, mb << 20) != cudaSuccess) { ok = 0; ipc.base = nullptr; cudaGetLastError(); }
+   if (ok && cudaMemset(ipc.base, 0, mb << 20) != cudaSuccess) ok = 0;
+   if (ok && cudaIpcGetMemHandle(&mine, ipc.base) != cudaSuccess) { ok = 0; cudaGetLastError(); }
+   // exchange the handles (and whether every rank got this far)
+   const size_t   hb = sizeof(cudaIpcMemHandle_t) + 8;
+   char          *d;
+   std::vector<char> host((size_t)g.nranks * hb, 0), my(hb, 0);
+   memcpy(my.data(), &mine, sizeof(mine));
+   my[sizeof(mine)] = (char)ok;
+   HDK_TRY(dalloc(&d, (size_t)(g.nranks + 1) * hb));
+   HDK_CUDA(cudaMemcpyAsync(d + (size_t)g.nranks * hb, my.data(), hb, cudaMemcpyHostToDevice, g.stream));
+   HDK_NCCL(nccl.AllGather(d + (size_t)g.nranks * hb, d, hb, 0 /* ncclInt8 */, (ncclComm_p)g.nccl, g.stream));
+   HDK_CUDA(cudaMemcpyAsync(host.data(), d, (size_t)g.nranks * hb, cudaMemcpyDeviceToHost, g.stream));
+   HDK_CUDA(cudaStreamSynchronize(g.stream));
+   dfree(d);
+   for (int r = 0; r < g.nranks; r++) if (!host[(size_t)r * hb + sizeof(mine)]) ok = 0;
+   ipc.peer.assign((size_t)g.nranks, nullptr);
+   if (ok)
+   {
+      for (int r = 0; r < g.nranks && ok; r++)
+      {
+         if (r == g.rank) { ipc.peer[(size_t)r] = ipc.base; continue; }
+         cudaIpcMemHandle_t h;
+         memcpy(&h, host.data() + (size_t)r * hb, sizeof(h));
+         void *p = nullptr;
+         if (cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { ok = 0; cudaGetLastError(); }
+         ipc.peer[(size_t)r] = static_cast<char *>(p);
+      }
+   }
+   // every rank must agree
+   std::vector<int64_t> oks;
+   HDK_TRY(allgather_i64_host(ok, oks));
+   for (int64_t v : oks) if (!v) ok = 0;
+   if (!ok)
+   {
+      for (int r = 0; r < g.nranks; r++)
+         if (r != g.rank && ipc.peer[(size_t)r]) cudaIpcCloseMemHandle(ipc.peer[(size_t)r]);
+      if (ipc.base) cudaFree(ipc.base);
+      ipc = IpcState();
+      cudaGetLastError();
+      return HDK_OK; // NCCL send/recv path stays in use
+   }
+   ipc.size = mb << 20;
+   ipc.free_.clear();
+   ipc.free_.emplace(0, ipc.size);
+   ipc.on = true;
+   return HDK_OK;
+}
+
+static void ipc_teardown()
+{
+   if (!ipc.base) return;
+   cudaDeviceSynchronize();
+   for (int r = 0; r < (int)ipc.peer.size(); r++)
+      if (r != g.rank && ipc.peer[(size_t)r]) cudaIpcCloseMemHandle(ipc.peer[(size_t)r]);
+   cudaFree(ipc.base);
+   ipc = IpcState();
+}
 
 int allreduce_dev(double *buf_d, int count)
 {
@@ -129,6 +244,123 @@ int allgather_i32_host(const int *mine, int cnt, std::vector<int> &all)
    return HDK_OK;
 }
 
+// ---- peer-memory halo plans -------------------------------------------------------------
+// Gather the boundary values and store them into the neighbours' halo buffers (NVLink peer
+// stores); the last block to finish publishes the sequence number in every neighbour's flag.
+// A buffer half is reused every second exchange: wait until the neighbour has read seq - 2.
+__global__ void k_pack_ipc(const double *x, const int *idx, int n, IpcSendArgs a)
+{
+   if (threadIdx.x == 0 && a.seq > 2)
+      for (int p = 0; p < a.npeer; p++) wait_seq_sys(a.ack + p, a.seq - 2);
+   __syncthreads();
+   int i = blockIdx.x * blockDim.x + threadIdx.x;
+   if (i < n)
+   {
+      int p = 0;
+      while (p + 1 < a.npeer && i >= a.off[p + 1]) p++;
+      a.dst[p][i - a.off[p]] = x[idx[i]];
+   }
+   __threadfence_system();
+   __syncthreads();
+   if (threadIdx.x == 0)
+   {
+      unsigned t = atomicInc(a.ticket, gridDim.x - 1);
+      if (t == gridDim.x - 1)
+      {
+         __threadfence_system();
+         for (int p = 0; p < a.npeer; p++) st_release_sys_u64(a.flag[p], a.seq);
+      }
+   }
+}
+
+// one region per plan in my arena: [8 data flags | 8 ack flags | x_halo half 0 | x_halo half 1]
+static size_t ipc_half_doubles(int n_halo) { return ((size_t)n_halo + 15) & ~(size_t)15; }
+
+static int ipc_plan_build(HaloPlan &H, const std::vector<int> &all /* all[r*R+q]: columns r wants from q */)
+{
+   IpcHalo &I = H.ipc;
+   I = IpcHalo();
+   if (!ipc.on) return HDK_OK;
+   arena_collect(); // the host-synchronised collectives earlier in the plan build make released regions safe
+   const int R = g.nranks, me = g.rank;
+   int ok = (H.send_rank.size() <= (size_t)IPC_MAXP && H.recv_rank.size() <= (size_t)IPC_MAXP) ? 1 : 0;
+   const size_t bytes = 128 + 2 * ipc_half_doubles(H.n_halo) * sizeof(double);
+   int64_t off = ok ? arena_alloc(bytes) : -1;
+   if (off >= 0) HDK_CUDA(cudaMemsetAsync(ipc.base + off, 0, 128, g.stream)); // flags start at sequence 0
+   std::vector<int64_t> offs;
+   HDK_TRY(allgather_i64_host(off, offs)); // also orders my memset before any neighbour's first store
+   bool all_ok = true;
+   for (int64_t v : offs) if (v < 0) all_ok = false;
+   if (!all_ok)
+   {
+      if (off >= 0) arena_release_now((size_t)off, (bytes + 255) & ~(size_t)255);
+      return HDK_OK; // this plan stays on NCCL send/recv (same decision on every rank)
+   }
+   I.region_off = off; I.region_bytes = (bytes + 255) & ~(size_t)255;
+   I.data_flag = reinterpret_cast<unsigned long long *>(ipc.base + off);
+   I.ack_flag  = I.data_flag + 8;
+   I.xh[0]     = reinterpret_cast<double *>(ipc.base + off + 128);
+   I.xh[1]     = I.xh[0] + ipc_half_doubles(H.n_halo);
+   // my position in every neighbour's lists, from the global want matrix
+   for (size_t i = 0; i < H.send_rank.size(); i++)
+   {
+      const int D = H.send_rank[i];
+      int       roff = 0, ridx = 0, nh = 0;
+      for (int q = 0; q < R; q++)
+      {
+         int c = all[(size_t)D * R + q];
+         if (q < me) { roff += c; if (c > 0) ridx++; }
+         nh += c;
+      }
+      char *rb = ipc.peer[(size_t)D] + offs[(size_t)D];
+      I.dst[0][i]   = reinterpret_cast<double *>(rb + 128) + roff;
+      I.dst[1][i]   = I.dst[0][i] + ipc_half_doubles(nh);
+      I.dst_flag[i] = reinterpret_cast<unsigned long long *>(rb) + ridx;
+   }
+   for (size_t i = 0; i < H.recv_rank.size(); i++)
+   {
+      const int S = H.recv_rank[i];
+      int       sidx = 0;
+      for (int r = 0; r < me; r++) if (all[(size_t)r * R + S] > 0) sidx++;
+      char *rb = ipc.peer[(size_t)S] + offs[(size_t)S];
+      I.src_ack[i] = reinterpret_cast<unsigned long long *>(rb) + 8 + sidx;
+   }
+   HDK_TRY(dalloc(&I.tickets, 2));
+   HDK_CUDA(cudaMemsetAsync(I.tickets, 0, 2 * sizeof(unsigned), g.stream));
+   I.seq = 0;
+   I.on  = true;
+   return HDK_OK;
+}
+
+void halo_plan_free(HaloPlan &H)
+{
+   dfree(H.col_map); dfree(H.send_idx); dfree(H.send_buf); dfree(H.x_halo);
+   H.col_map = nullptr; H.send_idx = nullptr; H.send_buf = nullptr; H.x_halo = nullptr;
+   if (H.ipc.on)
+   {
+      dfree(H.ipc.tickets);
+      if (ipc.on) ipc.pending.emplace_back((size_t)H.ipc.region_off, H.ipc.region_bytes);
+      H.ipc = IpcHalo();
+   }
+}
+
+// arguments of the consumer of the halo (k_offd_correct): where x_halo is and what to wait for
+IpcRecvArgs halo_recv_args(const hdk_csr_s &A, const double **xh)
+{
+   const HaloPlan &H = A.halo;
+   IpcRecvArgs     r;
+   memset(&r, 0, sizeof(r));
+   if (!H.ipc.on) { *xh = H.x_halo; return r; }
+   const IpcHalo &I = H.ipc;
+   *xh      = I.xh[I.seq & 1];
+   r.flag   = I.data_flag;
+   r.nflag  = (int)H.recv_rank.size();
+   r.seq    = I.seq;
+   r.ticket = I.tickets + 1;
+   for (size_t i = 0; i < H.recv_rank.size(); i++) r.ack[i] = I.src_ack[i];
+   return r;
+}
+
 __global__ void k_ids_to_local(const int64_t *ids, int n, int64_t row_start, int *idx)
 {
    int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -174,6 +406,7 @@ int build_halo_plan(hdk_csr_s &A, int64_t *uniq, int n_halo)
       if (c > 0) { H.send_rank.push_back(r); H.send_off.push_back(soff); H.send_cnt.push_back(c); soff += c; }
    }
    H.n_send = soff;
+   HDK_TRY(ipc_plan_build(H, all));
    int64_t *req;
    HDK_TRY(dalloc(&req, (size_t)soff + 1));
    HDK_TRY(dalloc(&H.send_idx, (size_t)soff + 1));
@@ -205,6 +438,29 @@ int halo_exchange_begin(const hdk_csr_s &A, const double *x)
 {
    const HaloPlan &H = A.halo;
    if (g.nranks <= 1) return HDK_OK;
+   if (H.ipc.on)
+   {
+      // peer-memory path: one kernel packs, stores over NVLink and signals; the consumer waits
+      IpcHalo &I = const_cast<IpcHalo &>(H.ipc);
+      I.seq++;
+      if (H.n_send > 0)
+      {
+         IpcSendArgs a;
+         memset(&a, 0, sizeof(a));
+         a.npeer = (int)H.send_rank.size();
+         for (int p = 0; p < a.npeer; p++)
+         {
+            a.dst[p]  = I.dst[I.seq & 1][p];
+            a.flag[p] = I.dst_flag[p];
+            a.off[p]  = H.send_off[(size_t)p];
+         }
+         a.off[a.npeer] = H.n_send;
+         a.ack = I.ack_flag; a.seq = I.seq; a.ticket = I.tickets;
+         k_pack_ipc<<<cdiv(H.n_send, 256), 256, 0, g.stream>>>(x, H.send_idx, H.n_send, a);
+         HDK_LAUNCH_CHECK();
+      }
+      return HDK_OK;
+   }
    if (H.n_send > 0)
    {
       k_pack<<<cdiv(H.n_send, 256), 256, 0, g.stream>>>(x, H.send_idx, H.n_send, H.send_buf);
@@ -224,7 +480,7 @@ int halo_exchange_begin(const hdk_csr_s &A, const double *x)
 
 int halo_exchange_end(const hdk_csr_s &A)
 {
-   if (g.nranks <= 1) return HDK_OK;
+   if (g.nranks <= 1 || A.halo.ipc.on) return HDK_OK;
    HDK_CUDA(cudaStreamWaitEvent(g.stream, g.ev_halo, 0));
    return HDK_OK;
 }
@@ -255,7 +511,7 @@ int hdk_comm_init(int rank, int nranks, const void *id128_h)
    ncclComm_p comm = nullptr;
    HDK_NCCL(nccl.CommInitRank(&comm, nranks, id, rank));
    g.nccl = comm; g.rank = rank; g.nranks = nranks;
-   return HDK_OK;
+   return ipc_setup();
 }
 
 int hdk_comm_max_i64(int64_t local, int64_t *global)
@@ -279,11 +535,13 @@ int hdk_comm_sum_i64(int64_t local, int64_t *global)
    return HDK_OK;
 }
 
+int hdk_comm_halo_mode(void) { return (g.nranks > 1) ? (ipc.on ? 2 : 1) : 0; }
 int hdk_comm_rank(void) { return g.rank; }
 int hdk_comm_size(void) { return g.nranks; }
 
 int hdk_comm_finalize(void)
 {
+   ipc_teardown();
    if (g.nccl && nccl.CommDestroy) nccl.CommDestroy((ncclComm_p)g.nccl);
    g.nccl = nullptr; g.rank = 0; g.nranks = 1;
    return HDK_OK;

@@ -222,7 +222,7 @@ static int parcsr_from_device(int64_t rs, int64_t re, int64_t grows, const int64
 // ---- y = op(A) x with halo exchange: diag kernel overlaps the exchange, offd kernel follows
 __global__ void k_offd_correct(const int *rows, const int *rowptr, const int *col, const double *val, int nrows,
                                const double *xh, double *y, const double *d, double w, int mode,
-                               double alpha);
+                               double alpha, IpcRecvArgs ipc);
 
 int parcsr_matvec(const hdk_csr_s &A, int mode, SpmvArgs a)
 {
@@ -238,9 +238,11 @@ int parcsr_matvec(const hdk_csr_s &A, int mode, SpmvArgs a)
    // offd contribution: y_i += sign * sum_o (linear correction of the diag-only epilogue)
    if (A.offd.nnz > 0)
    {
-      int grid = cdiv(A.n_offd_rows, 128);
+      int           grid = cdiv(A.n_offd_rows, 128);
+      const double *xh;
+      IpcRecvArgs   ra = halo_recv_args(A, &xh);
       k_offd_correct<<<grid, 128, 0, g.stream>>>(A.offd_rows, A.offd.rowptr, A.offd.col, A.offd.val, A.n_offd_rows,
-                                                 A.halo.x_halo, a.y, a.d, a.w, mode, a.alpha);
+                                                 xh, a.y, a.d, a.w, mode, a.alpha, ra);
       HDK_LAUNCH_CHECK();
    }
    if (a.fin != FIN_NONE && a.dotv)
@@ -252,22 +254,46 @@ int parcsr_matvec(const hdk_csr_s &A, int mode, SpmvArgs a)
 
 __global__ void k_offd_correct(const int *rows, const int *rowptr, const int *col, const double *val, int nrows,
                                const double *xh, double *y, const double *d, double w, int mode,
-                               double alpha)
+                               double alpha, IpcRecvArgs ipc)
 {
-   int i = blockIdx.x * blockDim.x + threadIdx.x;
-   if (i >= nrows) return;
-   int r = rows[i];
-   int s = rowptr[r], e = rowptr[r + 1];
-   double acc = 0.0;
-   for (int k = s; k < e; k++) acc += val[k] * xh[col[k]];
-   switch (mode)
+   // peer-memory exchange: the neighbours' pack kernels store into xh and then raise the
+   // sequence flags; wait for them here, so the transfer overlaps the diag-block kernel
+   if (ipc.seq)
    {
-      case SPMV_SET:
-      case SPMV_ADD: y[r] += acc; break;
-      case SPMV_AXPBY: y[r] += alpha * acc; break;
-      case SPMV_RESIDUAL: y[r] -= acc; break;
-      case SPMV_JACOBI:
-      case SPMV_JACOBI_R: { double dd = d[r]; if (dd != 0.0) y[r] -= (w * acc) / dd; break; }
+      if (threadIdx.x == 0)
+         for (int p = 0; p < ipc.nflag; p++) wait_seq_sys(ipc.flag + p, ipc.seq);
+      __syncthreads();
+   }
+   int i = blockIdx.x * blockDim.x + threadIdx.x;
+   if (i < nrows)
+   {
+      int r = rows[i];
+      int s = rowptr[r], e = rowptr[r + 1];
+      double acc = 0.0;
+      for (int k = s; k < e; k++) acc += val[k] * __ldcg(xh + col[k]); // L2: written by a peer
+      switch (mode)
+      {
+         case SPMV_SET:
+         case SPMV_ADD: y[r] += acc; break;
+         case SPMV_AXPBY: y[r] += alpha * acc; break;
+         case SPMV_RESIDUAL: y[r] -= acc; break;
+         case SPMV_JACOBI:
+         case SPMV_JACOBI_R: { double dd = d[r]; if (dd != 0.0) y[r] -= (w * acc) / dd; break; }
+      }
+   }
+   if (ipc.seq)
+   {
+      // tell the senders this half of the buffer has been read (they reuse it at seq + 2)
+      __syncthreads();
+      if (threadIdx.x == 0)
+      {
+         unsigned t = atomicInc(ipc.ticket, gridDim.x - 1);
+         if (t == gridDim.x - 1)
+         {
+            __threadfence_system();
+            for (int p = 0; p < ipc.nflag; p++) st_release_sys_u64(ipc.ack[p], ipc.seq);
+         }
+      }
    }
 }
 
@@ -466,7 +492,7 @@ int hdk_csr_destroy(hdk_csr *A)
    if (g.inited)
    {
       csr_free(A->diag); csr_free(A->offd);
-      dfree(A->halo.col_map); dfree(A->halo.send_idx); dfree(A->halo.send_buf); dfree(A->halo.x_halo);
+      halo_plan_free(A->halo);
       dfree(A->orig_indptr); dfree(A->orig_cols); dfree(A->orig_vals); dfree(A->offd_rows);
    }
    delete A;

@@ -172,8 +172,68 @@ int allreduce_dev(double *buf_d, int count);                                    
 // ---------------------------------------------------------------------------------------
 // ParCSR of one rank: diag + offd blocks, halo bookkeeping
 // ---------------------------------------------------------------------------------------
+// Peer-memory halo exchange (CUDA IPC over NVLink): the pack kernel stores the boundary values
+// straight into the neighbours' halo buffers and raises a sequence flag there; the kernel that
+// consumes the halo waits for the flags itself.  See hdk_comm.cu.
+constexpr int IPC_MAXP = 8; // neighbours per direction handled by the peer-memory path
+struct IpcSendArgs
+{
+   double             *dst[IPC_MAXP];   // remote segment of x_halo (current half) per send neighbour
+   unsigned long long *flag[IPC_MAXP];  // remote "data arrived" sequence slot
+   const unsigned long long *ack;       // local: sequence each send neighbour has finished reading
+   int                 off[IPC_MAXP + 1];
+   int                 npeer;
+   unsigned long long  seq;
+   unsigned           *ticket;
+};
+struct IpcRecvArgs
+{
+   const unsigned long long *flag;      // local: one slot per recv neighbour
+   int                 nflag;
+   unsigned long long  seq;             // 0: no wait (NCCL path)
+   unsigned long long *ack[IPC_MAXP];   // remote "consumed" slot per recv neighbour
+   unsigned           *ticket;
+};
+struct IpcHalo
+{
+   bool                on = false;
+   int64_t             region_off = -1;
+   size_t              region_bytes = 0;
+   double             *xh[2] = {nullptr, nullptr}; // local halves of x_halo
+   unsigned long long *data_flag = nullptr, *ack_flag = nullptr; // local slots
+   double             *dst[2][IPC_MAXP];
+   unsigned long long *dst_flag[IPC_MAXP], *src_ack[IPC_MAXP];
+   unsigned long long  seq = 0;
+   unsigned           *tickets = nullptr; // two device counters
+};
+
+#ifdef __CUDACC__
+__device__ __forceinline__ unsigned long long ld_acquire_sys_u64(const unsigned long long *p)
+{
+   unsigned long long v;
+   asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+   return v;
+}
+__device__ __forceinline__ void st_release_sys_u64(unsigned long long *p, unsigned long long v)
+{
+   asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+// bounded wait (about 10 s): a lost neighbour ends in a trap -- a loud CUDA error, not a hung GPU
+__device__ __forceinline__ void wait_seq_sys(const unsigned long long *p, unsigned long long want)
+{
+   if (ld_acquire_sys_u64(p) >= want) return;
+   const long long t0 = clock64();
+   while (ld_acquire_sys_u64(p) < want)
+   {
+      __nanosleep(64);
+      if (clock64() - t0 > 20000000000LL) __trap();
+   }
+}
+#endif
+
 struct HaloPlan
 {
+   IpcHalo             ipc;
    int                 n_halo = 0;         // number of offd columns (size of x_halo)
    int64_t            *col_map = nullptr;  // device, sorted global ids of offd columns
    std::vector<int>     recv_rank, recv_off, recv_cnt; // per neighbour (host)
@@ -208,6 +268,8 @@ int parcsr_build(int64_t rs, int64_t re, int64_t cs, int64_t ce, int64_t grows, 
 int bcast_bytes(void *buf_d, size_t bytes, int root);                 // NCCL broadcast on the compute stream
 int allgather_i64_host(int64_t mine, std::vector<int64_t> &all);
 int allgatherv_bytes(void *base_d, const int64_t *byte_offs /* nranks+1 */); // in place, compute stream
+void halo_plan_free(HaloPlan &H);
+IpcRecvArgs halo_recv_args(const hdk_csr_s &A, const double **xh); // after halo_exchange_begin
 int halo_exchange_begin(const hdk_csr_s &A, const double *x);
 int halo_exchange_end(const hdk_csr_s &A);
 

@@ -43,6 +43,9 @@ void       *hdk_stream(void);            /* cudaStream_t of the compute stream *
  * the host program (torch.distributed / any launcher) before hdk_comm_init. */
 int hdk_comm_unique_id(void *id128_h);
 int hdk_comm_init(int rank, int nranks, const void *id128_h);
+/* halo exchange in use: 0 = single rank, 1 = NCCL send/recv on a communication stream,
+ * 2 = peer-memory stores over NVLink (CUDA IPC arena; HDK_HALO_IPC=0 disables) */
+int hdk_comm_halo_mode(void);
 int hdk_comm_rank(void);
 int hdk_comm_size(void);
 int hdk_comm_finalize(void);

@@ -23,13 +23,17 @@ def _run(world, args, env_extra=None):
     ("lap7", ("12", "11", "6"), "40", "0"), ("lap7", ("16", "16", "10"), "262144", "0"),
     ("lap27", ("8", "8", "6"), "30", "0"), ("convdif", ("16", "8", "6"), "40", "0"),
     # replicated setup only (no work sharing between the ranks)
-    ("lap7", ("12", "11", "6"), "40", "off")])
+    ("lap7", ("12", "11", "6"), "40", "off"),
+    # NCCL send/recv halo exchange instead of the peer-memory (CUDA IPC) path
+    ("lap7", ("12", "11", "6"), "40", "nccl")])
 def test_two_rank_solve_matches_oracle(gpu, kind, dims, rep, share):
     if gpu.device_count() < 2:
         pytest.skip("needs two GPUs")
     env = {"HDK_REPLICATE_ROWS": rep}
     if share == "off":
         env["HDK_SETUP_SHARE"] = "0"
+    elif share == "nccl":
+        env["HDK_HALO_IPC"] = "0"
     else:
         env["HDK_SHARE_MIN_ROWS"] = share  # share the interpolation / RAP rows even on these tiny levels
     r = _run(2, [kind, *dims], env)
