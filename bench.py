@@ -12,8 +12,8 @@ of the reference) on an already set-up hierarchy.
           right-hand side from pinned host memory (SetRHSFromArray), solves (LinearSolverApply,
           including the reference's untimed r0 / final-residual evaluations) and downloads the
           solution (GetSolutionValues).
-  roofline     : the fine-level CSR SpMV stream kernel, algorithmic bytes / CUDA-event time,
-                 against MEASURED_PEAKS.json.
+  roofline     : the fine-level fused residual SpMV (the kernel with the largest share of a
+                 solve), algorithmic bytes / CUDA-event time, against MEASURED_PEAKS.json.
   cpu_baseline : the CPU oracle (restated reference, OpenMP) on a bounded sample, rank 0, N=1.
 
 `--impl reference` times the restated reference (oracle/) on the host cores; the real
@@ -54,10 +54,10 @@ preconditioner:
       num_sweeps: 1
 """
 
-# dram__bytes_read.sum + dram__bytes_write.sum per launch of the fine-level SpMV at the bench
+# dram__bytes_read.sum + dram__bytes_write.sum per launch of the fine-level residual SpMV at the bench
 # workload (256^3 7-point rows per GPU), from the `ncu --set full` capture summarised under
 # profiles/ (see profiles/README.md); None when no capture exists for the selected kernel
-NCU_TRAFFIC_BYTES = {"k_spmv_sell": None, "k_spmv_tma": 1.871e9}
+NCU_TRAFFIC_BYTES = {"k_spmv_sell": 1.7438e9 + 0.1185e9, "k_spmv_tma": 1.7404e9 + 0.1303e9}
 CPU_SAMPLE_EDGE = 160  # cube edge of the bounded CPU sample (about 10-30 s of work on ~8 cores)
 
 
@@ -301,13 +301,14 @@ def ours(args):
         hdk.check(hdk.lib().hdk_time_kernel(hA, hM, kid, 20, C.byref(ms), C.byref(by)))
         extra_kernels[name] = {"ms": ms.value, "GBps": by.value / ms.value / 1e6, "bytes": by.value}
     if rank == 0:
-        k0 = extra_kernels["spmv"]
+        k0 = extra_kernels["residual"]   # largest share of a solve (profiles/r01_launch_shares.csv)
         kk, ka, km = C.c_int(), C.c_double(), C.c_int()
         hdk.check(hdk.lib().hdk_csr_spmv_kind(hA, C.byref(kk), C.byref(ka), C.byref(km)))
         kname = {0: "k_spmv_tma", 1: "k_spmv_vector", 2: "k_spmv_sell"}.get(kk.value, "k_spmv")
         roof = {"bound": "hbm", "achieved": k0["GBps"], "peak": peak, "unit": "GB/s", "frac": k0["GBps"] / peak,
-                "traffic": NCU_TRAFFIC_BYTES.get(kname), "kernel": kname + "<SET> (fine level, y = A x, per GPU)",
+                "traffic": NCU_TRAFFIC_BYTES.get(kname), "kernel": kname + "<RESIDUAL> (fine level, r = b - A x, per GPU)",
                 "peak_source": peak_src,
+                "note": "peak is the measured copy bandwidth (half reads, half writes); this kernel is 94% reads",
                 "algorithmic_bytes": k0["bytes"], "ms": k0["ms"]}
     if dist is not None:
         dist.barrier()
