@@ -706,50 +706,75 @@ __global__ void __launch_bounds__(32 * IW_WARPS) k_interp_warp(const int *arp, c
       }
       return;
    }
-   // ---- weights: sequential over the row of A, lanes over the inner look-ups
-   double diagonal = aval[arp[i]];
-   for (int jj = arp[i] + 1; jj < arp[i + 1]; jj++)
+   // ---- weights: sequential over the row of A (hypre's order), lanes over the inner look-ups.
+   // The per-entry operands (column, value, table look-up, and for strong F neighbours the row
+   // bounds and diagonal sign of A_{i1}) are fetched by 32 lanes at once and broadcast with
+   // shuffles, so the sequential loop has no chain of dependent global loads.
+   const int rs = arp[i], re = arp[i + 1];
+   double    diagonal = aval[rs];
+   for (int cb = rs + 1; cb < re; cb += 32)
    {
-      const int    i1 = acol[jj];
-      const double a  = aval[jj];
-      const int    m  = wt_find(keys, idx, IW_CAP, i1);
-      if (m >= 0) { if (lane == 0) lv[m] = __dadd_rn(lv[m], a); }
-      else if (m == -2)
+      const int    jl = cb + lane;
+      const bool   vl = jl < re;
+      const int    p_i1 = vl ? acol[jl] : -1;
+      const double p_a  = vl ? aval[jl] : 0.0;
+      int          p_m = -1, p_b1 = 0, p_e1 = 0, p_cf = 0;
+      double       p_sgn = 1.0;
+      if (vl)
       {
-         const double sgn = aval[arp[i1]] < 0 ? -1.0 : 1.0;
-         const int    b1 = arp[i1] + 1, e1 = arp[i1 + 1];
-         double       sum = 0.0;
-         for (int base = b1; base < e1; base += 32)
+         p_m = wt_find(keys, idx, IW_CAP, p_i1);
+         if (p_m == -2)
          {
-            const int    j1 = base + lane;
-            const bool   v1 = j1 < e1;
-            const int    i2 = v1 ? acol[j1] : -1;
-            const double v  = v1 ? aval[j1] : 0.0;
-            const bool   q  = v1 && (sgn * v < 0) && (i2 == i || wt_find(keys, idx, IW_CAP, i2) >= 0);
-            unsigned     rem = __ballot_sync(FULL, q);
-            while (rem) { int src = __ffs(rem) - 1; sum = __dadd_rn(sum, __shfl_sync(FULL, v, src)); rem &= rem - 1u; }
+            const int d1 = arp[p_i1];
+            p_e1  = arp[p_i1 + 1];
+            p_sgn = aval[d1] < 0 ? -1.0 : 1.0;
+            p_b1  = d1 + 1;
          }
-         if (sum != 0.0)
+         else if (p_m < 0) p_cf = cf[p_i1];
+      }
+      const int nchunk = (re - cb) < 32 ? (re - cb) : 32;
+      for (int t = 0; t < nchunk; t++)
+      {
+         const double a = __shfl_sync(FULL, p_a, t);
+         const int    m = __shfl_sync(FULL, p_m, t);
+         if (m >= 0) { if (lane == 0) lv[m] = __dadd_rn(lv[m], a); }
+         else if (m == -2)
          {
-            const double distribute = __ddiv_rn(a, sum);
+            const double sgn = __shfl_sync(FULL, p_sgn, t);
+            const int    b1 = __shfl_sync(FULL, p_b1, t), e1 = __shfl_sync(FULL, p_e1, t);
+            double       sum = 0.0;
             for (int base = b1; base < e1; base += 32)
             {
                const int    j1 = base + lane;
                const bool   v1 = j1 < e1;
                const int    i2 = v1 ? acol[j1] : -1;
                const double v  = v1 ? aval[j1] : 0.0;
-               const bool   neg = v1 && (sgn * v < 0);
-               const int    m2 = neg ? wt_find(keys, idx, IW_CAP, i2) : -1;
-               const double t  = __dmul_rn(distribute, v);
-               if (neg && m2 >= 0) lv[m2] = __dadd_rn(lv[m2], t);
-               const unsigned dm = __ballot_sync(FULL, neg && i2 == i);
-               if (dm) diagonal = __dadd_rn(diagonal, __shfl_sync(FULL, t, __ffs(dm) - 1));
+               const bool   q  = v1 && (sgn * v < 0) && (i2 == i || wt_find(keys, idx, IW_CAP, i2) >= 0);
+               unsigned     rem = __ballot_sync(FULL, q);
+               while (rem) { int src = __ffs(rem) - 1; sum = __dadd_rn(sum, __shfl_sync(FULL, v, src)); rem &= rem - 1u; }
             }
+            if (sum != 0.0)
+            {
+               const double distribute = __ddiv_rn(a, sum);
+               for (int base = b1; base < e1; base += 32)
+               {
+                  const int    j1 = base + lane;
+                  const bool   v1 = j1 < e1;
+                  const int    i2 = v1 ? acol[j1] : -1;
+                  const double v  = v1 ? aval[j1] : 0.0;
+                  const bool   neg = v1 && (sgn * v < 0);
+                  const int    m2 = neg ? wt_find(keys, idx, IW_CAP, i2) : -1;
+                  const double tt = __dmul_rn(distribute, v);
+                  if (neg && m2 >= 0) lv[m2] = __dadd_rn(lv[m2], tt);
+                  const unsigned dm = __ballot_sync(FULL, neg && i2 == i);
+                  if (dm) diagonal = __dadd_rn(diagonal, __shfl_sync(FULL, tt, __ffs(dm) - 1));
+               }
+            }
+            else diagonal = __dadd_rn(diagonal, a);
          }
-         else diagonal = __dadd_rn(diagonal, a);
+         else if (__shfl_sync(FULL, p_cf, t) != SF_PT) diagonal = __dadd_rn(diagonal, a);
+         __syncwarp();
       }
-      else if (cf[i1] != SF_PT) diagonal = __dadd_rn(diagonal, a);
-      __syncwarp();
    }
    if (diagonal != 0.0)
    {
@@ -980,14 +1005,14 @@ __global__ void __launch_bounds__(32 * RW_WARPS) k_rap_warp(const int *rrp, cons
                                                             const int *arp, const int *acol, const double *aval,
                                                             const int *prp, const int *pcol, const double *pval,
                                                             int nc, int *cnt, const int *crp, int *ccol, double *cval,
-                                                            int row_lo)
+                                                            int row_lo, int len_lo, int len_hi)
 {
    extern __shared__ __align__(16) unsigned char rw_smem[];
    const int      lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
    const unsigned FULL = 0xffffffffu;
    const int      ic = row_lo + blockIdx.x * RW_WARPS + wid; // rows [row_lo, nc)
    if (ic >= nc) return;
-   if (FILL && cnt[ic] > RW_LIMIT) return;
+   if (FILL) { const int c = cnt[ic]; if (c > RW_LIMIT || c <= len_lo || c > len_hi) return; } // rows of this table size
    int    *keys = reinterpret_cast<int *>(rw_smem) + (size_t)wid * CAP;
    int    *idx  = reinterpret_cast<int *>(rw_smem) + (size_t)RW_WARPS * CAP + (size_t)wid * CAP;
    double *vals = reinterpret_cast<double *>(rw_smem + (size_t)2 * RW_WARPS * CAP * sizeof(int)) + (size_t)wid * CAP;
@@ -1002,22 +1027,55 @@ __global__ void __launch_bounds__(32 * RW_WARPS) k_rap_warp(const int *rrp, cons
       if (FILL) { idx[h] = 0; vals[h] = 0.0; }
    }
    __syncwarp();
-   for (int j1 = rrp[ic]; j1 < rrp[ic + 1] && !overflow; j1++)
+   // The loop nest is hypre's (R row -> A rows -> P rows) and is walked in its order, 32 entries
+   // of an A row ("chunk") at a time.  Latency hiding: the R row with the bounds of its A rows is
+   // fetched 32 entries at once and broadcast by shuffles, and the operands of chunk k+1 (A
+   // entries and their P row bounds) are loaded before chunk k is processed.
+   const int rend = rrp[ic + 1];
+   for (int rb = rrp[ic]; rb < rend && !overflow; rb += 32)
    {
-      const int    i1 = rcol[j1];
-      const double r  = FILL ? rval[j1] : 0.0;
-      const int    a0 = arp[i1], a1 = arp[i1 + 1];
-      for (int base = a0; base < a1 && !overflow; base += 32)
+      const int    jr = rb + lane;
+      const bool   vr = jr < rend;
+      const int    p_i1 = vr ? rcol[jr] : 0;
+      const double p_r  = (FILL && vr) ? rval[jr] : 0.0;
+      const int    p_a0 = vr ? arp[p_i1] : 0, p_a1 = vr ? arp[p_i1 + 1] : 0;
+      const int    nR = (rend - rb) < 32 ? (rend - rb) : 32;
+      int          t = 0, base = __shfl_sync(FULL, p_a0, 0);
+      // operands of the current chunk
+      int    i2, ps, pl;
+      double ra;
       {
-         const int  j2 = base + lane;
-         const bool v2 = j2 < a1;
-         int        i2 = v2 ? acol[j2] : 0;
-         double     ra = (FILL && v2) ? __dmul_rn(r, aval[j2]) : 0.0;
-         int        ps = v2 ? prp[i2] : 0;
-         int        pl = v2 ? prp[i2 + 1] - ps : 0;
-         int        incl = pl;
+         const int    a1 = __shfl_sync(FULL, p_a1, 0);
+         const double r  = __shfl_sync(FULL, p_r, 0);
+         const int    j2 = base + lane;
+         const bool   v2 = j2 < a1;
+         i2 = v2 ? acol[j2] : 0;
+         ra = (FILL && v2) ? __dmul_rn(r, aval[j2]) : 0.0;
+         ps = v2 ? prp[i2] : 0;
+         pl = v2 ? prp[i2 + 1] - ps : 0;
+      }
+      while (t < nR && !overflow)
+      {
+         // coordinates and operands of the next chunk
+         int nt = t, nbase = base + 32;
+         if (nbase >= __shfl_sync(FULL, p_a1, t)) { nt = t + 1; nbase = __shfl_sync(FULL, p_a0, nt & 31); }
+         int    n_i2 = 0, n_ps = 0, n_pl = 0;
+         double n_ra = 0.0;
+         if (nt < nR)
+         {
+            const int    a1 = __shfl_sync(FULL, p_a1, nt);
+            const double r  = __shfl_sync(FULL, p_r, nt);
+            const int    j2 = nbase + lane;
+            const bool   v2 = j2 < a1;
+            n_i2 = v2 ? acol[j2] : 0;
+            n_ra = (FILL && v2) ? __dmul_rn(r, aval[j2]) : 0.0;
+            n_ps = v2 ? prp[n_i2] : 0;
+            n_pl = v2 ? prp[n_i2 + 1] - n_ps : 0;
+         }
+         // process the current chunk
+         int incl = pl;
 #pragma unroll
-         for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(FULL, incl, o); if (lane >= o) incl += t; }
+         for (int o = 1; o < 32; o <<= 1) { int u = __shfl_up_sync(FULL, incl, o); if (lane >= o) incl += u; }
          const int excl = incl - pl, Tc = __shfl_sync(FULL, incl, 31);
          for (int q0 = 0; q0 < Tc; q0 += 32)
          {
@@ -1068,6 +1126,8 @@ __global__ void __launch_bounds__(32 * RW_WARPS) k_rap_warp(const int *rrp, cons
             __syncwarp();
             if (overflow) break;
          }
+         t = nt; base = nbase;
+         i2 = n_i2; ra = n_ra; ps = n_ps; pl = n_pl;
       }
    }
    if (!FILL) { if (lane == 0) cnt[ic] = overflow ? -1 : count; return; }
@@ -1181,7 +1241,7 @@ static int build_rap(const DevCSR &R, const DevCSR &A, const DevCSR &P, DevCSR &
    if (share_on(nc)) HDK_CUDA(cudaMemsetAsync(cnt, 0, sizeof(int) * ((size_t)nc + 1), g.stream));
    // pass 1a: exact row lengths by the warp kernel (rows longer than RW_LIMIT are flagged -1)
    k_rap_warp<false, RW_CAP><<<cdiv(hi - lo, RW_WARPS), 32 * RW_WARPS, (size_t)RW_WARPS * RW_CAP * sizeof(int), g.stream>>>(
-      R.rowptr, R.col, R.val, A.rowptr, A.col, A.val, P.rowptr, P.col, P.val, hi, cnt, nullptr, nullptr, nullptr, lo);
+      R.rowptr, R.col, R.val, A.rowptr, A.col, A.val, P.rowptr, P.col, P.val, hi, cnt, nullptr, nullptr, nullptr, lo, 0, 0);
    HDK_LAUNCH_CHECK();
    stage_mark("  rap.warp1", -1);
    // pass 1b: flagged rows through the one-thread-per-row kernel with hash sets in global scratch
@@ -1228,12 +1288,23 @@ static int build_rap(const DevCSR &R, const DevCSR &A, const DevCSR &P, DevCSR &
       static bool attr = false;
       size_t      smem = (size_t)RW_WARPS * RW_CAP * (2 * sizeof(int) + sizeof(double));
       if (!attr) { HDK_CUDA(cudaFuncSetAttribute(k_rap_warp<true, RW_CAP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = true; }
-      if (hmax <= 80)
-         k_rap_warp<true, 128><<<cdiv(hi - lo, RW_WARPS), 32 * RW_WARPS, (size_t)RW_WARPS * 128 * 16, g.stream>>>(
-            R.rowptr, R.col, R.val, A.rowptr, A.col, A.val, P.rowptr, P.col, P.val, hi, cnt, crp, C.col, C.val, lo);
-      else
-         k_rap_warp<true, RW_CAP><<<cdiv(hi - lo, RW_WARPS), 32 * RW_WARPS, smem, g.stream>>>(
-            R.rowptr, R.col, R.val, A.rowptr, A.col, A.val, P.rowptr, P.col, P.val, hi, cnt, crp, C.col, C.val, lo);
+      // the table size is a static share of shared memory, so it sets the occupancy: rows are
+      // served by the smallest table that holds them (load factor <= 5/8), one launch per size
+      static bool attr256 = false;
+      if (!attr256) { HDK_CUDA(cudaFuncSetAttribute(k_rap_warp<true, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, RW_WARPS * 256 * 16)); attr256 = true; }
+      const int nb = cdiv(hi - lo, RW_WARPS);
+      k_rap_warp<true, 128><<<nb, 32 * RW_WARPS, (size_t)RW_WARPS * 128 * 16, g.stream>>>(
+         R.rowptr, R.col, R.val, A.rowptr, A.col, A.val, P.rowptr, P.col, P.val, hi, cnt, crp, C.col, C.val, lo, 0, 80);
+      HDK_LAUNCH_CHECK();
+      if (hmax > 80)
+      {
+         k_rap_warp<true, 256><<<nb, 32 * RW_WARPS, (size_t)RW_WARPS * 256 * 16, g.stream>>>(
+            R.rowptr, R.col, R.val, A.rowptr, A.col, A.val, P.rowptr, P.col, P.val, hi, cnt, crp, C.col, C.val, lo, 80, 160);
+         HDK_LAUNCH_CHECK();
+      }
+      if (hmax > 160)
+         k_rap_warp<true, RW_CAP><<<nb, 32 * RW_WARPS, smem, g.stream>>>(
+            R.rowptr, R.col, R.val, A.rowptr, A.col, A.val, P.rowptr, P.col, P.val, hi, cnt, crp, C.col, C.val, lo, 160, RW_LIMIT);
       HDK_LAUNCH_CHECK();
       stage_mark("  rap.warp2", -1);
    }
