@@ -175,6 +175,7 @@ int parcsr_build(int64_t rs, int64_t re, int64_t cs, int64_t ce, int64_t grows, 
    else if (tot[1] > 0)
       return set_error(HDK_ERR_INVALID, "matrix has %d off-rank columns but is not distributed", n_halo);
    dfree(gcol_o);
+   A->diag.offd_rowptr = (tot[1] > 0) ? A->offd.rowptr : nullptr;
    if (analyze) HDK_TRY(csr_analyze(A->diag));
    if (A->offd.nnz > 0)
    {
@@ -222,17 +223,50 @@ static int parcsr_from_device(int64_t rs, int64_t re, int64_t grows, const int64
 // ---- y = op(A) x with halo exchange: diag kernel overlaps the exchange, offd kernel follows
 __global__ void k_offd_correct(const int *rows, const int *rowptr, const int *col, const double *val, int nrows,
                                const double *xh, double *y, const double *d, double w, int mode,
-                               double alpha, IpcRecvArgs ipc);
+                               double alpha, IpcRecvArgs ipc, const double *dotv, const double *diag_part,
+                               double *dot_out, double *partials, unsigned *ticket);
+
+// The fused variant needs 48-64 registers (5 or 4 CTAs per SM instead of 8): it wins on the
+// coarser operators, where the saved kernel + launch gap matters, and loses ~20-30 us on the
+// 16.7 M-row fine level, where occupancy matters more -- hence the row limit.
+static bool fuse_offd_enabled(int nrows)
+{
+   static int       on = -1;
+   static long long max_rows = 4000000;
+   if (on < 0)
+   {
+      const char *e = getenv("HDK_FUSE_OFFD");
+      on = (e && atoi(e) == 0) ? 0 : 1;
+      if (getenv("HDK_FUSE_OFFD_MAX_ROWS")) max_rows = atoll(getenv("HDK_FUSE_OFFD_MAX_ROWS"));
+   }
+   return on == 1 && nrows <= max_rows;
+}
 
 int parcsr_matvec(const hdk_csr_s &A, int mode, SpmvArgs a)
 {
    // p2p exchange partners must match: a rank takes part when it sends OR receives
    bool exch = g.nranks > 1 && (A.halo.n_send > 0 || A.halo.n_halo > 0);
    if (!exch) return spmv_launch(A.diag, mode, a);
-   // start the exchange, run the diag block (no fused dot: the result is not final yet)
+   if (A.halo.ipc.on && A.diag.kind == 2 && A.diag.sl_offd_flags && A.offd.nnz > 0 && fuse_offd_enabled(A.diag.nrows))
+   {
+      // peer-memory halo + sliced-ELL: ONE kernel does the diag block, waits in-kernel for the
+      // neighbours' values where a row needs them, adds the off-diagonal entries and runs the
+      // fused epilogue / dot exactly as on a single rank
+      HDK_TRY(halo_exchange_begin(A, a.x));
+      OffdFuse of;
+      of.orp = A.offd.rowptr; of.ocol = A.offd.col; of.oval = A.offd.val;
+      of.ipc = halo_recv_args(A, &of.xh);
+      return spmv_launch(A.diag, mode, a, &of);
+   }
+   // start the exchange, run the diag block.  A fused dot <dotv, y> is linear in the off-diagonal
+   // correction: the diag kernel leaves <dotv, y_diag> in a scratch scalar and the correction
+   // kernel adds <dotv, delta y> over its rows -- no extra pass over the vectors
    HDK_TRY(halo_exchange_begin(A, a.x));
+   const bool want_dot  = (a.fin != FIN_NONE && a.dotv);
+   const bool fused_dot = want_dot && a.fin == FIN_STORE && a.fin_out != nullptr;
    SpmvArgs ad = a;
-   ad.fin = FIN_NONE; ad.dotv = nullptr;
+   if (fused_dot && A.offd.nnz > 0) ad.fin_out = g.dscal + S_TMP1;
+   else if (!fused_dot) { ad.fin = FIN_NONE; ad.dotv = nullptr; }
    HDK_TRY(spmv_launch(A.diag, mode, ad));
    HDK_TRY(halo_exchange_end(A));
    // offd contribution: y_i += sign * sum_o (linear correction of the diag-only epilogue)
@@ -242,10 +276,11 @@ int parcsr_matvec(const hdk_csr_s &A, int mode, SpmvArgs a)
       const double *xh;
       IpcRecvArgs   ra = halo_recv_args(A, &xh);
       k_offd_correct<<<grid, 128, 0, g.stream>>>(A.offd_rows, A.offd.rowptr, A.offd.col, A.offd.val, A.n_offd_rows,
-                                                 xh, a.y, a.d, a.w, mode, a.alpha, ra);
+                                                 xh, a.y, a.d, a.w, mode, a.alpha, ra, fused_dot ? a.dotv : nullptr,
+                                                 g.dscal + S_TMP1, a.fin_out, g.partials, g.counters + 1);
       HDK_LAUNCH_CHECK();
    }
-   if (a.fin != FIN_NONE && a.dotv)
+   if (want_dot && !fused_dot)
    {
       HDK_TRY(vec_dot_dev(a.dotv, a.y, A.diag.nrows, a.fin, a.fin_out));
    }
@@ -254,8 +289,12 @@ int parcsr_matvec(const hdk_csr_s &A, int mode, SpmvArgs a)
 
 __global__ void k_offd_correct(const int *rows, const int *rowptr, const int *col, const double *val, int nrows,
                                const double *xh, double *y, const double *d, double w, int mode,
-                               double alpha, IpcRecvArgs ipc)
+                               double alpha, IpcRecvArgs ipc, const double *dotv, const double *diag_part,
+                               double *dot_out, double *partials, unsigned *ticket)
 {
+   __shared__ double red[128 / 32];
+   __shared__ int    lastflag;
+   double            dcorr = 0.0; // dotv[r] * (change of y[r])
    // peer-memory exchange: the neighbours' pack kernels store into xh and then raise the
    // sequence flags; wait for them here, so the transfer overlaps the diag-block kernel
    if (ipc.seq)
@@ -271,14 +310,39 @@ __global__ void k_offd_correct(const int *rows, const int *rowptr, const int *co
       int s = rowptr[r], e = rowptr[r + 1];
       double acc = 0.0;
       for (int k = s; k < e; k++) acc += val[k] * __ldcg(xh + col[k]); // L2: written by a peer
+      double delta = 0.0;
       switch (mode)
       {
          case SPMV_SET:
-         case SPMV_ADD: y[r] += acc; break;
-         case SPMV_AXPBY: y[r] += alpha * acc; break;
-         case SPMV_RESIDUAL: y[r] -= acc; break;
+         case SPMV_ADD: delta = acc; break;
+         case SPMV_AXPBY: delta = alpha * acc; break;
+         case SPMV_RESIDUAL: delta = -acc; break;
          case SPMV_JACOBI:
-         case SPMV_JACOBI_R: { double dd = d[r]; if (dd != 0.0) y[r] -= (w * acc) / dd; break; }
+         case SPMV_JACOBI_R: { double dd = d[r]; if (dd != 0.0) delta = -(w * acc) / dd; break; }
+      }
+      y[r] += delta;
+      if (dotv) dcorr = dotv[r] * delta;
+   }
+   if (dotv)
+   {
+      // <dotv, y> = <dotv, y_diag> (left in *diag_part by the diag kernel) + sum of the corrections
+      double bs = block_sum<128>(dcorr, red);
+      if (threadIdx.x == 0)
+      {
+         partials[blockIdx.x] = bs;
+         __threadfence();
+         unsigned t = atomicInc(ticket, gridDim.x - 1);
+         lastflag   = (t == gridDim.x - 1);
+      }
+      __syncthreads();
+      if (lastflag)
+      {
+         __threadfence();
+         double sacc = 0.0;
+         for (unsigned b = threadIdx.x; b < gridDim.x; b += 128) sacc += __ldcg(partials + b);
+         __syncthreads();
+         sacc = block_sum<128>(sacc, red);
+         if (threadIdx.x == 0) *dot_out = *diag_part + sacc;
       }
    }
    if (ipc.seq)

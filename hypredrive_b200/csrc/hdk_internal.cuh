@@ -100,9 +100,11 @@ struct DevCSR
    // sliced-ELL copy (kind 2): slices of 32 rows stored column-major, see hdk_spmv.cu
    int     nslice = 0;
    int    *sl_off = nullptr;  // nslice+1 prefix sums of slice widths (units of 32 entries)
-   int    *sl_meta = nullptr; // nslice*32: (row length << 5) | row offset inside the slice
+   int    *sl_meta = nullptr; // nslice*32: row length << 6 | has-offd flag << 5 | row offset inside the slice
    int    *sl_col = nullptr;
    double *sl_val = nullptr;
+   const int *offd_rowptr = nullptr; // set before csr_analyze: rows with off-rank entries get flagged in sl_meta
+   bool    sl_offd_flags = false;
    bool    coarse_op = false; // Galerkin operator of the hierarchy: its stored column order may be changed
    bool    owns = true;
 };
@@ -154,7 +156,6 @@ struct SpmvArgs
    double       *fin_out = nullptr;
 };
 
-int spmv_launch(const DevCSR &A, int mode, const SpmvArgs &a);
 
 // vector kernels (hdk_vec.cu)
 int vec_fill(double *x, double v, int64_t n);
@@ -164,7 +165,8 @@ int vec_scale(double a, double *x, int64_t n);
 int vec_dot_dev(const double *x, const double *y, int64_t n, int fin, double *out_d); // device result
 int vec_dot_host(const double *x, const double *y, int64_t n, double *out_h);         // + allreduce
 int vec_scaled_div(double *u, const double *f, const double *d, double w, int64_t n); // u = w f / d
-int pcg_update_xr(double *x, double *r, const double *p, const double *s, int64_t n, double *scal);
+int pcg_update_xr(double *x, double *r, const double *p, const double *s, int64_t n, double *scal,
+                  int fin = FIN_IPROD, double *fin_out = nullptr); // <r,r> -> fin (FIN_STORE at N > 1)
 int pcg_update_p(double *p, const double *z, int64_t n, const double *scal);
 int vec_copy_dot(double *z, const double *r, int64_t n, int fin, double *out_d);      // z=r, <r,r>
 int allreduce_dev(double *buf_d, int count);                                          // NCCL sum (no-op on 1 rank)
@@ -194,6 +196,16 @@ struct IpcRecvArgs
    unsigned long long *ack[IPC_MAXP];   // remote "consumed" slot per recv neighbour
    unsigned           *ticket;
 };
+// off-diagonal block fused into the sliced-ELL kernel (peer-memory halo only): rows flagged in
+// sl_meta add their offd entries after waiting for the neighbours' sequence flags in-kernel
+struct OffdFuse
+{
+   const int    *orp = nullptr, *ocol = nullptr;
+   const double *oval = nullptr, *xh = nullptr;
+   IpcRecvArgs   ipc;
+};
+int spmv_launch(const DevCSR &A, int mode, const SpmvArgs &a, const OffdFuse *of = nullptr);
+
 struct IpcHalo
 {
    bool                on = false;
@@ -219,15 +231,19 @@ __device__ __forceinline__ void st_release_sys_u64(unsigned long long *p, unsign
    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 // bounded wait (about 10 s): a lost neighbour ends in a trap -- a loud CUDA error, not a hung GPU
-__device__ __forceinline__ void wait_seq_sys(const unsigned long long *p, unsigned long long want)
+static __device__ __noinline__ void wait_seq_slow(const unsigned long long *p, unsigned long long want)
 {
-   if (ld_acquire_sys_u64(p) >= want) return;
    const long long t0 = clock64();
    while (ld_acquire_sys_u64(p) < want)
    {
       __nanosleep(64);
       if (clock64() - t0 > 20000000000LL) __trap();
    }
+}
+__device__ __forceinline__ void wait_seq_sys(const unsigned long long *p, unsigned long long want)
+{
+   if (ld_acquire_sys_u64(p) >= want) return;
+   wait_seq_slow(p, want); // out of line: keeps the waiting kernels' register count down
 }
 #endif
 

@@ -120,14 +120,8 @@ int hdk_pcg(const hdk_csr *A, hdk_amg *M, const double *b, double *x, hdk_krylov
       if ((rc = parcsr_matvec(*A, SPMV_SET, a))) goto done;
       if ((rc = finish_dot(FIN_SDOTP, nullptr))) goto done;
       // x += alpha p ; r -= alpha s ; i_prod = <r,r>       (one kernel)
-      if (g.nranks <= 1) { if ((rc = pcg_update_xr(x, r, p, s, n, S))) goto done; }
-      else
-      {
-         if ((rc = axpy_dev(S + S_ALPHA, 1.0, p, x, n))) goto done;
-         if ((rc = axpy_dev(S + S_ALPHA, -1.0, s, r, n))) goto done;
-         if ((rc = vec_dot_dev(r, r, n, FIN_STORE, S + S_TMP0))) goto done;
-         if ((rc = finish_dot(FIN_IPROD, nullptr))) goto done;
-      }
+      if ((rc = pcg_update_xr(x, r, p, s, n, S, local_fin(FIN_IPROD), local_out(nullptr)))) goto done;
+      if ((rc = finish_dot(FIN_IPROD, nullptr))) goto done;
       if ((rc = read_scalars(8))) goto done;
       // s = M^{-1} r ; gamma_new = <r,s> ; beta = gamma_new / gamma  (V-cycle; the host
       // decision below overlaps it -- hypre also preconditions before testing)

@@ -80,6 +80,10 @@ struct SpmvDev
    const int    *sl_off, *sl_meta, *sl_col;
    const double *sl_val;
    int           nslice;
+   // fused off-diagonal block (peer-memory halo): see OffdFuse
+   const int    *orp, *ocol;
+   const double *oval, *xh;
+   IpcRecvArgs   ipc;
 };
 
 // ---- PTX helpers: mbarrier + 1-D bulk tensor-memory-accelerator copies -------------------
@@ -362,6 +366,7 @@ __global__ void __launch_bounds__(ST, 4) k_spmv_tma(SpmvDev a, int nblk, int cap
 // its stored order with separately rounded multiply and add.
 // ---------------------------------------------------------------------------------------
 constexpr int SELL_T = 256;
+constexpr int SELL_OFFD_BIT = 32; // sl_meta = len << 6 | offd flag << 5 | row offset in the slice
 
 template <int MODE>
 __device__ __forceinline__ double row_epilogue(const SpmvDev &a, const RowOps &o, double acc)
@@ -374,7 +379,7 @@ __device__ __forceinline__ double row_epilogue(const SpmvDev &a, const RowOps &o
    return (o.d != 0.0) ? __ddiv_rn(__dmul_rn(a.w, acc), o.d) : 0.0;
 }
 
-template <int MODE, bool DOT>
+template <int MODE, bool DOT, bool OFFD>
 __global__ void __launch_bounds__(SELL_T) k_spmv_sell(SpmvDev a)
 {
    constexpr bool SUB = (MODE == SPMV_RESIDUAL || MODE == SPMV_JACOBI || MODE == SPMV_JACOBI_R);
@@ -383,10 +388,11 @@ __global__ void __launch_bounds__(SELL_T) k_spmv_sell(SpmvDev a)
    const int lane = threadIdx.x & 31;
    const int wpb  = SELL_T / 32;
    double    dacc = 0.0;
+   bool      halo_ready = false;
    for (int s = blockIdx.x * wpb + (threadIdx.x >> 5); s < a.nslice; s += gridDim.x * wpb)
    {
       const int  meta  = __ldg(a.sl_meta + (size_t)s * 32 + lane);
-      const int  len   = meta >> 5;
+      const int  len   = meta >> 6;
       const int  r     = s * 32 + (meta & 31);
       const bool valid = r < a.nrows;
       const size_t base = (size_t)__ldg(a.sl_off + s) * 32 + lane;
@@ -429,11 +435,41 @@ __global__ void __launch_bounds__(SELL_T) k_spmv_sell(SpmvDev a)
          c0 = n0; c1 = n1; c2 = n2; c3 = n3;
          v0 = w0; v1 = w1; v2 = w2; v3 = w3;
       }
+      if (OFFD && (meta & SELL_OFFD_BIT))
+      {
+         // row with off-rank entries: the neighbours' pack kernels store the halo values into xh
+         // over NVLink and then raise their sequence flags -- wait for them here (only the first
+         // flagged row of a lane really waits), then continue the row in stored order
+         if (!halo_ready)
+         {
+            for (int p = 0; p < a.ipc.nflag; p++) wait_seq_sys(a.ipc.flag + p, a.ipc.seq);
+            halo_ready = true;
+         }
+         for (int k = __ldg(a.orp + r), e = __ldg(a.orp + r + 1); k < e; ++k)
+         {
+            const double p0 = __dmul_rn(__ldg(a.oval + k), __ldcg(a.xh + __ldg(a.ocol + k)));
+            acc = __dadd_rn(acc, SUB ? -p0 : p0);
+         }
+      }
       if (valid)
       {
          double yn = row_epilogue<MODE>(a, o, acc);
          a.y[r]    = yn;
          if (DOT) dacc += o.dv * yn;
+      }
+   }
+   if (OFFD && a.ipc.seq)
+   {
+      // all reads of xh by this CTA are done; the last CTA tells the senders (buffer reuse at seq + 2)
+      __syncthreads();
+      if (threadIdx.x == 0)
+      {
+         unsigned t = atomicInc(a.ipc.ticket, gridDim.x - 1);
+         if (t == gridDim.x - 1)
+         {
+            __threadfence_system();
+            for (int p = 0; p < a.ipc.nflag; p++) st_release_sys_u64(a.ipc.ack[p], a.ipc.seq);
+         }
       }
    }
    if (DOT)
@@ -445,7 +481,8 @@ __global__ void __launch_bounds__(SELL_T) k_spmv_sell(SpmvDev a)
 }
 
 // slice metadata: lanes ranked by decreasing row length (ties by row), slice width = longest row
-__global__ void k_sell_meta(const int *rowptr, int nrows, int nslice, int *meta, int *width, int *max_slice_nnz)
+__global__ void k_sell_meta(const int *rowptr, int nrows, int nslice, int *meta, int *width, int *max_slice_nnz,
+                            const int *offd_rowptr)
 {
    const int lane = threadIdx.x & 31;
    const int s    = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -460,7 +497,8 @@ __global__ void k_sell_meta(const int *rowptr, int nrows, int nslice, int *meta,
       rank += (kj > key) || (kj == key && j < lane);
       w = kj > w ? kj : w;
    }
-   meta[(size_t)s * 32 + rank] = (len << 5) | lane;
+   const int ob = (offd_rowptr && r < nrows && offd_rowptr[r + 1] > offd_rowptr[r]) ? SELL_OFFD_BIT : 0;
+   meta[(size_t)s * 32 + rank] = (len << 6) | lane | ob;
    if (lane == 0)
    {
       width[s] = w;
@@ -488,7 +526,7 @@ __global__ void k_sell_fill(const int *rowptr, const int *col, const double *val
    const int k0 = rowptr[s * 32], k1 = rowptr[hi];
    for (int k = k0 + lane; k < k1; k += 32) { cs[k - k0] = col[k]; vs[k - k0] = val[k]; }
    __syncwarp();
-   const int m = meta[(size_t)s * 32 + lane], len = m >> 5, r = s * 32 + (m & 31);
+   const int m = meta[(size_t)s * 32 + lane], len = m >> 6, r = s * 32 + (m & 31);
    if (r >= nrows || len == 0) return;
    const int rs = rowptr[r] - k0;
    if (SORT)
@@ -511,20 +549,25 @@ __global__ void k_sell_fill(const int *rowptr, const int *col, const double *val
    }
 }
 
-template <int MODE, bool DOT>
-static int launch_sell(const DevCSR &A, const SpmvDev &d)
+template <int MODE, bool DOT, bool OFFD>
+static int launch_sell_v(const DevCSR &A, const SpmvDev &d)
 {
    static int occ = 0;
    if (!occ)
    {
-      HDK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_spmv_sell<MODE, DOT>, SELL_T, 0));
+      HDK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_spmv_sell<MODE, DOT, OFFD>, SELL_T, 0));
       if (occ < 1) occ = 1;
    }
    int grid = cdiv(A.nslice, SELL_T / 32);
    int cap  = g.sm_count * occ;
    if (grid > cap) grid = cap;
-   k_spmv_sell<MODE, DOT><<<grid, SELL_T, 0, g.stream>>>(d);
+   k_spmv_sell<MODE, DOT, OFFD><<<grid, SELL_T, 0, g.stream>>>(d);
    return HDK_OK;
+}
+template <int MODE, bool DOT>
+static int launch_sell(const DevCSR &A, const SpmvDev &d)
+{
+   return d.orp ? launch_sell_v<MODE, DOT, true>(A, d) : launch_sell_v<MODE, DOT, false>(A, d);
 }
 
 // one warp per row; lanes stride the row with scalar loads (rows here are long, so each warp
@@ -627,7 +670,7 @@ static int launch_mode(const DevCSR &A, const SpmvDev &d, bool dot)
    return HDK_OK;
 }
 
-int spmv_launch(const DevCSR &A, int mode, const SpmvArgs &s)
+int spmv_launch(const DevCSR &A, int mode, const SpmvArgs &s, const OffdFuse *of)
 {
    if (A.nrows <= 0) return HDK_OK;
    SpmvDev d;
@@ -637,6 +680,13 @@ int spmv_launch(const DevCSR &A, int mode, const SpmvArgs &s)
    d.nrows = A.nrows; d.fin = s.fin; d.fin_out = s.fin_out;
    d.scal = g.dscal; d.partials = g.partials; d.ticket = g.counters;
    d.sl_off = A.sl_off; d.sl_meta = A.sl_meta; d.sl_col = A.sl_col; d.sl_val = A.sl_val; d.nslice = A.nslice;
+   d.orp = nullptr; d.ocol = nullptr; d.oval = nullptr; d.xh = nullptr;
+   memset(&d.ipc, 0, sizeof(d.ipc));
+   if (of)
+   {
+      if (A.kind != 2 || !A.sl_offd_flags) return set_error(HDK_ERR_INVALID, "fused off-diagonal block needs the sliced-ELL layout");
+      d.orp = of->orp; d.ocol = of->ocol; d.oval = of->oval; d.xh = of->xh; d.ipc = of->ipc;
+   }
    bool dot = (s.fin != FIN_NONE && s.dotv != nullptr);
    switch (mode)
    {
@@ -698,7 +748,8 @@ static int sell_build(DevCSR &A)
    HDK_TRY(dalloc(&width, (size_t)ns + 1));
    HDK_CUDA(cudaMemsetAsync(width + ns, 0, sizeof(int), g.stream));
    HDK_CUDA(cudaMemsetAsync(dmax, 0, sizeof(int), g.stream));
-   k_sell_meta<<<cdiv(ns, 8), 256, 0, g.stream>>>(A.rowptr, A.nrows, ns, A.sl_meta, width, dmax);
+   k_sell_meta<<<cdiv(ns, 8), 256, 0, g.stream>>>(A.rowptr, A.nrows, ns, A.sl_meta, width, dmax, A.offd_rowptr);
+   A.sl_offd_flags = (A.offd_rowptr != nullptr);
    HDK_LAUNCH_CHECK();
    HDK_TRY(exclusive_scan_int(width, A.sl_off, ns + 1));
    int h[2] = {0, 0};

@@ -101,7 +101,8 @@ __global__ void __launch_bounds__(VT) k_reduce(const double *__restrict__ x, con
 // PCG: x += alpha p ; r -= alpha s ; i_prod = <r,r>   (one pass, 48 bytes per row)
 __global__ void __launch_bounds__(VT) k_pcg_xr(double *__restrict__ x, double *__restrict__ r,
                                                const double *__restrict__ p, const double *__restrict__ s,
-                                               int64_t n, double *partials, unsigned *ticket, double *scal)
+                                               int64_t n, double *partials, unsigned *ticket, double *scal,
+                                               int fin, double *fin_out)
 {
    __shared__ double sm[VT / 32];
    __shared__ int    flag;
@@ -116,7 +117,7 @@ __global__ void __launch_bounds__(VT) k_pcg_xr(double *__restrict__ x, double *_
    }
    double bs = block_sum<VT>(acc, sm);
    __syncthreads();
-   grid_finish<VT>(bs, partials, ticket, FIN_IPROD, nullptr, scal, sm, &flag);
+   grid_finish<VT>(bs, partials, ticket, fin, fin_out, scal, sm, &flag);
 }
 
 // PCG: p = z + beta p
@@ -207,9 +208,9 @@ int vec_copy_dot(double *z, const double *r, int64_t n, int fin, double *out_d)
    HDK_LAUNCH_CHECK();
    return HDK_OK;
 }
-int pcg_update_xr(double *x, double *r, const double *p, const double *s, int64_t n, double *scal)
+int pcg_update_xr(double *x, double *r, const double *p, const double *s, int64_t n, double *scal, int fin, double *fin_out)
 {
-   k_pcg_xr<<<vec_grid(n), VT, 0, g.stream>>>(x, r, p, s, n, g.partials, g.counters, scal);
+   k_pcg_xr<<<vec_grid(n), VT, 0, g.stream>>>(x, r, p, s, n, g.partials, g.counters, scal, fin, fin_out);
    HDK_LAUNCH_CHECK();
    return HDK_OK;
 }

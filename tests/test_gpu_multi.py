@@ -25,7 +25,12 @@ def _run(world, args, env_extra=None):
     # replicated setup only (no work sharing between the ranks)
     ("lap7", ("12", "11", "6"), "40", "off"),
     # NCCL send/recv halo exchange instead of the peer-memory (CUDA IPC) path
-    ("lap7", ("12", "11", "6"), "40", "nccl")])
+    ("lap7", ("12", "11", "6"), "40", "nccl"),
+    # sliced-ELL kernel on every level: off-diagonal block fused into the SpMV kernel (in-kernel
+    # wait on the neighbours' flags), and the same layout with the separate correction kernel
+    ("lap7", ("16", "16", "10"), "40", "sell-fused"), ("lap27", ("8", "8", "6"), "30", "sell-fused"),
+    ("convdif", ("16", "8", "6"), "40", "sell-fused"), ("lap7", ("16", "16", "10"), "40", "sell-unfused"),
+    ("lap7", ("12", "11", "6"), "40", "sell-nccl")])
 def test_two_rank_solve_matches_oracle(gpu, kind, dims, rep, share):
     if gpu.device_count() < 2:
         pytest.skip("needs two GPUs")
@@ -34,6 +39,12 @@ def test_two_rank_solve_matches_oracle(gpu, kind, dims, rep, share):
         env["HDK_SETUP_SHARE"] = "0"
     elif share == "nccl":
         env["HDK_HALO_IPC"] = "0"
+    elif share.startswith("sell"):
+        env["HDK_SELL_MIN_ROWS"] = "0"
+        if share == "sell-unfused":
+            env["HDK_FUSE_OFFD"] = "0"
+        if share == "sell-nccl":
+            env["HDK_HALO_IPC"] = "0"
     else:
         env["HDK_SHARE_MIN_ROWS"] = share  # share the interpolation / RAP rows even on these tiny levels
     r = _run(2, [kind, *dims], env)
