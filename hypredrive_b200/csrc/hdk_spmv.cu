@@ -366,6 +366,9 @@ __global__ void __launch_bounds__(ST, 4) k_spmv_tma(SpmvDev a, int nblk, int cap
 // its stored order with separately rounded multiply and add.
 // ---------------------------------------------------------------------------------------
 constexpr int SELL_T = 256;
+#ifndef SELL_DOT_MINB
+#define SELL_DOT_MINB 6
+#endif
 constexpr int SELL_OFFD_BIT = 32; // sl_meta = len << 6 | offd flag << 5 | row offset in the slice
 
 template <int MODE>
@@ -380,7 +383,7 @@ __device__ __forceinline__ double row_epilogue(const SpmvDev &a, const RowOps &o
 }
 
 template <int MODE, bool DOT, bool OFFD>
-__global__ void __launch_bounds__(SELL_T) k_spmv_sell(SpmvDev a)
+__device__ __forceinline__ void sell_body(const SpmvDev &a)
 {
    constexpr bool SUB = (MODE == SPMV_RESIDUAL || MODE == SPMV_JACOBI || MODE == SPMV_JACOBI_R);
    __shared__ double red[SELL_T / 32];
@@ -480,6 +483,14 @@ __global__ void __launch_bounds__(SELL_T) k_spmv_sell(SpmvDev a)
    }
 }
 
+// Kernel entry points.  The kernel lives on memory-level parallelism, so occupancy matters: the
+// plain variant compiles to 32 registers (8 CTAs per SM) by itself; the fused-dot variant would
+// take 62, so it gets an explicit budget; the fused off-diagonal variants take 48-64.
+template <int MODE, bool DOT, bool OFFD>
+__global__ void __launch_bounds__(SELL_T) k_spmv_sell(SpmvDev a) { sell_body<MODE, DOT, OFFD>(a); }
+template <int MODE>
+__global__ void __launch_bounds__(SELL_T, SELL_DOT_MINB) k_spmv_sell_dot(SpmvDev a) { sell_body<MODE, true, false>(a); }
+
 // slice metadata: lanes ranked by decreasing row length (ties by row), slice width = longest row
 __global__ void k_sell_meta(const int *rowptr, int nrows, int nslice, int *meta, int *width, int *max_slice_nnz,
                             const int *offd_rowptr)
@@ -552,16 +563,19 @@ __global__ void k_sell_fill(const int *rowptr, const int *col, const double *val
 template <int MODE, bool DOT, bool OFFD>
 static int launch_sell_v(const DevCSR &A, const SpmvDev &d)
 {
+   constexpr bool DK = DOT && !OFFD; // the budgeted fused-dot entry point
    static int occ = 0;
    if (!occ)
    {
-      HDK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_spmv_sell<MODE, DOT, OFFD>, SELL_T, 0));
+      if (DK) HDK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_spmv_sell_dot<MODE>, SELL_T, 0));
+      else HDK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_spmv_sell<MODE, DOT, OFFD>, SELL_T, 0));
       if (occ < 1) occ = 1;
    }
    int grid = cdiv(A.nslice, SELL_T / 32);
    int cap  = g.sm_count * occ;
    if (grid > cap) grid = cap;
-   k_spmv_sell<MODE, DOT, OFFD><<<grid, SELL_T, 0, g.stream>>>(d);
+   if (DK) k_spmv_sell_dot<MODE><<<grid, SELL_T, 0, g.stream>>>(d);
+   else k_spmv_sell<MODE, DOT, OFFD><<<grid, SELL_T, 0, g.stream>>>(d);
    return HDK_OK;
 }
 template <int MODE, bool DOT>

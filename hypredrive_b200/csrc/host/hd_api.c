@@ -19,6 +19,8 @@ struct hypredrv_struct
    bool      lib_mode;
    hd_args  *args;
    hdk_csr  *A;
+   hdk_csr  *A_prec;  /* preconditioner reuse: the (older) matrix the live hierarchy was built on */
+   int       ls_index; /* 0-based index of the installed linear system (-1: none yet) */
    int64_t   row_start, row_end, n;
    double   *b_d, *x0_d, *x_d;
    double   *x_host, *b_host;
@@ -126,6 +128,7 @@ uint32_t HYPREDRV_Create(MPI_Comm comm, HYPREDRV_t *out)
    MPI_Comm_rank(comm, &h->rank);
    MPI_Comm_size(comm, &h->nprocs);
    h->stats     = hd_stats_create();
+   h->ls_index  = -1;
    h->row_end   = -1;
    int slot = -1;
    for (int i = 0; i < HD_MAX_LIVE; i++) if (!g_live[i]) { slot = i; break; }
@@ -135,10 +138,24 @@ uint32_t HYPREDRV_Create(MPI_Comm comm, HYPREDRV_t *out)
    return hd_err_get();
 }
 
-static void free_system(HYPREDRV_t h)
+static void drop_precon(HYPREDRV_t h)
 {
    if (h->precon) { hdk_amg_destroy(h->precon); h->precon = NULL; }
+   if (h->A_prec) { hdk_csr_destroy(h->A_prec); h->A_prec = NULL; }
    h->precon_is_setup = false;
+}
+
+/* static reuse policy (reference src/internal/precon_reuse.c:780-830): may the live hierarchy
+ * serve linear system `ls_id`? */
+static bool precon_reusable_for(HYPREDRV_t h, int ls_id)
+{
+   return h->precon && h->precon_is_setup && h->args && h->args->reuse.enabled &&
+          !hd_reuse_should_rebuild(&h->args->reuse, ls_id);
+}
+
+static void free_system(HYPREDRV_t h)
+{
+   drop_precon(h);
    if (h->A) { hdk_csr_destroy(h->A); h->A = NULL; }
    if (h->b_d) { hdk_vec_free(h->b_d); h->b_d = NULL; }
    if (h->x0_d) { hdk_vec_free(h->x0_d); h->x0_d = NULL; }
@@ -310,7 +327,7 @@ uint32_t HYPREDRV_InputArgsSetPreconPreset(HYPREDRV_t h, const char *preset)
    CHECK_OBJ(h);
    if (!preset) return fail(HYPREDRV_ERROR_INVALID_VAL, "%s", "Preconditioner preset name cannot be NULL");
    ensure_args(h);
-   if (h->precon) { hdk_amg_destroy(h->precon); h->precon = NULL; h->precon_is_setup = false; h->precon_created = false; }
+   drop_precon(h); h->precon_created = false;
    hd_args_apply_precon_preset(h->args, preset);
    return hd_err_get();
 }
@@ -348,9 +365,24 @@ static void build_timer_add(HYPREDRV_t h, double t0)
 
 static uint32_t install_matrix(HYPREDRV_t h, hdk_csr *A, int64_t rs, int64_t re)
 {
+   const int next = h->ls_index + 1;
+   if (precon_reusable_for(h, next) && h->row_start == rs && h->row_end == re)
+   {
+      /* keep the hierarchy (and the matrix its level 0 refers to) for the new system */
+      hdk_amg  *M = h->precon;
+      hdk_csr  *Ap = h->A_prec ? h->A_prec : h->A;
+      if (h->A_prec) hdk_csr_destroy(h->A);
+      h->A = NULL; h->precon = NULL; h->A_prec = NULL;
+      free_system(h);
+      h->precon = M; h->A_prec = Ap; h->precon_is_setup = true;
+      h->A = A; h->row_start = rs; h->row_end = re; h->n = re - rs + 1;
+      h->ls_index = next;
+      return hd_err_get();
+   }
    free_system(h);
    h->A = A; h->row_start = rs; h->row_end = re; h->n = re - rs + 1;
    h->precon_created = false; h->solver_created = false;
+   h->ls_index = next;
    return hd_err_get();
 }
 
@@ -708,7 +740,8 @@ uint32_t HYPREDRV_PreconCreate(HYPREDRV_t h)
     * is built by Setup */
    CHECK_ARGS(h);
    hd_err_reset();
-   if (h->precon) { hdk_amg_destroy(h->precon); h->precon = NULL; }
+   if (precon_reusable_for(h, h->ls_index)) { h->precon_created = true; return hd_err_get(); } /* reference HYPREDRV.c:2814-2833 */
+   drop_precon(h);
    h->precon_created = true; h->precon_is_setup = false;
    return hd_err_get();
 }
@@ -716,7 +749,8 @@ uint32_t HYPREDRV_PreconCreate(HYPREDRV_t h)
 static uint32_t do_precon_setup(HYPREDRV_t h)
 {
    if (!h->A) return fail(HYPREDRV_ERROR_INVALID_VAL, "%s", "the matrix must be set before the preconditioner setup");
-   if (h->precon) { hdk_amg_destroy(h->precon); h->precon = NULL; }
+   if (precon_reusable_for(h, h->ls_index)) { h->setup_time = 0.0; return hd_err_get(); } /* reuse: no rebuild for this system */
+   drop_precon(h);
    hdk_sync();
    double t0 = hd_wtime();
    if (h->args->precon_method == HD_PRECON_AMG)
@@ -764,7 +798,11 @@ uint32_t HYPREDRV_LinearSolverCreate(HYPREDRV_t h)
    /* reference src/HYPREDRV.c:2897-2932: creates the preconditioner too when none exists */
    CHECK_ARGS(h);
    hd_err_reset();
-   if (!h->precon_created) { h->precon_created = true; h->precon_is_setup = false; }
+   if (!h->precon_created)
+   {
+      h->precon_created = true;
+      if (!precon_reusable_for(h, h->ls_index)) drop_precon(h); /* else: kept from an earlier system (reuse) */
+   }
    h->solver_created = true;
    return hd_err_get();
 }
@@ -858,8 +896,9 @@ uint32_t HYPREDRV_PreconApply(HYPREDRV_t h, HYPRE_Vector vec_b, HYPRE_Vector vec
 uint32_t HYPREDRV_PreconDestroy(HYPREDRV_t h)
 {
    CHECK_OBJ(h);
-   if (h->precon) { hdk_amg_destroy(h->precon); h->precon = NULL; }
-   h->precon_created = false; h->precon_is_setup = false;
+   h->precon_created = false;
+   if (precon_reusable_for(h, h->ls_index + 1)) return hd_err_get(); /* the next system reuses it */
+   drop_precon(h);
    return hd_err_get();
 }
 

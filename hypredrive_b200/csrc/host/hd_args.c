@@ -360,6 +360,111 @@ static int parse_solver_node(hd_args *a, hd_node *n)
    return 0;
 }
 
+/* preconditioner.reuse: `reuse: <frequency>` | `reuse: yes/no` | block {enabled, policy, frequency,
+ * linear_system_ids (alias linear_solver_ids), per_timestep}.  Only the static policy exists
+ * here; `adaptive` and `per_timestep: yes` are rejected (reference precon_reuse.c:2290-2400). */
+static int parse_bool_word(const char *v, int *out)
+{
+   if (!strcmp(v, "yes") || !strcmp(v, "on") || !strcmp(v, "true") || !strcmp(v, "1")) { *out = 1; return 0; }
+   if (!strcmp(v, "no") || !strcmp(v, "off") || !strcmp(v, "false") || !strcmp(v, "0")) { *out = 0; return 0; }
+   return 1;
+}
+
+static int parse_reuse_node(hd_args *a, hd_node *n)
+{
+   hd_reuse_args *r = &a->reuse;
+   n->used = 1;
+   if (!n->child)
+   {
+      char *end = NULL;
+      long  f = strtol(n->val, &end, 10);
+      int   b;
+      if (n->val[0] && end && !*end && f >= 0) { r->enabled = 1; r->frequency = (int)f; return 0; }
+      if (!parse_bool_word(n->val, &b)) { r->enabled = b; return 0; }
+      hd_err_set(HYPREDRV_ERROR_INVALID_VAL);
+      hd_err_msg("preconditioner.reuse: '%s' is not supported (static reuse only: a frequency, yes/no or a block)", n->val);
+      n->invalid = 2;
+      return 1;
+   }
+   int seen_freq = 0, seen_ids = 0;
+   for (hd_node *c = n->child; c; c = c->next)
+   {
+      c->used = 1;
+      if (!strcmp(c->key, "enabled"))
+      {
+         if (parse_bool_word(c->val, &r->enabled)) { hd_err_set(HYPREDRV_ERROR_INVALID_VAL); hd_err_msg("Invalid value for preconditioner.reuse.enabled: '%s'", c->val); c->invalid = 2; return 1; }
+      }
+      else if (!strcmp(c->key, "frequency"))
+      {
+         char *end = NULL;
+         long  f = strtol(c->val, &end, 10);
+         if (!c->val[0] || !end || *end || f < 0) { hd_err_set(HYPREDRV_ERROR_INVALID_VAL); hd_err_msg("Invalid value for preconditioner.reuse.frequency: '%s'", c->val); c->invalid = 2; return 1; }
+         r->frequency = (int)f; seen_freq = 1;
+      }
+      else if (!strcmp(c->key, "linear_system_ids") || !strcmp(c->key, "linear_solver_ids"))
+      {
+         /* flow list "[0, 5, 10]" or a block sequence of "- id" items */
+         r->n_ids = 0;
+         const char *p = c->val;
+         for (hd_node *it = c->child; it; it = it->next)
+         {
+            it->used = 1;
+            if (r->n_ids < HD_REUSE_MAX_IDS) r->ids[r->n_ids++] = atoi(it->val[0] ? it->val : it->key);
+         }
+         while (*p)
+         {
+            while (*p && (*p < '0' || *p > '9') && *p != '-') p++;
+            if (!*p) break;
+            char *end = NULL;
+            long  v = strtol(p, &end, 10);
+            if (end == p) break;
+            if (v < 0 || r->n_ids >= HD_REUSE_MAX_IDS) { hd_err_set(HYPREDRV_ERROR_INVALID_VAL); hd_err_msg("Failed to parse preconditioner.reuse.linear_system_ids"); c->invalid = 2; return 1; }
+            r->ids[r->n_ids++] = (int)v;
+            p = end;
+         }
+         if (r->n_ids == 0) { hd_err_set(HYPREDRV_ERROR_INVALID_VAL); hd_err_msg("Failed to parse preconditioner.reuse.linear_system_ids"); c->invalid = 2; return 1; }
+         seen_ids = 1;
+      }
+      else if (!strcmp(c->key, "policy"))
+      {
+         if (strcmp(c->val, "static")) { hd_err_set(HYPREDRV_ERROR_INVALID_VAL); hd_err_msg("preconditioner.reuse.policy '%s' is not supported (static only)", c->val); c->invalid = 2; return 1; }
+      }
+      else if (!strcmp(c->key, "per_timestep"))
+      {
+         int b = 0;
+         if (parse_bool_word(c->val, &b) || b) { hd_err_set(HYPREDRV_ERROR_INVALID_VAL); hd_err_msg("preconditioner.reuse.per_timestep is not supported"); c->invalid = 2; return 1; }
+      }
+      else
+      {
+         hd_err_set(HYPREDRV_ERROR_INVALID_KEY);
+         hd_err_msg("unknown key 'preconditioner.reuse.%s'", c->key);
+         c->invalid = 1;
+         return 1;
+      }
+   }
+   if (seen_freq && seen_ids)
+   {
+      hd_err_set(HYPREDRV_ERROR_INVALID_VAL);
+      hd_err_msg("preconditioner.reuse: do not combine linear_system_ids with frequency");
+      return 1;
+   }
+   return 0;
+}
+
+int hd_reuse_should_rebuild(const hd_reuse_args *r, int ls_id)
+{
+   /* reference precon_reuse.c:780-830 */
+   if (ls_id < 0) ls_id = 0;
+   if (!r || !r->enabled) return 1;
+   if (r->n_ids > 0)
+   {
+      for (int i = 0; i < r->n_ids; i++) if (r->ids[i] == ls_id) return 1;
+      return 0;
+   }
+   int freq = r->frequency < 0 ? 0 : r->frequency;
+   return (ls_id % (freq + 1)) == 0;
+}
+
 static int parse_precon_node(hd_args *a, hd_node *n)
 {
    n->used = 1;
@@ -372,7 +477,7 @@ static int parse_precon_node(hd_args *a, hd_node *n)
    hd_node *method = NULL;
    for (hd_node *c = n->child; c; c = c->next)
    {
-      if (!strcmp(c->key, "reuse")) { c->used = 1; continue; } /* always rebuild (out of scope) */
+      if (!strcmp(c->key, "reuse")) { if (parse_reuse_node(a, c)) return 1; continue; }
       if (!strcmp(c->key, "preset")) { c->used = 1; if (hd_args_apply_precon_preset(a, c->val)) { c->invalid = 2; return 1; } method = c; continue; }
       if (method) { hd_err_set(HYPREDRV_ERROR_EXTRA_KEY); hd_err_msg("preconditioner section must name exactly one method"); c->invalid = 1; return 1; }
       method = c;

@@ -95,6 +95,15 @@ typedef struct
    int    smooth_type, smooth_num_levels, smooth_num_sweeps;
 } hd_amg_args;
 
+/* preconditioner.reuse, static policy (reference src/internal/precon_reuse.c:780-830,
+ * docs/usrman-src/input_structure.rst "Static reuse") */
+#define HD_REUSE_MAX_IDS 256
+typedef struct
+{
+   int enabled, frequency, n_ids;
+   int ids[HD_REUSE_MAX_IDS];
+} hd_reuse_args;
+
 typedef struct
 {
    hd_general_args general;
@@ -104,6 +113,7 @@ typedef struct
    hd_gmres_args   gmres;
    hd_precon_t     precon_method;
    hd_amg_args     amg;
+   hd_reuse_args   reuse;
    int             num_precon_variants, active_precon_variant;
    bool            lib_mode;
 } hd_args;
@@ -119,6 +129,8 @@ int  hd_args_apply_precon_preset(hd_args *a, const char *preset);
 int  hd_args_apply_solver_preset(hd_args *a, const char *preset);
 int  hd_preset_register(int kind, const char *name, const char *text, const char *help);
 void hd_amg_to_hdk(const hd_amg_args *a, hdk_amg_params *p);
+/* 1 if the preconditioner must be rebuilt for the 0-based linear system `ls_id` */
+int  hd_reuse_should_rebuild(const hd_reuse_args *r, int ls_id);
 
 /* ---------------------------------------------------------------- statistics (hd_stats.c) */
 #define HD_STATS_MAX 4096

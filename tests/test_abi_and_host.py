@@ -64,6 +64,10 @@ def test_yaml_forms_accepted():
         "solver:\n    gmres:\n        krylov_dim: 20\npreconditioner: jacobi\n",  # 4-space base indent
         "solver: pcg\npreconditioner:\n  amg: { print_level: 0, coarsening: { type: pmis, max_levels: 10 } }\n",
         "solver: pcg\npreconditioner:\n  amg:\n    - print_level: 0\n      coarsening:\n        type: pmis\n",
+        # static preconditioner reuse (docs/usrman-src/input_structure.rst "Static reuse")
+        "solver: pcg\npreconditioner:\n  amg:\n    print_level: 0\n  reuse:\n    enabled: yes\n    frequency: 2\n",
+        "solver: pcg\npreconditioner:\n  amg:\n    print_level: 0\n  reuse:\n    enabled: yes\n    linear_system_ids: [0, 10, 20]\n",
+        "solver: pcg\npreconditioner:\n  amg:\n    print_level: 0\n  reuse: 3\n",
     ]
     for text in good:
         assert _parse(h, text) == 0, text
@@ -86,6 +90,9 @@ def test_yaml_errors_set_the_reference_error_bits():
         ("solver:\n  pcg:\n   max_iter: 5\npreconditioner: amg\n", 0x4),          # inconsistent indent
         ("solver:\n      pcg:\n        max_iter: 5\n  x: 1\npreconditioner: amg\n", 0x4 | 0x80 | INVALID_KEY),
         ("solver pcg\npreconditioner: amg\n", 0x8),                               # missing divisor
+        ("solver: pcg\npreconditioner:\n  amg:\n    print_level: 0\n  reuse: adaptive\n", INVALID_VAL),      # static only
+        ("solver: pcg\npreconditioner:\n  amg:\n    print_level: 0\n  reuse:\n    frequency: -1\n", INVALID_VAL),
+        ("solver: pcg\npreconditioner:\n  amg:\n    print_level: 0\n  reuse:\n    enabled: yes\n    cadence: 2\n", INVALID_KEY),
     ]
     for text, bits in cases:
         code = _parse(h, text)

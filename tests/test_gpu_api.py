@@ -86,6 +86,39 @@ def test_known_answers_and_matrix_replacement(gpu):
         assert abs(drv.solution_norm("l2") - 2.0) < 1e-6
 
 
+def test_static_preconditioner_reuse(gpu):
+    """preconditioner.reuse (static policy): rebuild when ls_index % (frequency + 1) == 0, otherwise
+    keep the hierarchy of the earlier matrix (reference src/internal/precon_reuse.c:780-830)."""
+    A, b = O.gen("lap7", 12, 10, 8)
+    opts = {"general": {"statistics": False}, "solver": {"pcg": {"relative_tol": 1e-8, "max_iter": 100}},
+            "preconditioner": {"amg": {"print_level": 0}, "reuse": {"enabled": True, "frequency": 1}}}
+    setups, iters = [], []
+    with hd.HypreDrive(options=opts) as drv:
+        for k in range(4):
+            Ak = (A + 0.05 * k * sp.eye(A.shape[0])).tocsr()        # a slowly changing operator
+            drv.set_matrix_from_csr(Ak)
+            drv.set_rhs(b)
+            drv.solve()
+            assert drv.last_converged
+            x = drv.get_solution()
+            assert np.linalg.norm(b - Ak @ x) <= 1e-8 * np.linalg.norm(b) * 1.0001
+            setups.append(drv.last_setup_time)
+            iters.append(drv.last_iterations)
+    assert setups[0] > 0 and setups[2] > 0            # systems 0 and 2: rebuilt
+    assert setups[1] == 0 and setups[3] == 0          # systems 1 and 3: reused
+    # explicit rebuild list
+    opts["preconditioner"]["reuse"] = {"enabled": True, "linear_system_ids": [0, 3]}
+    setups = []
+    with hd.HypreDrive(options=opts) as drv:
+        for k in range(4):
+            drv.set_matrix_from_csr(A)
+            drv.set_rhs(b)
+            drv.solve()
+            assert drv.last_converged
+            setups.append(drv.last_setup_time)
+    assert [s > 0 for s in setups] == [True, False, False, True]
+
+
 def test_unsorted_columns_and_diag_swap(gpu):
     # rows given with the diagonal last (27-pt generator style): assembly swaps it to the front
     A, b = O.gen("lap27", 8, 7, 6, c=(1.0, 1.0, 0.01), diag_first=False)
