@@ -196,6 +196,42 @@ def test_vcycle_and_pcg_parity(gpu, kind, dims, c):
     assert np.linalg.norm(b - A @ x) / np.linalg.norm(b) < (1e-8 if kind == "convdif" else 1e-6) * 1.0001
 
 
+def test_cuda_path_against_committed_fixtures(gpu):
+    """The CUDA path against tests/golden/hierarchy_fixtures.json without running the oracle:
+    C/F splitting, P and coarse-operator patterns AND values bit for bit (SHA-256), iteration
+    counts equal, leading solution entries to 1e-8."""
+    import hashlib, json, os
+
+    def digest(*arrays):
+        h = hashlib.sha256()
+        for a in arrays:
+            h.update(np.ascontiguousarray(a).tobytes())
+        return h.hexdigest()
+
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "hierarchy_fixtures.json")
+    for fx in json.load(open(path)):
+        A, b = O.gen(fx["kind"], *fx["dims"], c=tuple(fx["c"]))   # input generator only
+        dA = gpu.DCsr.from_scipy(A)
+        M = gpu.DAmg(dA)
+        assert [s[0] for s in M.sizes()] == [e["rows"] for e in fx["levels"]]
+        assert np.array_equal(M.cf(0), np.array(fx["cf_level0"], dtype=np.int32))
+        for l, e in enumerate(fx["levels"]):
+            rp, cj, va = M.matrix(l, "A")
+            assert digest(rp.astype(np.int32), cj.astype(np.int32)) == e["A_pattern"], f"A pattern level {l}"
+            assert digest(va.astype(np.float64)) == e["A_values"], f"A values level {l}"
+            if "nnz_P" in e:
+                rp, cj, va = M.matrix(l, "P")
+                assert digest(rp.astype(np.int32), cj.astype(np.int32)) == e["P_pattern"], f"P pattern level {l}"
+                assert digest(va.astype(np.float64)) == e["P_values"], f"P values level {l}"
+                assert digest(M.cf(l).astype(np.int32)) == e["cf"], f"C/F splitting level {l}"
+        n = A.shape[0]
+        db, dx = gpu.DVec(n, b), gpu.DVec(n)
+        fn = gpu.pcg if fx["solver"] == "pcg" else gpu.gmres
+        info = fn(dA, db, dx, M, rel_tol=fx["rel_tol"], max_iter=100)
+        assert info["converged"] and info["iters"] == fx["iterations"]
+        assert np.allclose(dx.get()[:8], fx["x_head"], rtol=1e-8, atol=0)
+
+
 @pytest.mark.parametrize("sort", [0, 1])
 def test_sliced_ell_levels_parity(gpu, sort):
     """Every operator of the hierarchy (A, P, R on all levels) on the sliced-ELL kernel: the

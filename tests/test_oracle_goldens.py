@@ -4,7 +4,61 @@ import numpy as np
 import scipy.sparse as sp
 import scipy.sparse.linalg as spla
 
+import hashlib
+import json
+import os
+
 from oracle import oracle as O
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def _digest(*arrays):
+    h = hashlib.sha256()
+    for a in arrays:
+        h.update(np.ascontiguousarray(a).tobytes())
+    return h.hexdigest()
+
+
+def test_reference_outputs_fixture():
+    """tests/golden/reference_outputs.json: the values the reference tree pins (file:line inside)."""
+    ref = json.load(open(os.path.join(GOLDEN, "reference_outputs.json")))
+    A, _ = O.gen("lap7", 10, 10, 10)
+    assert A.shape[0] == ref["ex1"]["rows"] and A.nnz == ref["ex1"]["nnz"]
+    H = O.Hierarchy(A, O.default_params(False))
+    for key, b in (("ex1", np.ones(1000)), ("laplacian", O.gen("lap7", 10, 10, 10)[1])):
+        x, info = O.pcg(A, b, M=H, rel_tol=1e-6, max_iter=100)
+        assert f"{np.linalg.norm(b):.2e}" == ref[key]["r0"]
+        assert info["iters"] == ref[key]["iterations"]
+        assert f"{np.linalg.norm(b - A @ x) / np.linalg.norm(b):.2e}" == ref[key]["rel_res"]
+    for s_ in ref["known_answers"]["systems"]:
+        D = sp.diags(s_["diag"]).tocsr()
+        x, info = O.pcg(D, np.array(s_["rhs"]), M=O.Hierarchy(D, O.default_params(True)), rel_tol=1e-8)
+        assert info["converged"] and np.allclose(x, s_["x"], atol=1e-6)
+
+
+def test_oracle_reproduces_committed_hierarchy_fixtures():
+    """tests/golden/hierarchy_fixtures.json (made by tests/golden/make_goldens.py): guards the oracle
+    against drift -- C/F splitting, P and coarse-operator patterns and values, iteration counts."""
+    for fx in json.load(open(os.path.join(GOLDEN, "hierarchy_fixtures.json"))):
+        A, b = O.gen(fx["kind"], *fx["dims"], c=tuple(fx["c"]))
+        H = O.Hierarchy(A, O.default_params(True))
+        assert H.nlev == len(fx["levels"])
+        assert np.array_equal(H.cf(0), np.array(fx["cf_level0"]))
+        for l, e in enumerate(fx["levels"]):
+            Al = H.A(l)
+            assert Al.shape[0] == e["rows"] and Al.nnz == e["nnz_A"]
+            assert _digest(Al.indptr.astype(np.int32), Al.indices.astype(np.int32)) == e["A_pattern"]
+            assert _digest(Al.data.astype(np.float64)) == e["A_values"]
+            if "nnz_P" in e:
+                P = H.P(l)
+                assert _digest(P.indptr.astype(np.int32), P.indices.astype(np.int32)) == e["P_pattern"]
+                assert _digest(P.data.astype(np.float64)) == e["P_values"]
+                assert _digest(H.cf(l).astype(np.int32)) == e["cf"]
+        fn = O.pcg if fx["solver"] == "pcg" else O.gmres
+        x, info = fn(A, b, M=H, rel_tol=fx["rel_tol"], max_iter=100)
+        assert info["iters"] == fx["iterations"]
+        assert np.allclose(x[:8], fx["x_head"], rtol=1e-12, atol=0)
 
 
 def test_park_miller_stream_known_answer():
