@@ -32,6 +32,7 @@ struct hdk_amg_s
    double                     op_complexity = 0.0;
    double                     vcycle_bytes = 0.0;
    bool                       keep_debug = true; // keep S / measure for introspection
+   bool                       prefilled_l0 = false; // next zero-guess cycle: level-0 first sweep already done by the caller
    bool                       keep_f2c = false;
    // N > 1: levels [0, nlev) are row-distributed; from level `tail_level` on, the hierarchy is
    // replicated on every rank (`tail`, a serial hierarchy of the GLOBAL problem) and the
@@ -49,4 +50,5 @@ int amg_precond(hdk_amg_s *M, const double *r, double *z, int fin, double *fin_o
 // V-cycle over levels [l0, nlev) of M; level l0 uses the caller's vectors
 int amg_cycle(hdk_amg_s *M, const double *f, double *u, bool zero_guess, int fin, double *fin_out, int l0 = 0);
 int exclusive_scan_int(const int *in, int *out, int n);
+bool amg_prefill_target(hdk_amg_s *M, double *z, double **buf, const double **d, double *w);
 } // namespace hdk

@@ -144,6 +144,11 @@ int amg_cycle(hdk_amg_s *M, const double *f0, double *u0, bool zero_guess, int f
    }
    for (int l = l0 + 1; l < nl; l++) { cur[(size_t)l] = M->lev[(size_t)l].u; alt[(size_t)l] = M->lev[(size_t)l].t; rhs[(size_t)l] = M->lev[(size_t)l].f; }
 
+   // the first pre-smoothing sweep of a level entered with a zero guess is u = (w f)/d: it is
+   // produced by the kernel that produces f (the restriction of the level above, or the PCG
+   // residual update for level l0), so it costs no pass of its own
+   bool prefilled = (M->prefilled_l0 && zero_guess && l0 == 0);
+   M->prefilled_l0 = false;
    for (int l = l0; l < nfine; l++)
    {
       AmgLevel &L = M->lev[(size_t)l];
@@ -152,7 +157,7 @@ int amg_cycle(hdk_amg_s *M, const double *f0, double *u0, bool zero_guess, int f
       {
          if (s == 0 && zg && is_jacobi(p.relax_down))
          {
-            HDK_TRY(vec_scaled_div(cur[(size_t)l], rhs[(size_t)l], L.l1_down, p.relax_weight, L.n));
+            if (!prefilled) HDK_TRY(vec_scaled_div(cur[(size_t)l], rhs[(size_t)l], L.l1_down, p.relax_weight, L.n));
          }
          else
          {
@@ -175,6 +180,7 @@ int amg_cycle(hdk_amg_s *M, const double *f0, double *u0, bool zero_guess, int f
       }
       SpmvArgs rr;
       rr.x = alt[(size_t)l];
+      prefilled = false;
       if (l + 1 < nl) rr.y = M->lev[(size_t)l + 1].f;
       else
       {
@@ -182,7 +188,14 @@ int amg_cycle(hdk_amg_s *M, const double *f0, double *u0, bool zero_guess, int f
          HDK_TRY(vec_fill(M->full_f, 0.0, M->tail_n));
          rr.y = M->full_f + M->tail_off;
       }
-      HDK_TRY(parcsr_matvec(*L.R, SPMV_SET, rr));
+      if (l + 1 < nfine && p.sweeps_down > 0 && is_jacobi(p.relax_down))
+      {
+         // f_{l+1} = R r  and  u_{l+1} = (w f_{l+1})/d_{l+1}  in one kernel
+         rr.y2 = cur[(size_t)l + 1]; rr.d = M->lev[(size_t)l + 1].l1_down; rr.w = p.relax_weight;
+         HDK_TRY(parcsr_matvec(*L.R, SPMV_SET_DIV, rr));
+         prefilled = true;
+      }
+      else HDK_TRY(parcsr_matvec(*L.R, SPMV_SET, rr));
    }
    // coarsest stage
    const double *coarse_sol = nullptr; // solution feeding the prolongation of level nfine-1
@@ -221,6 +234,21 @@ int amg_cycle(hdk_amg_s *M, const double *f0, double *u0, bool zero_guess, int f
    if (cur[(size_t)l0] != u0) HDK_TRY(vec_copy(u0, cur[(size_t)l0], M->lev[(size_t)l0].n));
    if (fin != FIN_NONE && !fin_done) HDK_TRY(vec_dot_dev(f0, u0, M->lev[(size_t)l0].n, fin, fin_out));
    return HDK_OK;
+}
+
+// For a caller that can produce u0 = (w r)/d itself (PCG's fused x/r update): the buffer the
+// V-cycle expects it in, the diagonal and the weight.  false: the cycle does not start that way.
+bool amg_prefill_target(hdk_amg_s *M, double *z, double **buf, const double **d, double *w)
+{
+   const hdk_amg_params &p = M->prm;
+   const bool has_tail = (M->tail != nullptr);
+   const int  nl = M->nlev, nfine = has_tail ? nl : nl - 1;
+   if (nl == 0 || nfine <= 0 || p.sweeps_down <= 0 || !is_jacobi(p.relax_down)) return false;
+   const int  oop = (p.sweeps_down - 1) + p.sweeps_up;
+   *buf = (oop % 2 == 0) ? z : M->lev[0].t;
+   *d   = M->lev[0].l1_down;
+   *w   = p.relax_weight;
+   return true;
 }
 
 int amg_precond(hdk_amg_s *M, const double *r, double *z, int fin, double *fin_out)

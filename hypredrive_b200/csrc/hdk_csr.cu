@@ -247,7 +247,16 @@ int parcsr_matvec(const hdk_csr_s &A, int mode, SpmvArgs a)
    // p2p exchange partners must match: a rank takes part when it sends OR receives
    bool exch = g.nranks > 1 && (A.halo.n_send > 0 || A.halo.n_halo > 0);
    if (!exch) return spmv_launch(A.diag, mode, a);
-   if (A.halo.ipc.on && A.diag.kind == 2 && A.diag.sl_offd_flags && A.offd.nnz > 0 && fuse_offd_enabled(A.diag.nrows))
+   const bool fused_offd = A.halo.ipc.on && A.diag.kind == 2 && A.diag.sl_offd_flags && A.offd.nnz > 0 && fuse_offd_enabled(A.diag.nrows);
+   if (mode == SPMV_SET_DIV && !fused_offd && A.offd.nnz > 0)
+   {
+      // the second output needs the final y: plain product first, then the scaled division
+      SpmvArgs a1 = a;
+      a1.y2 = nullptr;
+      HDK_TRY(parcsr_matvec(A, SPMV_SET, a1));
+      return vec_scaled_div(a.y2, a.y, a.d, a.w, A.diag.nrows);
+   }
+   if (fused_offd)
    {
       // peer-memory halo + sliced-ELL: ONE kernel does the diag block, waits in-kernel for the
       // neighbours' values where a row needs them, adds the off-diagonal entries and runs the

@@ -122,7 +122,8 @@ enum SpmvMode
    SPMV_JACOBI = 2,   // y = x + w*(b - A x)/d
    SPMV_ADD = 3,      // y = y + A x        (s = y; s += a*x in CSR order)
    SPMV_AXPBY = 4,    // y = alpha*(A x) + beta*y
-   SPMV_JACOBI_R = 5  // y = w*(b - A x)/d  (two-stage GS first stage)
+   SPMV_JACOBI_R = 5, // y = w*(b - A x)/d  (two-stage GS first stage)
+   SPMV_SET_DIV = 6   // y = A x ; y2 = w*y/d  (restriction fused with the next level's first l1-Jacobi sweep)
 };
 
 // what the last block does with a fused dot product
@@ -149,6 +150,7 @@ struct SpmvArgs
    const double *b = nullptr;   // rhs (RESIDUAL / JACOBI)
    const double *d = nullptr;   // diagonal scaling (JACOBI)
    const double *xo = nullptr;  // halo part of x (offd block), appended columns
+   double       *y2 = nullptr;  // second output of SPMV_SET_DIV
    double        w = 1.0, alpha = 1.0, beta = 0.0;
    // fused dot: sum_i dotv[i]*y_new[i]  (dotv may alias x or b)
    const double *dotv = nullptr;
@@ -166,7 +168,8 @@ int vec_dot_dev(const double *x, const double *y, int64_t n, int fin, double *ou
 int vec_dot_host(const double *x, const double *y, int64_t n, double *out_h);         // + allreduce
 int vec_scaled_div(double *u, const double *f, const double *d, double w, int64_t n); // u = w f / d
 int pcg_update_xr(double *x, double *r, const double *p, const double *s, int64_t n, double *scal,
-                  int fin = FIN_IPROD, double *fin_out = nullptr); // <r,r> -> fin (FIN_STORE at N > 1)
+                  int fin = FIN_IPROD, double *fin_out = nullptr, // <r,r> -> fin (FIN_STORE at N > 1)
+                  double *z0 = nullptr, const double *zd = nullptr, double zw = 1.0); // optional z0 = (zw r)/zd
 int pcg_update_p(double *p, const double *z, int64_t n, const double *scal);
 int vec_copy_dot(double *z, const double *r, int64_t n, int fin, double *out_d);      // z=r, <r,r>
 int allreduce_dev(double *buf_d, int count);                                          // NCCL sum (no-op on 1 rank)

@@ -120,7 +120,15 @@ int hdk_pcg(const hdk_csr *A, hdk_amg *M, const double *b, double *x, hdk_krylov
       if ((rc = parcsr_matvec(*A, SPMV_SET, a))) goto done;
       if ((rc = finish_dot(FIN_SDOTP, nullptr))) goto done;
       // x += alpha p ; r -= alpha s ; i_prod = <r,r>       (one kernel)
-      if ((rc = pcg_update_xr(x, r, p, s, n, S, local_fin(FIN_IPROD), local_out(nullptr)))) goto done;
+      //   + the first smoothing sweep of the coming V-cycle, z0 = (w r)/l1, written where the cycle expects it
+      {
+         double       *zb = nullptr;
+         const double *zd = nullptr;
+         double        zw = 1.0;
+         const bool    pf = M && amg_prefill_target(M, s, &zb, &zd, &zw);
+         if ((rc = pcg_update_xr(x, r, p, s, n, S, local_fin(FIN_IPROD), local_out(nullptr), pf ? zb : nullptr, zd, zw))) goto done;
+         if (pf) M->prefilled_l0 = true;
+      }
       if ((rc = finish_dot(FIN_IPROD, nullptr))) goto done;
       if ((rc = read_scalars(8))) goto done;
       // s = M^{-1} r ; gamma_new = <r,s> ; beta = gamma_new / gamma  (V-cycle; the host

@@ -71,7 +71,7 @@ struct SpmvDev
    const int    *rowptr, *col, *blk_row;
    const double *val;
    const double *x, *b, *d, *dotv;
-   double       *y;
+   double       *y, *y2;
    double        w, alpha, beta;
    int           nrows, fin;
    double       *fin_out, *scal, *partials;
@@ -113,6 +113,14 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
                 "}" ::"r"(bar), "r"(parity) : "memory");
 }
 
+// second output of SPMV_SET_DIV: the zero-guess l1-Jacobi sweep of the next level, u = (w*f)/d
+// (same expression as k_scaled_div)
+template <int MODE>
+__device__ __forceinline__ void store_y2(const SpmvDev &a, int r, double yn, double dd)
+{
+   if (MODE == SPMV_SET_DIV) a.y2[r] = (dd != 0.0) ? __ddiv_rn(__dmul_rn(a.w, yn), dd) : 0.0;
+}
+
 struct BlkMeta { int r0, r1, k0, k1; };
 __device__ __forceinline__ BlkMeta blk_meta(const SpmvDev &a, int b)
 {
@@ -137,7 +145,7 @@ __device__ __forceinline__ void row_load(const SpmvDev &a, int r, int ka, RowOps
    o.s = __ldg(a.rowptr + r) - ka;
    o.e = __ldg(a.rowptr + r + 1) - ka;
    if (MODE == SPMV_RESIDUAL || MODE == SPMV_JACOBI || MODE == SPMV_JACOBI_R) o.b = a.b[r];
-   if (MODE == SPMV_JACOBI || MODE == SPMV_JACOBI_R) o.d = a.d[r];
+   if (MODE == SPMV_JACOBI || MODE == SPMV_JACOBI_R || MODE == SPMV_SET_DIV) o.d = a.d[r];
    if (MODE == SPMV_JACOBI) o.xo = a.x[r];
    if (MODE == SPMV_ADD || MODE == SPMV_AXPBY) o.yo = a.y[r];
    if (DOT) o.dv = a.dotv[r];
@@ -170,7 +178,7 @@ __device__ __forceinline__ double row_compute(const SpmvDev &a, const RowOps &o,
       if (k + 1 < o.e) { double p1 = __dmul_rn(vs[k + 1], x1); acc = __dadd_rn(acc, SUB ? -p1 : p1); }
       if (k + 2 < o.e) { double p2 = __dmul_rn(vs[k + 2], x2); acc = __dadd_rn(acc, SUB ? -p2 : p2); }
    }
-   if (MODE == SPMV_SET || MODE == SPMV_ADD || MODE == SPMV_RESIDUAL) return acc;
+   if (MODE == SPMV_SET || MODE == SPMV_SET_DIV || MODE == SPMV_ADD || MODE == SPMV_RESIDUAL) return acc;
    if (MODE == SPMV_AXPBY)
       return (a.beta == 0.0) ? __dmul_rn(a.alpha, acc) : __dadd_rn(__dmul_rn(a.alpha, acc), __dmul_rn(a.beta, o.yo));
    if (MODE == SPMV_JACOBI)
@@ -202,7 +210,7 @@ __device__ __forceinline__ double row_partial(const SpmvDev &a, int k, int e, co
 template <int MODE>
 __device__ __forceinline__ double row_finish(const SpmvDev &a, const RowOps &o, double total)
 {
-   if (MODE == SPMV_SET) return total;
+   if (MODE == SPMV_SET || MODE == SPMV_SET_DIV) return total;
    if (MODE == SPMV_ADD) return __dadd_rn(o.yo, total);
    if (MODE == SPMV_AXPBY)
       return (a.beta == 0.0) ? __dmul_rn(a.alpha, total) : __dadd_rn(__dmul_rn(a.alpha, total), __dmul_rn(a.beta, o.yo));
@@ -296,6 +304,7 @@ __global__ void __launch_bounds__(ST, 4) k_spmv_tma(SpmvDev a, int nblk, int cap
             {
                double yn = row_compute<MODE>(a, ro[j], vs, cs);
                a.y[r]    = yn;
+               store_y2<MODE>(a, r, yn, ro[j].d);
                if (DOT) dacc += ro[j].dv * yn;
             }
          }
@@ -305,6 +314,7 @@ __global__ void __launch_bounds__(ST, 4) k_spmv_tma(SpmvDev a, int nblk, int cap
             row_load<MODE, DOT>(a, r, ka, o);
             double yn = row_compute<MODE>(a, o, vs, cs);
             a.y[r]    = yn;
+            store_y2<MODE>(a, r, yn, o.d);
             if (DOT) dacc += o.dv * yn;
          }
       }
@@ -323,6 +333,7 @@ __global__ void __launch_bounds__(ST, 4) k_spmv_tma(SpmvDev a, int nblk, int cap
             {
                double yn = row_finish<MODE>(a, ro[j], part);
                a.y[r]    = yn;
+               store_y2<MODE>(a, r, yn, ro[j].d);
                if (DOT) dacc += ro[j].dv * yn;
             }
          }
@@ -340,6 +351,7 @@ __global__ void __launch_bounds__(ST, 4) k_spmv_tma(SpmvDev a, int nblk, int cap
             {
                double yn = row_finish<MODE>(a, o, part);
                a.y[r]    = yn;
+               store_y2<MODE>(a, r, yn, o.d);
                if (DOT) dacc += o.dv * yn;
             }
          }
@@ -366,15 +378,12 @@ __global__ void __launch_bounds__(ST, 4) k_spmv_tma(SpmvDev a, int nblk, int cap
 // its stored order with separately rounded multiply and add.
 // ---------------------------------------------------------------------------------------
 constexpr int SELL_T = 256;
-#ifndef SELL_DOT_MINB
-#define SELL_DOT_MINB 6
-#endif
 constexpr int SELL_OFFD_BIT = 32; // sl_meta = len << 6 | offd flag << 5 | row offset in the slice
 
 template <int MODE>
 __device__ __forceinline__ double row_epilogue(const SpmvDev &a, const RowOps &o, double acc)
 {
-   if (MODE == SPMV_SET || MODE == SPMV_ADD || MODE == SPMV_RESIDUAL) return acc;
+   if (MODE == SPMV_SET || MODE == SPMV_SET_DIV || MODE == SPMV_ADD || MODE == SPMV_RESIDUAL) return acc;
    if (MODE == SPMV_AXPBY)
       return (a.beta == 0.0) ? __dmul_rn(a.alpha, acc) : __dadd_rn(__dmul_rn(a.alpha, acc), __dmul_rn(a.beta, o.yo));
    if (MODE == SPMV_JACOBI)
@@ -404,7 +413,7 @@ __device__ __forceinline__ void sell_body(const SpmvDev &a)
       if (valid)
       {
          if (SUB) o.b = a.b[r];
-         if (MODE == SPMV_JACOBI || MODE == SPMV_JACOBI_R) o.d = a.d[r];
+         if (MODE == SPMV_JACOBI || MODE == SPMV_JACOBI_R || MODE == SPMV_SET_DIV) o.d = a.d[r];
          if (MODE == SPMV_JACOBI) o.xo = a.x[r];
          if (MODE == SPMV_ADD || MODE == SPMV_AXPBY) o.yo = a.y[r];
          if (DOT) o.dv = a.dotv[r];
@@ -420,6 +429,7 @@ __device__ __forceinline__ void sell_body(const SpmvDev &a)
       if (1 < len) { c1 = __ldcs(cp + 32); v1 = __ldcs(vp + 32); }
       if (2 < len) { c2 = __ldcs(cp + 64); v2 = __ldcs(vp + 64); }
       if (3 < len) { c3 = __ldcs(cp + 96); v3 = __ldcs(vp + 96); }
+#pragma unroll 1 // unrolled copies of this software-pipelined body double the register count (occupancy)
       for (int k = 0; k < len; k += 4)
       {
          const double x0 = __ldg(a.x + c0), x1 = __ldg(a.x + c1), x2 = __ldg(a.x + c2), x3 = __ldg(a.x + c3);
@@ -458,6 +468,7 @@ __device__ __forceinline__ void sell_body(const SpmvDev &a)
       {
          double yn = row_epilogue<MODE>(a, o, acc);
          a.y[r]    = yn;
+         store_y2<MODE>(a, r, yn, o.d);
          if (DOT) dacc += o.dv * yn;
       }
    }
@@ -483,13 +494,11 @@ __device__ __forceinline__ void sell_body(const SpmvDev &a)
    }
 }
 
-// Kernel entry points.  The kernel lives on memory-level parallelism, so occupancy matters: the
-// plain variant compiles to 32 registers (8 CTAs per SM) by itself; the fused-dot variant would
-// take 62, so it gets an explicit budget; the fused off-diagonal variants take 48-64.
+// Kernel entry point.  The kernel lives on memory-level parallelism across warps, so occupancy
+// matters: 32 registers (8 CTAs per SM) for the plain variants, 40-48 with a fused dot, 48-64 with
+// the fused off-diagonal block.
 template <int MODE, bool DOT, bool OFFD>
 __global__ void __launch_bounds__(SELL_T) k_spmv_sell(SpmvDev a) { sell_body<MODE, DOT, OFFD>(a); }
-template <int MODE>
-__global__ void __launch_bounds__(SELL_T, SELL_DOT_MINB) k_spmv_sell_dot(SpmvDev a) { sell_body<MODE, true, false>(a); }
 
 // slice metadata: lanes ranked by decreasing row length (ties by row), slice width = longest row
 __global__ void k_sell_meta(const int *rowptr, int nrows, int nslice, int *meta, int *width, int *max_slice_nnz,
@@ -563,19 +572,16 @@ __global__ void k_sell_fill(const int *rowptr, const int *col, const double *val
 template <int MODE, bool DOT, bool OFFD>
 static int launch_sell_v(const DevCSR &A, const SpmvDev &d)
 {
-   constexpr bool DK = DOT && !OFFD; // the budgeted fused-dot entry point
    static int occ = 0;
    if (!occ)
    {
-      if (DK) HDK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_spmv_sell_dot<MODE>, SELL_T, 0));
-      else HDK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_spmv_sell<MODE, DOT, OFFD>, SELL_T, 0));
+      HDK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_spmv_sell<MODE, DOT, OFFD>, SELL_T, 0));
       if (occ < 1) occ = 1;
    }
    int grid = cdiv(A.nslice, SELL_T / 32);
    int cap  = g.sm_count * occ;
    if (grid > cap) grid = cap;
-   if (DK) k_spmv_sell_dot<MODE><<<grid, SELL_T, 0, g.stream>>>(d);
-   else k_spmv_sell<MODE, DOT, OFFD><<<grid, SELL_T, 0, g.stream>>>(d);
+   k_spmv_sell<MODE, DOT, OFFD><<<grid, SELL_T, 0, g.stream>>>(d);
    return HDK_OK;
 }
 template <int MODE, bool DOT>
@@ -603,7 +609,7 @@ __global__ void __launch_bounds__(ST) k_spmv_vector(SpmvDev a)
       if (lane == 0)
       {
          double yn;
-         if (MODE == SPMV_SET) yn = acc;
+         if (MODE == SPMV_SET || MODE == SPMV_SET_DIV) yn = acc;
          else if (MODE == SPMV_AXPBY) yn = (a.beta == 0.0) ? a.alpha * acc : a.alpha * acc + a.beta * a.y[r];
          else if (MODE == SPMV_ADD) yn = a.y[r] + acc;
          else
@@ -618,6 +624,7 @@ __global__ void __launch_bounds__(ST) k_spmv_vector(SpmvDev a)
             }
          }
          a.y[r] = yn;
+         if (MODE == SPMV_SET_DIV) store_y2<MODE>(a, r, yn, a.d[r]);
          if (DOT) dacc += a.dotv[r] * yn;
       }
    }
@@ -689,7 +696,7 @@ int spmv_launch(const DevCSR &A, int mode, const SpmvArgs &s, const OffdFuse *of
    if (A.nrows <= 0) return HDK_OK;
    SpmvDev d;
    d.rowptr = A.rowptr; d.col = A.col; d.val = A.val; d.blk_row = A.blk_row;
-   d.x = s.x; d.b = s.b; d.d = s.d; d.dotv = s.dotv; d.y = s.y;
+   d.x = s.x; d.b = s.b; d.d = s.d; d.dotv = s.dotv; d.y = s.y; d.y2 = s.y2;
    d.w = s.w; d.alpha = s.alpha; d.beta = s.beta;
    d.nrows = A.nrows; d.fin = s.fin; d.fin_out = s.fin_out;
    d.scal = g.dscal; d.partials = g.partials; d.ticket = g.counters;
@@ -710,6 +717,7 @@ int spmv_launch(const DevCSR &A, int mode, const SpmvArgs &s, const OffdFuse *of
       case SPMV_ADD: return launch_mode<SPMV_ADD>(A, d, dot);
       case SPMV_AXPBY: return launch_mode<SPMV_AXPBY>(A, d, dot);
       case SPMV_JACOBI_R: return launch_mode<SPMV_JACOBI_R>(A, d, dot);
+      case SPMV_SET_DIV: return launch_mode<SPMV_SET_DIV>(A, d, dot);
    }
    return set_error(HDK_ERR_INVALID, "unknown spmv mode %d", mode);
 }

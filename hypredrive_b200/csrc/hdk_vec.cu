@@ -102,7 +102,7 @@ __global__ void __launch_bounds__(VT) k_reduce(const double *__restrict__ x, con
 __global__ void __launch_bounds__(VT) k_pcg_xr(double *__restrict__ x, double *__restrict__ r,
                                                const double *__restrict__ p, const double *__restrict__ s,
                                                int64_t n, double *partials, unsigned *ticket, double *scal,
-                                               int fin, double *fin_out)
+                                               int fin, double *fin_out, double *z0, const double *zd, double zw)
 {
    __shared__ double sm[VT / 32];
    __shared__ int    flag;
@@ -114,6 +114,8 @@ __global__ void __launch_bounds__(VT) k_pcg_xr(double *__restrict__ x, double *_
       double rn = __dadd_rn(r[i], -__dmul_rn(alpha, s[i]));
       r[i]      = rn;
       acc += rn * rn;
+      // first l1-Jacobi sweep of the coming V-cycle (zero guess): z0 = (w r)/d, as k_scaled_div
+      if (z0) { double dd = zd[i]; z0[i] = (dd != 0.0) ? __ddiv_rn(__dmul_rn(zw, rn), dd) : 0.0; }
    }
    double bs = block_sum<VT>(acc, sm);
    __syncthreads();
@@ -208,9 +210,10 @@ int vec_copy_dot(double *z, const double *r, int64_t n, int fin, double *out_d)
    HDK_LAUNCH_CHECK();
    return HDK_OK;
 }
-int pcg_update_xr(double *x, double *r, const double *p, const double *s, int64_t n, double *scal, int fin, double *fin_out)
+int pcg_update_xr(double *x, double *r, const double *p, const double *s, int64_t n, double *scal, int fin, double *fin_out,
+                  double *z0, const double *zd, double zw)
 {
-   k_pcg_xr<<<vec_grid(n), VT, 0, g.stream>>>(x, r, p, s, n, g.partials, g.counters, scal, fin, fin_out);
+   k_pcg_xr<<<vec_grid(n), VT, 0, g.stream>>>(x, r, p, s, n, g.partials, g.counters, scal, fin, fin_out, z0, zd, zw);
    HDK_LAUNCH_CHECK();
    return HDK_OK;
 }
