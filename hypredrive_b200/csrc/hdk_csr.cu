@@ -226,13 +226,12 @@ __global__ void k_offd_correct(const int *rows, const int *rowptr, const int *co
                                double alpha, IpcRecvArgs ipc, const double *dotv, const double *diag_part,
                                double *dot_out, double *partials, unsigned *ticket);
 
-// The fused variant needs 48-64 registers (5 or 4 CTAs per SM instead of 8): it wins on the
-// coarser operators, where the saved kernel + launch gap matters, and loses ~20-30 us on the
-// 16.7 M-row fine level, where occupancy matters more -- hence the row limit.
+// The fused variant runs at 32-40 registers like the plain one (the streaming loop is pinned to
+// no unrolling), so it is used on every level; HDK_FUSE_OFFD_MAX_ROWS / HDK_FUSE_OFFD=0 restrict it.
 static bool fuse_offd_enabled(int nrows)
 {
    static int       on = -1;
-   static long long max_rows = 4000000;
+   static long long max_rows = 2000000000LL;
    if (on < 0)
    {
       const char *e = getenv("HDK_FUSE_OFFD");
