@@ -410,15 +410,17 @@ __device__ __forceinline__ void sell_body(const SpmvDev &a)
       const size_t base = (size_t)__ldg(a.sl_off + s) * 32 + lane;
       RowOps o;
       o.b = o.d = o.xo = o.yo = o.dv = 0.0;
+      // (which operands are fetched before and which after the streaming loop is chosen by the
+      // register count ptxas ends up with: 32 = 8 CTAs per SM, 33-40 = 6, 41-48 = 5)
+      constexpr bool LATE = DOT; // fused-dot variants: smoother operands after the loop as well
       if (valid)
       {
          if (SUB) o.b = a.b[r];
-         if (MODE == SPMV_JACOBI || MODE == SPMV_JACOBI_R || MODE == SPMV_SET_DIV) o.d = a.d[r];
-         if (MODE == SPMV_JACOBI) o.xo = a.x[r];
-         if (MODE == SPMV_ADD || MODE == SPMV_AXPBY) o.yo = a.y[r];
-         if (DOT) o.dv = a.dotv[r];
+         if (!LATE && (MODE == SPMV_JACOBI || MODE == SPMV_JACOBI_R || MODE == SPMV_SET_DIV)) o.d = a.d[r];
+         if (!LATE && MODE == SPMV_JACOBI) o.xo = a.x[r];
+         if (MODE == SPMV_AXPBY) o.yo = a.y[r];
       }
-      double        acc = SUB ? o.b : ((MODE == SPMV_ADD) ? o.yo : 0.0);
+      double        acc = SUB ? o.b : 0.0;
       const int    *cp  = a.sl_col + base;
       const double *vp  = a.sl_val + base;
       // software pipeline: the val / col loads of group k+1 are in flight while the gathers of
@@ -466,6 +468,12 @@ __device__ __forceinline__ void sell_body(const SpmvDev &a)
       }
       if (valid)
       {
+         if (LATE && (MODE == SPMV_JACOBI || MODE == SPMV_JACOBI_R || MODE == SPMV_SET_DIV)) o.d = a.d[r];
+         if (LATE && MODE == SPMV_JACOBI) o.xo = a.x[r];
+         if (DOT) o.dv = a.dotv[r];
+         // y += A x: y is read only now (live across the loop it costs 10 registers = 3 CTAs per SM),
+         // so the sum is y + (a_0 x_0 + a_1 x_1 + ...) -- rounding-level difference to the CSR-order sum
+         if (MODE == SPMV_ADD) acc = __dadd_rn(a.y[r], acc);
          double yn = row_epilogue<MODE>(a, o, acc);
          a.y[r]    = yn;
          store_y2<MODE>(a, r, yn, o.d);

@@ -180,3 +180,23 @@ def test_options_dict_to_yaml():
     y = driver.normalize_options({"general": {"statistics": False}, "solver": {"pcg": {"max_iter": 10}},
                                   "preconditioner": {"amg": {"print_level": 0}}})
     assert "statistics: off" in y and "    max_iter: 10" in y and y.startswith("general:")
+
+
+def test_sliced_ell_kernel_register_budget():
+    """Occupancy guard for the kernel that is 80 % of a solve: the plain sliced-ELL variants must
+    compile to <= 32 registers (8 CTAs of 256 threads per SM) and the fused-dot / fused-offd
+    variants to <= 40 (6 CTAs), without spills -- ptxas is touchy here."""
+    import re
+    import shutil
+    import subprocess
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(cuobjdump):
+        pytest.skip("cuobjdump not available")
+    lib = os.path.join(ROOT, "hypredrive_b200", "lib", "libHYPREDRV.so")
+    out = subprocess.run([cuobjdump, "--dump-resource-usage", lib], capture_output=True, text=True).stdout
+    found = re.findall(r"Function _ZN3hdk11k_spmv_sellILi(\d)ELb([01])ELb([01])EEEvNS_7SpmvDevE:\s*\n\s*REG:(\d+) STACK:(\d+)", out)
+    assert len(found) >= 28, len(found)
+    for mode, dot, offd, reg, stack in found:
+        limit = 32 if (dot == "0" and offd == "0") else 40
+        assert int(reg) <= limit, (mode, dot, offd, reg)
+        assert int(stack) <= 8, (mode, dot, offd, stack)
