@@ -57,7 +57,7 @@ preconditioner:
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of the fine-level residual SpMV at the bench
 # workload (256^3 7-point rows per GPU), from the `ncu --set full` capture summarised under
 # profiles/ (see profiles/README.md); None when no capture exists for the selected kernel
-NCU_TRAFFIC_BYTES = {"k_spmv_sell": 1.7438e9 + 0.1185e9, "k_spmv_tma": 1.7404e9 + 0.1303e9}
+NCU_TRAFFIC_BYTES = {"k_spmv_sell": 1.7437e9 + 0.1171e9, "k_spmv_tma": 1.7404e9 + 0.1303e9}
 CPU_SAMPLE_EDGE = 160  # cube edge of the bounded CPU sample (about 10-30 s of work on ~8 cores)
 
 
