@@ -284,6 +284,7 @@ int parcsr_matvec(const hdk_csr_s &A, int mode, SpmvArgs a); // halo exchange + 
 int parcsr_build(int64_t rs, int64_t re, int64_t cs, int64_t ce, int64_t grows, int64_t gcols, bool square,
                  bool distributed, bool keep_orig, const int64_t *indptr, const int64_t *cols, const double *vals,
                  hdk_csr_s **out, bool analyze = true);
+int allreduce_max_dev(double *buf_d, int count);
 int bcast_bytes(void *buf_d, size_t bytes, int root);                 // NCCL broadcast on the compute stream
 int allgather_i64_host(int64_t mine, std::vector<int64_t> &all);
 int allgatherv_bytes(void *base_d, const int64_t *byte_offs /* nranks+1 */); // in place, compute stream

@@ -284,11 +284,11 @@ int hdk_vec_norm(const double *x_d, int64_t n, int kind, double *result_h)
    else
       k_reduce<2><<<vec_grid(n), VT, 0, g.stream>>>(x_d, x_d, n, g.partials, g.counters, FIN_STORE, g.dscal + S_TMP0, g.dscal);
    HDK_LAUNCH_CHECK();
-   if (kind == 0) HDK_TRY(allreduce_dev(g.dscal + S_TMP0, 1));
+   if (kind == 0) HDK_TRY(allreduce_dev(g.dscal + S_TMP0, 1));   // L1: sum over ranks
+   else HDK_TRY(allreduce_max_dev(g.dscal + S_TMP0, 1));        // Linf: max over ranks
    HDK_CUDA(cudaMemcpyAsync(g.hscal + S_TMP0, g.dscal + S_TMP0, sizeof(double), cudaMemcpyDeviceToHost, g.stream));
    HDK_CUDA(cudaStreamSynchronize(g.stream));
    *result_h = g.hscal[S_TMP0];
-   // Linf over ranks is not summed: the host layer takes the max of per-rank values
    return HDK_OK;
 }
 
