@@ -87,6 +87,31 @@ __global__ void k_cast_i64(const int *in, int64_t *out, int n)
    if (i < n) out[i] = (int64_t)in[i];
 }
 
+// sum of n non-negative ints in 64 bits: the row counts of a product must fit the int32 row
+// pointers before they are scanned (a 640^3 7-point problem overflows at level 1)
+__global__ void k_sum_i64(const int *v, int n, unsigned long long *out)
+{
+   unsigned long long s = 0;
+   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) s += (unsigned long long)(v[i] > 0 ? v[i] : 0);
+   for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
+   if ((threadIdx.x & 31) == 0 && s) atomicAdd(out, s);
+}
+static int check_fits_int32(const int *cnt, int n, const char *what)
+{
+   unsigned long long *d = reinterpret_cast<unsigned long long *>(g.dscal + S_TMP2), h = 0;
+   HDK_CUDA(cudaMemsetAsync(d, 0, sizeof(unsigned long long), g.stream));
+   int grid = cdiv(n, 256);
+   if (grid > g.sm_count * 8) grid = g.sm_count * 8;
+   if (grid < 1) grid = 1;
+   k_sum_i64<<<grid, 256, 0, g.stream>>>(cnt, n, d);
+   HDK_LAUNCH_CHECK();
+   HDK_CUDA(cudaMemcpyAsync(&h, d, sizeof(h), cudaMemcpyDeviceToHost, g.stream));
+   HDK_CUDA(cudaStreamSynchronize(g.stream));
+   if (h > 2000000000ULL)
+      return set_error(HDK_ERR_UNSUPPORTED, "%s would have %llu non-zeros: more than the int32 row pointers of this setup hold", what, h);
+   return HDK_OK;
+}
+
 static int exclusive_scan_i64(const int *in, int64_t *out, int n)
 {
    k_cast_i64<<<cdiv(n, 256), 256, 0, g.stream>>>(in, out, n);
@@ -867,6 +892,7 @@ static int build_interp(const DevCSR &A, const DevCSR &S, int *cf, const int *f2
    HDK_CUDA(cudaMemsetAsync(rowlen + n, 0, sizeof(int), g.stream));
    HDK_CUDA(cudaMemsetAsync(cnt + n, 0, sizeof(int), g.stream));
    HDK_TRY(share_rows(rowlen, sizeof(int), n)); // row lengths of the other ranks' shares
+   HDK_TRY(check_fits_int32(rowlen, n, "the interpolation operator"));
    HDK_TRY(exclusive_scan_int(rowlen, prp, n + 1));
    int nnzP = 0;
    HDK_CUDA(cudaMemcpyAsync(&nnzP, prp + n, sizeof(int), cudaMemcpyDeviceToHost, g.stream));
@@ -1267,6 +1293,7 @@ static int build_rap(const DevCSR &R, const DevCSR &A, const DevCSR &P, DevCSR &
    stage_mark("  rap.thr1", -1);
    HDK_CUDA(cudaMemsetAsync(cnt + nc, 0, sizeof(int), g.stream));
    HDK_TRY(share_rows(cnt, sizeof(int), nc)); // row lengths of the other ranks' shares
+   HDK_TRY(check_fits_int32(cnt, nc, "the coarse-grid operator"));
    HDK_TRY(exclusive_scan_int(cnt, crp, nc + 1));
    int nnzC = 0;
    HDK_CUDA(cudaMemcpyAsync(&nnzC, crp + nc, sizeof(int), cudaMemcpyDeviceToHost, g.stream));
