@@ -841,8 +841,89 @@ __global__ void k_cf_reset_sf(int *cf, int n)
    if (i < n && cf[i] == SF_PT) cf[i] = F_PT;
 }
 
-static int build_interp(const DevCSR &A, const DevCSR &S, int *cf, const int *f2c, int nc, int max_elmts, DevCSR &P)
+// hypre_BoomerAMGInterpTruncation as a post-pass (used when trunc_factor > 0; with trunc_factor
+// = 0 the max_elmts stage is fused into the interpolation kernels): per row, drop the weights
+// below trunc_factor * max|w| and rescale the rest to the old row sum, then keep the max_elmts
+// largest |w| (hypre_qsort2abs order) and rescale again.  One thread per row, in place.
+__global__ void k_trunc_rows(const int *rp, int *col, double *val, int n, double tf, int max_elmts, int *newlen)
 {
+   int i = blockIdx.x * blockDim.x + threadIdx.x;
+   if (i > n) return;
+   if (i == n) { newlen[i] = 0; return; }
+   int b = rp[i], e = rp[i + 1], len = e - b;
+   if (tf > 0.0 && len > 0)
+   {
+      double maxc = 0.0, row_sum = 0.0, scale = 0.0;
+      for (int k = b; k < e; k++) if (fabs(val[k]) > maxc) maxc = fabs(val[k]);
+      maxc  = __dmul_rn(maxc, tf);
+      int w = b;
+      for (int k = b; k < e; k++)
+      {
+         double v = val[k];
+         row_sum  = __dadd_rn(row_sum, v);
+         if (!(fabs(v) < maxc)) { scale = __dadd_rn(scale, v); col[w] = col[k]; val[w] = v; w++; }
+      }
+      if (scale != 0.0 && scale != row_sum)
+      {
+         scale = __ddiv_rn(row_sum, scale);
+         for (int k = b; k < w; k++) val[k] = __dmul_rn(val[k], scale);
+      }
+      len = w - b;
+      e   = w;
+   }
+   if (max_elmts > 0 && len > max_elmts)
+   {
+      double row_sum = 0.0, scale = 0.0;
+      for (int k = b; k < e; k++) row_sum = __dadd_rn(row_sum, val[k]);
+      qsort2abs_dev(col + b, val + b, len);
+      for (int k = 0; k < max_elmts; k++) scale = __dadd_rn(scale, val[b + k]);
+      if (scale != 0.0 && scale != row_sum)
+      {
+         scale = __ddiv_rn(row_sum, scale);
+         for (int k = 0; k < max_elmts; k++) val[b + k] = __dmul_rn(val[b + k], scale);
+      }
+      len = max_elmts;
+   }
+   newlen[i] = len;
+}
+__global__ void k_compact_rows(const int *rp, const int *col, const double *val, const int *nrp, int n, int *ncol, double *nval)
+{
+   int i = blockIdx.x * blockDim.x + threadIdx.x;
+   if (i >= n) return;
+   int b = rp[i], nb = nrp[i], len = nrp[i + 1] - nb;
+   for (int k = 0; k < len; k++) { ncol[nb + k] = col[b + k]; nval[nb + k] = val[b + k]; }
+}
+static int interp_truncate(DevCSR &P, double trunc_factor, int max_elmts)
+{
+   const int n = P.nrows;
+   int *newlen, *nrp;
+   HDK_TRY(dalloc(&newlen, (size_t)n + 1));
+   HDK_TRY(dalloc(&nrp, (size_t)n + 1));
+   k_trunc_rows<<<cdiv(n + 1, 128), 128, 0, g.stream>>>(P.rowptr, P.col, P.val, n, trunc_factor, max_elmts, newlen);
+   HDK_LAUNCH_CHECK();
+   HDK_TRY(exclusive_scan_int(newlen, nrp, n + 1));
+   int nnz = 0;
+   HDK_CUDA(cudaMemcpyAsync(&nnz, nrp + n, sizeof(int), cudaMemcpyDeviceToHost, g.stream));
+   HDK_CUDA(cudaStreamSynchronize(g.stream));
+   DevCSR Q;
+   Q.nrows = n; Q.ncols = P.ncols; Q.nnz = nnz; Q.rowptr = nrp; Q.owns = true;
+   HDK_TRY(dalloc(&Q.col, (size_t)nnz + 8));
+   HDK_TRY(dalloc(&Q.val, (size_t)nnz + 8));
+   HDK_CUDA(cudaMemsetAsync(Q.col + nnz, 0, sizeof(int) * 8, g.stream));
+   HDK_CUDA(cudaMemsetAsync(Q.val + nnz, 0, sizeof(double) * 8, g.stream));
+   k_compact_rows<<<cdiv(n, 128), 128, 0, g.stream>>>(P.rowptr, P.col, P.val, nrp, n, Q.col, Q.val);
+   HDK_LAUNCH_CHECK();
+   dfree(newlen);
+   csr_free(P);
+   P = Q;
+   return HDK_OK;
+}
+
+static int build_interp(const DevCSR &A, const DevCSR &S, int *cf, const int *f2c, int nc, int max_elmts_in, double trunc_factor,
+                        DevCSR &P)
+{
+   // with a truncation factor the rows are built complete and truncated by the post-pass
+   const int max_elmts = (trunc_factor > 0.0) ? 0 : max_elmts_in;
    int  n = A.nrows;
    int *cap, *cnt, *rowlen, *prp;
    int64_t *off;
@@ -947,6 +1028,7 @@ static int build_interp(const DevCSR &A, const DevCSR &S, int *cf, const int *f2
    k_cf_reset_sf<<<cdiv(n, 256), 256, 0, g.stream>>>(cf, n);
    HDK_LAUNCH_CHECK();
    dfree(cap); dfree(cnt); dfree(rowlen); dfree(off); dfree(loff); dfree(slow);
+   if (trunc_factor > 0.0) HDK_TRY(interp_truncate(P, trunc_factor, max_elmts_in));
    return HDK_OK;
 }
 
@@ -1662,7 +1744,7 @@ static int setup_serial(const hdk_csr_s *A0, const hdk_amg_params *prm, hdk_amg_
       dfree(flag);
       if (nc == 0 || nc == n || nc < prm->min_coarse_size) { dfree(f2c); break; }
       DevCSR P, R, C;
-      rc = build_interp(A.diag, L.S, L.cf, f2c, nc, prm->max_nnz_row, P);
+      rc = build_interp(A.diag, L.S, L.cf, f2c, nc, prm->max_nnz_row, prm->trunc_factor, P);
       stage_mark("interp", level);
       if (keep_f2c) L.f2c = f2c; else dfree(f2c);
       if (rc) break;
@@ -1918,7 +2000,7 @@ int hdk_amg_setup(const hdk_csr *A0, const hdk_amg_params *prm, hdk_amg **out)
    HDK_TRY(require_init());
    if (!A0 || !prm || !out) return set_error(HDK_ERR_INVALID, "hdk_amg_setup: null argument");
    if (prm->interp_type != 6) return set_error(HDK_ERR_UNSUPPORTED, "interpolation type %d: only extended+i (6) has a device kernel", prm->interp_type);
-   if (prm->trunc_factor != 0.0) return set_error(HDK_ERR_UNSUPPORTED, "interpolation trunc_factor != 0 is not supported on the device path");
+   if (prm->trunc_factor < 0.0 || prm->trunc_factor >= 1.0) return set_error(HDK_ERR_INVALID, "interpolation trunc_factor must be in [0, 1)");
    g_timing = getenv("HDK_SETUP_TIMING") && atoi(getenv("HDK_SETUP_TIMING")) == 1;
    if (g.nranks > 1) return setup_distributed(A0, prm, out);
    return setup_serial(A0, prm, out, false);

@@ -160,6 +160,10 @@ def test_amg_setup_bit_exact(gpu, kind, dims, c):
 def test_amg_setup_other_options(gpu):
     A, _ = O.gen("lap7", 14, 13, 12)
     _compare_hierarchy(gpu, A, dict(max_nnz_row=0))            # no truncation
+    _compare_hierarchy(gpu, A, dict(trunc_factor=0.2))         # hypre_BoomerAMGInterpTruncation: factor, then max 4
+    _compare_hierarchy(gpu, A, dict(trunc_factor=0.35, max_nnz_row=0))
+    B, _ = O.gen("lap27", 9, 8, 7, c=(1.0, 1.0, 0.01))
+    _compare_hierarchy(gpu, B, dict(trunc_factor=0.1, max_nnz_row=6))
     _compare_hierarchy(gpu, A, dict(strong_th=0.5, max_coarse_size=20, max_nnz_row=6))
     _compare_hierarchy(gpu, A, dict(max_levels=2))
 
