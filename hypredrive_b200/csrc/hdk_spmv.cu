@@ -36,6 +36,7 @@ struct Tune
    double tgt_max       = 3072;     // HDK_SPMV_TGT_MAX     non-zeros per stream-kernel block (cap)
    double lpr           = 0;        // HDK_SPMV_LPR         force lanes per row (0 = by row length)
    double sell_min_rows = 200000;   // HDK_SELL_MIN_ROWS    sliced-ELL for matrices with at least this many rows
+   double sell_min_rows_dist = 30000;  // HDK_SELL_MIN_ROWS_DIST  the same for slabs with off-rank entries (fused halo wait)
    double sell_min_avg  = 0.0;      // HDK_SELL_MIN_AVG     ... and more than this many non-zeros per row
    double sell_sort     = 1;        // HDK_SELL_SORT        sort the columns of coarse operators in the slices
    bool   env_read      = false;
@@ -44,6 +45,7 @@ static Tune tune;
 static const struct { const char *key, *env; double Tune::*field; } tune_keys[] = {
    {"spmv_rows_mult", "HDK_SPMV_ROWS_MULT", &Tune::rows_mult}, {"spmv_tgt_max", "HDK_SPMV_TGT_MAX", &Tune::tgt_max},
    {"spmv_lpr", "HDK_SPMV_LPR", &Tune::lpr},                   {"sell_min_rows", "HDK_SELL_MIN_ROWS", &Tune::sell_min_rows},
+   {"sell_min_rows_dist", "HDK_SELL_MIN_ROWS_DIST", &Tune::sell_min_rows_dist},
    {"sell_min_avg", "HDK_SELL_MIN_AVG", &Tune::sell_min_avg},  {"sell_sort", "HDK_SELL_SORT", &Tune::sell_sort}};
 static Tune &tunables()
 {
@@ -837,7 +839,8 @@ int csr_analyze(DevCSR &A)
       // large operators go to the sliced-ELL kernel; small ones are latency-bound and do better
       // with several lanes per row in the stream kernel
       const Tune &t = tunables();
-      if ((double)A.nrows >= t.sell_min_rows && A.avg_row > t.sell_min_avg) HDK_TRY(sell_build(A));
+      const double min_rows = A.offd_rowptr ? t.sell_min_rows_dist : t.sell_min_rows;
+      if ((double)A.nrows >= min_rows && A.avg_row > t.sell_min_avg) HDK_TRY(sell_build(A));
    }
    if (A.kind == 0)
    {
