@@ -41,6 +41,7 @@ def test_two_rank_solve_matches_oracle(gpu, kind, dims, rep, share):
         env["HDK_HALO_IPC"] = "0"
     elif share.startswith("sell"):
         env["HDK_SELL_MIN_ROWS"] = "0"
+        env["HDK_SELL_MIN_ROWS_DIST"] = "0"
         if share == "sell-unfused":
             env["HDK_FUSE_OFFD"] = "0"
         if share == "sell-nccl":
