@@ -263,6 +263,28 @@ def test_sliced_ell_levels_parity(gpu, sort):
         gpu.tune("sell_sort", 1)
 
 
+@pytest.mark.parametrize("down,up", [(2, 2), (1, 2), (2, 1), (0, 1), (1, 0)])
+def test_sweep_counts_and_prefilled_first_sweep(gpu, down, up):
+    """Buffer parity of the V-cycle for every sweep combination, including the fused paths where
+    the first zero-guess sweep is produced by the restriction kernel / the PCG x-r update."""
+    A, b = O.gen("lap7", 14, 12, 10)
+    kw = dict(sweeps_down=down, sweeps_up=up)
+    H = O.Hierarchy(A, O.default_params(True, **kw))
+    dA = gpu.DCsr.from_scipy(A)
+    M = gpu.DAmg(dA, gpu.amg_params(**kw))
+    n = A.shape[0]
+    r = np.random.default_rng(5).standard_normal(n)
+    dr, dz = gpu.DVec(n, r), gpu.DVec(n)
+    M.apply(dr, dz)
+    z_ref = H.precond(r)
+    assert np.allclose(dz.get(), z_ref, rtol=1e-11, atol=1e-13 * np.abs(z_ref).max())
+    db, dx = gpu.DVec(n, b), gpu.DVec(n)
+    info = gpu.pcg(dA, db, dx, M, rel_tol=1e-8, max_iter=200)
+    xo, io = O.pcg(A, b, M=H, rel_tol=1e-8, max_iter=200)
+    assert info["converged"] and abs(info["iters"] - io["iters"]) <= 1
+    assert np.linalg.norm(dx.get() - xo) <= 1e-8 * np.linalg.norm(xo)
+
+
 def test_pcg_without_preconditioner_and_zero_rhs(gpu):
     A, b = O.gen("lap7", 8, 8, 8)
     n = A.shape[0]
