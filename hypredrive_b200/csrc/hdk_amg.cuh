@@ -31,7 +31,7 @@ struct hdk_amg_s
    int                        ge_n = 0;
    double                     op_complexity = 0.0;
    double                     vcycle_bytes = 0.0;
-   bool                       keep_debug = true; // keep S / measure for introspection
+   bool                       keep_debug = false; // keep S / measure for introspection (tunable amg_keep_debug)
    bool                       prefilled_l0 = false; // next zero-guess cycle: level-0 first sweep already done by the caller
    bool                       keep_f2c = false;
    // N > 1: levels [0, nlev) are row-distributed; from level `tail_level` on, the hierarchy is

@@ -1706,6 +1706,7 @@ static int setup_serial(const hdk_csr_s *A0, const hdk_amg_params *prm, hdk_amg_
    hdk_amg_s *M = new hdk_amg_s();
    M->prm       = *prm;
    M->keep_f2c  = keep_f2c;
+   M->keep_debug = tune_amg_keep_debug();
    int rc       = HDK_OK;
    M->lev.emplace_back();
    M->lev[0].A = const_cast<hdk_csr_s *>(A0);

@@ -113,6 +113,7 @@ int  csr_alloc(DevCSR &A, int nrows, int ncols, int nnz, bool values = true);
 void csr_free(DevCSR &A);
 int  csr_analyze(DevCSR &A);
 int  tune_set(const char *key, double value);
+bool tune_amg_keep_debug();
 
 // epilogue selectors of the fused SpMV family (see hdk_spmv.cu)
 enum SpmvMode

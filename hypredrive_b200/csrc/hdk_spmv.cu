@@ -39,6 +39,7 @@ struct Tune
    double sell_min_rows_dist = 30000;  // HDK_SELL_MIN_ROWS_DIST  the same for slabs with off-rank entries (fused halo wait)
    double sell_min_avg  = 0.0;      // HDK_SELL_MIN_AVG     ... and more than this many non-zeros per row
    double sell_sort     = 1;        // HDK_SELL_SORT        sort the columns of coarse operators in the slices
+   double amg_keep_debug = 0;       // HDK_AMG_KEEP_DEBUG   keep S and the PMIS measures of every level (introspection)
    bool   env_read      = false;
 };
 static Tune tune;
@@ -46,6 +47,7 @@ static const struct { const char *key, *env; double Tune::*field; } tune_keys[] 
    {"spmv_rows_mult", "HDK_SPMV_ROWS_MULT", &Tune::rows_mult}, {"spmv_tgt_max", "HDK_SPMV_TGT_MAX", &Tune::tgt_max},
    {"spmv_lpr", "HDK_SPMV_LPR", &Tune::lpr},                   {"sell_min_rows", "HDK_SELL_MIN_ROWS", &Tune::sell_min_rows},
    {"sell_min_rows_dist", "HDK_SELL_MIN_ROWS_DIST", &Tune::sell_min_rows_dist},
+   {"amg_keep_debug", "HDK_AMG_KEEP_DEBUG", &Tune::amg_keep_debug},
    {"sell_min_avg", "HDK_SELL_MIN_AVG", &Tune::sell_min_avg},  {"sell_sort", "HDK_SELL_SORT", &Tune::sell_sort}};
 static Tune &tunables()
 {
@@ -60,6 +62,8 @@ static Tune &tunables()
    }
    return tune;
 }
+bool tune_amg_keep_debug() { return tunables().amg_keep_debug != 0.0; }
+
 int tune_set(const char *key, double value)
 {
    Tune &t = tunables();

@@ -28,4 +28,5 @@ def gpu():
     if hdk.device_count() <= 0:
         pytest.fail("test marked gpu but no CUDA device is visible")
     hdk.init()
+    hdk.tune("amg_keep_debug", 1)       # tests compare S and the PMIS measures level by level
     return hdk
