@@ -99,23 +99,44 @@ __global__ void __launch_bounds__(VT) k_reduce(const double *__restrict__ x, con
 }
 
 // PCG: x += alpha p ; r -= alpha s ; i_prod = <r,r>   (one pass, 48 bytes per row)
-__global__ void __launch_bounds__(VT) k_pcg_xr(double *__restrict__ x, double *__restrict__ r,
-                                               const double *__restrict__ p, const double *__restrict__ s,
-                                               int64_t n, double *partials, unsigned *ticket, double *scal,
-                                               int fin, double *fin_out, double *z0, const double *zd, double zw)
+// PREFILL: also z0 = (w r)/d, the first l1-Jacobi sweep of the coming V-cycle from a zero guess
+// (the expression of k_scaled_div), 64 bytes per row.  Two rows per iteration, loads first.
+template <bool PREFILL>
+__device__ __forceinline__ double pcg_xr_row(double alpha, double xi, double pi, double ri, double si, double di, double zw,
+                                             double *x, double *r, double *z0, int64_t i)
+{
+   x[i]            = __dadd_rn(xi, __dmul_rn(alpha, pi));
+   const double rn = __dadd_rn(ri, -__dmul_rn(alpha, si));
+   r[i]            = rn;
+   if (PREFILL) z0[i] = (di != 0.0) ? __ddiv_rn(__dmul_rn(zw, rn), di) : 0.0;
+   return rn * rn;
+}
+
+template <bool PREFILL>
+__global__ void __launch_bounds__(VT) k_pcg_xr(double *x, double *r, const double *p, const double *s, int64_t n,
+                                               double *partials, unsigned *ticket, double *scal, int fin, double *fin_out,
+                                               double *z0, const double *zd, double zw)
 {
    __shared__ double sm[VT / 32];
    __shared__ int    flag;
    const double      alpha = scal[S_ALPHA];
    double            acc   = 0.0;
-   for (int64_t i = blockIdx.x * (int64_t)VT + threadIdx.x; i < n; i += (int64_t)gridDim.x * VT)
+   const int64_t     stride = (int64_t)gridDim.x * VT;
+   int64_t           i = blockIdx.x * (int64_t)VT + threadIdx.x;
+   for (; i + stride < n; i += 2 * stride)
    {
-      x[i]      = __dadd_rn(x[i], __dmul_rn(alpha, p[i]));
-      double rn = __dadd_rn(r[i], -__dmul_rn(alpha, s[i]));
-      r[i]      = rn;
-      acc += rn * rn;
-      // first l1-Jacobi sweep of the coming V-cycle (zero guess): z0 = (w r)/d, as k_scaled_div
-      if (z0) { double dd = zd[i]; z0[i] = (dd != 0.0) ? __ddiv_rn(__dmul_rn(zw, rn), dd) : 0.0; }
+      const int64_t j = i + stride;
+      const double  xi = x[i], pi = p[i], ri = r[i], si = s[i];
+      const double  xj = x[j], pj = p[j], rj = r[j], sj = s[j];
+      double        di = 0.0, dj = 0.0;
+      if (PREFILL) { di = zd[i]; dj = zd[j]; }
+      acc += pcg_xr_row<PREFILL>(alpha, xi, pi, ri, si, di, zw, x, r, z0, i);
+      acc += pcg_xr_row<PREFILL>(alpha, xj, pj, rj, sj, dj, zw, x, r, z0, j);
+   }
+   if (i < n)
+   {
+      const double di = PREFILL ? zd[i] : 0.0;
+      acc += pcg_xr_row<PREFILL>(alpha, x[i], p[i], r[i], s[i], di, zw, x, r, z0, i);
    }
    double bs = block_sum<VT>(acc, sm);
    __syncthreads();
@@ -213,7 +234,8 @@ int vec_copy_dot(double *z, const double *r, int64_t n, int fin, double *out_d)
 int pcg_update_xr(double *x, double *r, const double *p, const double *s, int64_t n, double *scal, int fin, double *fin_out,
                   double *z0, const double *zd, double zw)
 {
-   k_pcg_xr<<<vec_grid(n), VT, 0, g.stream>>>(x, r, p, s, n, g.partials, g.counters, scal, fin, fin_out, z0, zd, zw);
+   if (z0) k_pcg_xr<true><<<vec_grid(n), VT, 0, g.stream>>>(x, r, p, s, n, g.partials, g.counters, scal, fin, fin_out, z0, zd, zw);
+   else k_pcg_xr<false><<<vec_grid(n), VT, 0, g.stream>>>(x, r, p, s, n, g.partials, g.counters, scal, fin, fin_out, z0, zd, zw);
    HDK_LAUNCH_CHECK();
    return HDK_OK;
 }
