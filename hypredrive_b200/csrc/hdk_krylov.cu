@@ -50,20 +50,32 @@ static int read_scalars(int count)
    return HDK_OK;
 }
 
-__global__ void k_axpy_dev(const double *coef, double sign, const double *__restrict__ x,
-                           double *__restrict__ y, int64_t n)
+// Modified Gram-Schmidt step in one pass: y -= h x (h on the device) and <z, y_new> for the next
+// coefficient (z = the next basis vector, or y itself for the final norm): 4 vector accesses per
+// basis vector instead of the 5 of a separate dot + axpy
+__global__ void __launch_bounds__(256) k_axpy_dot(const double *coef, const double *x, double *y, const double *z, int64_t n,
+                                                  double *partials, unsigned *ticket, double *out, double *scal)
 {
-   const double a = sign * coef[0];
-   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
-      y[i] = __dadd_rn(y[i], __dmul_rn(a, x[i]));
+   __shared__ double sm[256 / 32];
+   __shared__ int    flag;
+   const double      a = -coef[0];
+   const bool        self = (z == y);
+   double            acc = 0.0;
+   for (int64_t i = blockIdx.x * (int64_t)256 + threadIdx.x; i < n; i += (int64_t)gridDim.x * 256)
+   {
+      const double yn = __dadd_rn(y[i], __dmul_rn(a, x[i]));
+      y[i]            = yn;
+      acc += (self ? yn : z[i]) * yn;
+   }
+   double bs = block_sum<256>(acc, sm);
+   __syncthreads();
+   grid_finish<256>(bs, partials, ticket, FIN_STORE, out, scal, sm, &flag);
 }
-
-static int axpy_dev(const double *coef, double sign, const double *x, double *y, int64_t n)
+static int axpy_dot_dev(const double *coef, const double *x, double *y, const double *z, int64_t n, double *out)
 {
-   if (n <= 0) return HDK_OK;
    int64_t want = (n + 1023) / 1024, cap = (int64_t)g.sm_count * 8;
-   int     grid = (int)(want < cap ? (want < 1 ? 1 : want) : cap);
-   k_axpy_dev<<<grid, 256, 0, g.stream>>>(coef, sign, x, y, n);
+   int     grid = (int)(want < 1 ? 1 : (want < cap ? want : cap));
+   k_axpy_dot<<<grid, 256, 0, g.stream>>>(coef, x, y, z, n, g.partials, g.counters, out, g.dscal);
    HDK_LAUNCH_CHECK();
    return HDK_OK;
 }
@@ -216,18 +228,19 @@ static int gmres_impl(const hdk_csr *A, hdk_amg *M, const double *b, double *x, 
             double *zz = flexible ? z[(size_t)i - 1] : r;
             if (M) { if ((rc = amg_precond(M, p[(size_t)i - 1], zz, FIN_NONE, nullptr))) goto done; }
             else if ((rc = vec_copy(zz, p[(size_t)i - 1], n))) goto done;
+            // modified Gram-Schmidt, coefficients on the device (S_H0 + j): h_0 = <p_0, A zz> comes out
+            // of the SpMV kernel; step j subtracts h_j p_j and produces h_{j+1} (or <p_i,p_i>) in one pass
             SpmvArgs a;
             a.x = zz; a.y = p[(size_t)i];
+            a.dotv = p[0]; a.fin = FIN_STORE; a.fin_out = S + S_H0;
             if ((rc = parcsr_matvec(*A, SPMV_SET, a))) goto done;
-            // modified Gram-Schmidt: coefficients stay on the device (S_H0 + j)
+            if ((rc = allreduce_dev(S + S_H0, 1))) goto done;
             for (int j = 0; j < i; j++)
             {
-               if ((rc = vec_dot_dev(p[(size_t)j], p[(size_t)i], n, FIN_STORE, S + S_H0 + j))) goto done;
-               if ((rc = allreduce_dev(S + S_H0 + j, 1))) goto done;
-               if ((rc = axpy_dev(S + S_H0 + j, -1.0, p[(size_t)j], p[(size_t)i], n))) goto done;
+               const double *znext = (j + 1 < i) ? p[(size_t)j + 1] : p[(size_t)i];
+               if ((rc = axpy_dot_dev(S + S_H0 + j, p[(size_t)j], p[(size_t)i], znext, n, S + S_H0 + j + 1))) goto done;
+               if ((rc = allreduce_dev(S + S_H0 + j + 1, 1))) goto done;
             }
-            if ((rc = vec_dot_dev(p[(size_t)i], p[(size_t)i], n, FIN_STORE, S + S_H0 + i))) goto done;
-            if ((rc = allreduce_dev(S + S_H0 + i, 1))) goto done;
             HDK_CUDA(cudaMemcpyAsync(g.hscal + S_H0, S + S_H0, sizeof(double) * (size_t)(i + 1), cudaMemcpyDeviceToHost, g.stream));
             HDK_CUDA(cudaStreamSynchronize(g.stream));
             for (int j = 0; j < i; j++) HH(j, i - 1) = g.hscal[S_H0 + j];
