@@ -256,6 +256,37 @@ static int parse_into(hd_node *root, const char *text, const char *base_dir, int
    return 0;
 }
 
+/* `include:` followed by a sequence of file names (reference examples/ex8-multi-1.yml: one
+ * preconditioner variant per file): every listed file becomes one sequence item of the parent,
+ * holding the file's tree.  The scalar form `include: file.yml` is spliced while parsing. */
+static void expand_include_lists(hd_node *n, const char *base_dir)
+{
+   for (hd_node *c = n->child; c; c = c->next) expand_include_lists(c, base_dir);
+   hd_node *prev = NULL, *c = n->child;
+   while (c)
+   {
+      hd_node *nx = c->next;
+      if (!strcmp(c->key, "include") && !c->val[0] && c->child && c->child->is_seq_item)
+      {
+         /* unlink the include node, append one item per file at the end of the parent */
+         if (prev) prev->next = nx; else n->child = nx;
+         c->next = NULL;
+         for (hd_node *it = c->child; it; it = it->next)
+         {
+            hd_node *item = node_new("-", "", n->level + 1);
+            item->is_seq_item = 1;
+            node_append(n, item);
+            splice_include(item, it->raw_val, base_dir, 1);
+         }
+         hd_yaml_free(c);
+         c = nx;
+         continue;
+      }
+      prev = c;
+      c    = nx;
+   }
+}
+
 hd_node *hd_yaml_parse(const char *text, const char *base_dir)
 {
    hd_node *root = calloc(1, sizeof(hd_node));
@@ -263,6 +294,7 @@ hd_node *hd_yaml_parse(const char *text, const char *base_dir)
    uint32_t before = hd_err_get();
    if (!text) { hd_err_set(HYPREDRV_ERROR_YAML_TREE_NULL); hd_yaml_free(root); return NULL; }
    parse_into(root, text, base_dir, 0);
+   if (!(hd_err_get() & ~before)) expand_include_lists(root, base_dir);
    if (hd_err_get() & ~before) { hd_yaml_free(root); return NULL; }
    return root;
 }

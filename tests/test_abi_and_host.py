@@ -76,6 +76,24 @@ def test_yaml_forms_accepted():
     driver.api().HYPREDRV_Destroy(C.byref(h))
 
 
+def test_yaml_include_scalar_and_list_forms(tmp_path):
+    """`include: file` splices a fragment; `include:` + a list of files makes one preconditioner
+    variant per file (reference examples/ex8-multi-1.yml with ex8-amg-N.yml fragments)."""
+    (tmp_path / "v1.yml").write_text("coarsening:\n  type: pmis\n  strong_th: 0.25\nrelaxation:\n  down_type: l1-jacobi\n  up_type: l1-jacobi\n")
+    (tmp_path / "v2.yml").write_text("coarsening:\n  type: pmis\n  strong_th: 0.5\n")
+    (tmp_path / "krylov.yml").write_text("pcg:\n  max_iter: 77\n")
+    main = tmp_path / "main.yml"
+    main.write_text("solver:\n  include: krylov.yml\npreconditioner:\n  amg:\n    include:\n      - v1.yml\n      - v2.yml\n")
+    h = _obj()
+    assert _parse(h, str(main)) == 0
+    nv = C.c_int()
+    driver.api().HYPREDRV_InputArgsGetNumPreconVariants(h, C.byref(nv))
+    assert nv.value == 2
+    (tmp_path / "bad.yml").write_text("solver: pcg\npreconditioner:\n  amg:\n    include:\n      - missing.yml\n")
+    assert _parse(h, str(tmp_path / "bad.yml")) != 0          # missing fragment: FILE_NOT_FOUND bit
+    driver.api().HYPREDRV_Destroy(C.byref(h))
+
+
 def test_yaml_errors_set_the_reference_error_bits():
     h = _obj()
     cases = [
