@@ -34,8 +34,16 @@ def main():
     nz = nzl * world
     code, c, solver, tol = {"lap7": (7, (1.0, 1.0, 1.0), "pcg", 1e-6), "lap27": (27, (1.0, 1.0, 0.01), "pcg", 1e-6),
                             "convdif": (107, (1e-3, 1.0, 0.1), "gmres", 1e-8)}[kind]
-    n_loc = nx * ny * nzl
-    rs, re = rank * n_loc, (rank + 1) * n_loc - 1
+    n_tot = nx * ny * nz
+    if os.environ.get("MPCHECK_RAGGED") == "1":
+        # uneven slabs that cut through grid planes: rank r owns rows [cuts[r], cuts[r+1])
+        w = np.array([1.0 + 0.7 * ((r * 37) % 5) for r in range(world)])
+        cuts = np.concatenate([[0], np.floor(np.cumsum(w) / w.sum() * n_tot).astype(np.int64)])
+        cuts[-1] = n_tot
+    else:
+        cuts = np.arange(world + 1, dtype=np.int64) * (nx * ny * nzl)
+    rs, re = int(cuts[rank]), int(cuts[rank + 1]) - 1
+    n_loc = re - rs + 1
     opts = {"general": {"statistics": False}, "solver": {solver: {"relative_tol": tol, "max_iter": 100}},
             "preconditioner": "amg"}
     with driver.HypreDrive(options=opts) as drv:
@@ -43,8 +51,11 @@ def main():
         drv.solve()
         x_loc = drv.get_solution()
         iters, conv = drv.last_iterations, drv.last_converged
-    xs = [torch.zeros(n_loc, dtype=torch.float64, device="cuda") for _ in range(world)]
-    dist.all_gather(xs, torch.from_numpy(x_loc).cuda())
+    xs = [torch.zeros(int(cuts[r + 1] - cuts[r]), dtype=torch.float64, device="cuda") for r in range(world)]
+    for r in range(world):                       # uneven pieces: one broadcast per owner
+        if r == rank:
+            xs[r].copy_(torch.from_numpy(x_loc).cuda())
+        dist.broadcast(xs[r], r)
     ok = True
     if rank == 0:
         from oracle import oracle as O

@@ -30,7 +30,10 @@ def _run(world, args, env_extra=None):
     # wait on the neighbours' flags), and the same layout with the separate correction kernel
     ("lap7", ("16", "16", "10"), "40", "sell-fused"), ("lap27", ("8", "8", "6"), "30", "sell-fused"),
     ("convdif", ("16", "8", "6"), "40", "sell-fused"), ("lap7", ("16", "16", "10"), "40", "sell-unfused"),
-    ("lap7", ("12", "11", "6"), "40", "sell-nccl")])
+    ("lap7", ("12", "11", "6"), "40", "sell-nccl"),
+    # uneven row slabs that cut through grid planes (asymmetric halo sizes), all three exchange paths
+    ("lap7", ("14", "9", "7"), "40", "ragged"), ("lap27", ("8", "8", "6"), "30", "ragged-sell"),
+    ("convdif", ("16", "8", "6"), "40", "ragged-nccl")])
 def test_two_rank_solve_matches_oracle(gpu, kind, dims, rep, share):
     if gpu.device_count() < 2:
         pytest.skip("needs two GPUs")
@@ -39,6 +42,14 @@ def test_two_rank_solve_matches_oracle(gpu, kind, dims, rep, share):
         env["HDK_SETUP_SHARE"] = "0"
     elif share == "nccl":
         env["HDK_HALO_IPC"] = "0"
+    elif share.startswith("ragged"):
+        env["MPCHECK_RAGGED"] = "1"
+        env["HDK_SHARE_MIN_ROWS"] = "0"
+        if share == "ragged-sell":
+            env["HDK_SELL_MIN_ROWS"] = "0"
+            env["HDK_SELL_MIN_ROWS_DIST"] = "0"
+        if share == "ragged-nccl":
+            env["HDK_HALO_IPC"] = "0"
     elif share.startswith("sell"):
         env["HDK_SELL_MIN_ROWS"] = "0"
         env["HDK_SELL_MIN_ROWS_DIST"] = "0"
