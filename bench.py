@@ -58,7 +58,7 @@ preconditioner:
 # workload (256^3 7-point rows per GPU), from the `ncu --set full` capture summarised under
 # profiles/ (see profiles/README.md); None when no capture exists for the selected kernel
 NCU_TRAFFIC_BYTES = {"k_spmv_sell": 1.7437e9 + 0.1171e9, "k_spmv_tma": 1.7404e9 + 0.1303e9}
-CPU_SAMPLE_EDGE = 160  # cube edge of the bounded CPU sample (about 10-30 s of work on ~8 cores)
+CPU_SAMPLE_EDGE = int(os.environ.get("HDK_BENCH_CPU_EDGE", "160"))  # cube edge of the bounded CPU sample (about 10-30 s of work on ~8 cores)
 
 
 def measured_peaks():

@@ -218,3 +218,21 @@ def test_sliced_ell_kernel_register_budget():
         limit = 32 if (dot == "0" and offd == "0") else 40
         assert int(reg) <= limit, (mode, dot, offd, reg)
         assert int(stack) <= 8, (mode, dot, offd, stack)
+
+
+def test_bench_reference_arm_contract():
+    """`bench.py --impl reference` (the restated reference on the host cores) prints one JSON line
+    with the contract's keys; a small sample keeps the test short."""
+    import json
+    import subprocess
+    import sys
+    env = dict(os.environ, HDK_BENCH_CPU_EDGE="40")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+                       capture_output=True, text=True, env=env, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    line = json.loads(r.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["unit"] == "DOF*iters/s" and line["value"] > 0
+    assert line["higher_is_better"] is True and line["vs_baseline"] is None and line["dtype"] == "f64"
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0
+    assert "workload" in line["config"]
