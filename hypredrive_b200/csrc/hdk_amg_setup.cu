@@ -39,6 +39,8 @@ static void stage_mark(const char *name, int level)
    g_t_last = t;
 }
 
+void setup_stage_mark(const char *name, int level) { stage_mark(name, level); }
+
 static const int64_t SCRATCH_BUDGET = (int64_t)1 << 30; // hash slots per chunk (4-8 GB)
 
 // ---- work sharing of the replicated multi-rank setup --------------------------------------
@@ -112,7 +114,7 @@ static int check_fits_int32(const int *cnt, int n, const char *what)
    return HDK_OK;
 }
 
-static int exclusive_scan_i64(const int *in, int64_t *out, int n)
+int exclusive_scan_i64(const int *in, int64_t *out, int n)
 {
    k_cast_i64<<<cdiv(n, 256), 256, 0, g.stream>>>(in, out, n);
    HDK_LAUNCH_CHECK();
@@ -283,12 +285,9 @@ __global__ void k_strength(const int *rp, const int *col, const double *val, con
    if (!FILL) cnt[i] = c;
 }
 
-static int build_strength(const hdk_csr_s &A, double theta, double mrs, DevCSR &S)
+int build_strength_csr(const DevCSR &D, const int *orp, const double *ov, double theta, double mrs, DevCSR &S)
 {
-   const DevCSR &D = A.diag;
-   int           n = D.nrows;
-   const int    *orp = A.offd.nnz > 0 ? A.offd.rowptr : nullptr;
-   const double *ov  = A.offd.nnz > 0 ? A.offd.val : nullptr;
+   int n = D.nrows;
    int *cnt, *srp;
    HDK_TRY(dalloc(&cnt, (size_t)n + 1));
    HDK_TRY(dalloc(&srp, (size_t)n + 1));
@@ -305,6 +304,13 @@ static int build_strength(const hdk_csr_s &A, double theta, double mrs, DevCSR &
    k_strength<true><<<cdiv(n + 1, 256), 256, 0, g.stream>>>(D.rowptr, D.col, D.val, orp, ov, n, theta, mrs, nullptr, srp, S.col);
    HDK_LAUNCH_CHECK();
    return HDK_OK;
+}
+
+static int build_strength(const hdk_csr_s &A, double theta, double mrs, DevCSR &S)
+{
+   const int    *orp = A.offd.nnz > 0 ? A.offd.rowptr : nullptr;
+   const double *ov  = A.offd.nnz > 0 ? A.offd.val : nullptr;
+   return build_strength_csr(A.diag, orp, ov, theta, mrs, S);
 }
 
 // =====================================================================================
@@ -356,10 +362,11 @@ __global__ void k_pmis_mark(int n, int *cf, const double *measure)
    if (i < n && cf[i] == 0 && measure[i] > 1.0) cf[i] = 1;
 }
 
-__global__ void k_pmis_elim(const int *srp, const int *scol, int n, int *cf, const double *measure)
+__global__ void k_pmis_elim(const int *srp, const int *scol, int n, int *cf, const double *measure, int row0)
 {
    int i = blockIdx.x * blockDim.x + threadIdx.x;
    if (i >= n) return;
+   i += row0; // rows [row0, row0 + n)
    double mi = measure[i];
    if (!(mi > 1.0)) return;
    for (int k = srp[i]; k < srp[i + 1]; k++)
@@ -374,12 +381,13 @@ __global__ void k_pmis_elim(const int *srp, const int *scol, int n, int *cf, con
    }
 }
 
-__global__ void k_pmis_set(const int *srp, const int *scol, int n, int *cf, double *measure, int *remaining)
+__global__ void k_pmis_set(const int *srp, const int *scol, int n, int *cf, double *measure, int *remaining, int row0)
 {
    int  i = blockIdx.x * blockDim.x + threadIdx.x;
    bool undecided = false;
    if (i < n)
    {
+      i += row0; // rows [row0, row0 + n)
       double mi = measure[i];
       if (mi > 0.0) // still in the graph
       {
@@ -418,15 +426,66 @@ static int run_pmis(const DevCSR &S, int seed, int64_t goff, int *cf, double *me
       HDK_CUDA(cudaMemsetAsync(rem, 0, sizeof(int), g.stream));
       k_pmis_mark<<<cdiv(n, 256), 256, 0, g.stream>>>(n, cf, measure);
       HDK_LAUNCH_CHECK();
-      k_pmis_elim<<<cdiv(n, 256), 256, 0, g.stream>>>(S.rowptr, S.col, n, cf, measure);
+      k_pmis_elim<<<cdiv(n, 256), 256, 0, g.stream>>>(S.rowptr, S.col, n, cf, measure, 0);
       HDK_LAUNCH_CHECK();
-      k_pmis_set<<<cdiv(n, 256), 256, 0, g.stream>>>(S.rowptr, S.col, n, cf, measure, rem);
+      k_pmis_set<<<cdiv(n, 256), 256, 0, g.stream>>>(S.rowptr, S.col, n, cf, measure, rem, 0);
       HDK_LAUNCH_CHECK();
       HDK_CUDA(cudaMemcpyAsync(&hrem, rem, sizeof(int), cudaMemcpyDeviceToHost, g.stream));
       HDK_CUDA(cudaStreamSynchronize(g.stream));
       iters++;
    }
    if (iters_out) *iters_out = iters;
+   return HDK_OK;
+}
+
+// stage launchers used by the distributed driver (hdk_amg_dist.cu): same kernels, rows [row0, row0+n)
+__global__ void k_count_cols_rows(const int *srp, const int *scol, int row0, int n, int *cnt)
+{
+   int i = blockIdx.x * blockDim.x + threadIdx.x;
+   if (i >= n) return;
+   for (int k = srp[row0 + i]; k < srp[row0 + i + 1]; k++) atomicAdd(cnt + scol[k], 1);
+}
+int pmis_count_cols(const DevCSR &S, int row0, int n, int *cnt)
+{
+   if (n <= 0) return HDK_OK;
+   k_count_cols_rows<<<cdiv(n, 256), 256, 0, g.stream>>>(S.rowptr, S.col, row0, n, cnt);
+   HDK_LAUNCH_CHECK();
+   return HDK_OK;
+}
+int pmis_measure(const int *cnt, int n, int seed, int64_t goff, double *measure)
+{
+   if (n <= 0) return HDK_OK;
+   uint32_t s0 = seed < 1 ? 1u : (seed >= 2147483647 ? 2147483646u : (uint32_t)seed);
+   k_measure<<<cdiv(n, 256), 256, 0, g.stream>>>(cnt, n, s0, goff, measure);
+   HDK_LAUNCH_CHECK();
+   return HDK_OK;
+}
+int pmis_init(const DevCSR &S, int row0, int n, int *cf, double *measure)
+{
+   if (n <= 0) return HDK_OK;
+   k_pmis_init<<<cdiv(n, 256), 256, 0, g.stream>>>(S.rowptr + row0, n, cf + row0, measure + row0);
+   HDK_LAUNCH_CHECK();
+   return HDK_OK;
+}
+int pmis_mark(int n, int *cf, const double *measure)
+{
+   if (n <= 0) return HDK_OK;
+   k_pmis_mark<<<cdiv(n, 256), 256, 0, g.stream>>>(n, cf, measure);
+   HDK_LAUNCH_CHECK();
+   return HDK_OK;
+}
+int pmis_elim(const DevCSR &S, int row0, int n, int *cf, const double *measure)
+{
+   if (n <= 0) return HDK_OK;
+   k_pmis_elim<<<cdiv(n, 256), 256, 0, g.stream>>>(S.rowptr, S.col, n, cf, measure, row0);
+   HDK_LAUNCH_CHECK();
+   return HDK_OK;
+}
+int pmis_set(const DevCSR &S, int row0, int n, int *cf, double *measure, int *remaining)
+{
+   if (n <= 0) return HDK_OK;
+   k_pmis_set<<<cdiv(n, 256), 256, 0, g.stream>>>(S.rowptr, S.col, n, cf, measure, remaining, row0);
+   HDK_LAUNCH_CHECK();
    return HDK_OK;
 }
 
@@ -919,8 +978,9 @@ static int interp_truncate(DevCSR &P, double trunc_factor, int max_elmts)
    return HDK_OK;
 }
 
-static int build_interp(const DevCSR &A, const DevCSR &S, int *cf, const int *f2c, int nc, int max_elmts_in, double trunc_factor,
-                        DevCSR &P)
+// rows [row_lo, row_hi) only (row_lo < 0: all rows, or this rank's share of a work-shared global level)
+int build_interp(const DevCSR &A, const DevCSR &S, int *cf, const int *f2c, int nc, int max_elmts_in, double trunc_factor,
+                 DevCSR &P, int row_lo, int row_hi)
 {
    // with a truncation factor the rows are built complete and truncated by the post-pass
    const int max_elmts = (trunc_factor > 0.0) ? 0 : max_elmts_in;
@@ -940,7 +1000,8 @@ static int build_interp(const DevCSR &A, const DevCSR &S, int *cf, const int *f2
    // rows outside it keep slow = cnt = rowlen = 0, which every later kernel skips
    int lo, hi;
    share_range(n, lo, hi);
-   if (share_on(n))
+   if (row_lo >= 0) { lo = row_lo; hi = row_hi; }
+   if (share_on(n) || lo != 0 || hi != n)
    {
       HDK_CUDA(cudaMemsetAsync(slow, 0, sizeof(int) * ((size_t)n + 1), g.stream));
       HDK_CUDA(cudaMemsetAsync(cnt, 0, sizeof(int) * ((size_t)n + 1), g.stream));
@@ -1063,7 +1124,7 @@ __global__ void k_rowptr_from_sorted(const int *keys, int nnz, int nrows, int *r
    rp[r] = lo;
 }
 
-static int csr_transpose(const DevCSR &A, DevCSR &T)
+int csr_transpose(const DevCSR &A, DevCSR &T)
 {
    int nnz = A.nnz;
    HDK_TRY(csr_alloc(T, A.ncols, A.nrows, nnz, A.val != nullptr));
@@ -1330,7 +1391,8 @@ __global__ void k_rap_fill(const int *rrp, const int *rcol, const double *rval, 
    }
 }
 
-static int build_rap(const DevCSR &R, const DevCSR &A, const DevCSR &P, DevCSR &C)
+// coarse rows [row_lo, row_hi) only (row_lo < 0: all rows, or this rank's share of a work-shared global level)
+int build_rap(const DevCSR &R, const DevCSR &A, const DevCSR &P, DevCSR &C, int row_lo, int row_hi)
 {
    stage_mark(nullptr, -1);
    int nc = R.nrows, n = A.nrows;
@@ -1346,7 +1408,8 @@ static int build_rap(const DevCSR &R, const DevCSR &A, const DevCSR &P, DevCSR &
    // this rank's share of the coarse rows (all of them unless the multi-rank setup shares the work)
    int lo, hi;
    share_range(nc, lo, hi);
-   if (share_on(nc)) HDK_CUDA(cudaMemsetAsync(cnt, 0, sizeof(int) * ((size_t)nc + 1), g.stream));
+   if (row_lo >= 0) { lo = row_lo; hi = row_hi; }
+   if (share_on(nc) || lo != 0 || hi != nc) HDK_CUDA(cudaMemsetAsync(cnt, 0, sizeof(int) * ((size_t)nc + 1), g.stream));
    // pass 1a: exact row lengths by the warp kernel (rows longer than RW_LIMIT are flagged -1)
    k_rap_warp<false, RW_CAP><<<cdiv(hi - lo, RW_WARPS), 32 * RW_WARPS, (size_t)RW_WARPS * RW_CAP * sizeof(int), g.stream>>>(
       R.rowptr, R.col, R.val, A.rowptr, A.col, A.val, P.rowptr, P.col, P.val, hi, cnt, nullptr, nullptr, nullptr, lo, 0, 0);
@@ -1600,7 +1663,7 @@ static int build_dense_inverse(const DevCSR &A, double **inv)
 }
 
 // wrap a rank-local DevCSR as a ParCSR object with an empty offd block
-static hdk_csr_s *wrap_local(DevCSR &D, int64_t grows)
+hdk_csr_s *wrap_local(DevCSR &D, int64_t grows)
 {
    hdk_csr_s *A  = new hdk_csr_s();
    A->row_start  = 0; A->row_end = (int64_t)D.nrows - 1; A->global_rows = grows; A->global_nnz = D.nnz;
@@ -1609,7 +1672,7 @@ static hdk_csr_s *wrap_local(DevCSR &D, int64_t grows)
    return A;
 }
 
-static void destroy_local(hdk_csr_s *A)
+void destroy_local(hdk_csr_s *A)
 {
    if (!A) return;
    csr_free(A->diag); csr_free(A->offd);
@@ -1650,6 +1713,7 @@ int hdk_amg_destroy(hdk_amg *M)
          if (L.l1_up != L.l1_down) dfree(L.l1_up);
          dfree(L.l1_down);
          dfree(L.u); dfree(L.f); dfree(L.t);
+         for (int w = 0; w < 2; w++) { dfree(L.dbg_ip[w]); dfree(L.dbg_col[w]); dfree(L.dbg_val[w]); }
       }
       dfree(M->ge_inv); dfree(M->full_f); dfree(M->full_u);
    }
@@ -1660,7 +1724,7 @@ int hdk_amg_destroy(hdk_amg *M)
 
 // per-level solve data: smoother diagonals, work vectors, (two-stage GS) lower triangles, and the
 // algorithmic byte count of one V-cycle
-static int finalize_levels(hdk_amg_s *M, const hdk_amg_params *prm, int64_t live_max_rows = -1)
+int finalize_levels(hdk_amg_s *M, const hdk_amg_params *prm, int64_t live_max_rows)
 {
    int    rc = HDK_OK;
    double bytes = 0.0;
@@ -1700,8 +1764,8 @@ static int finalize_levels(hdk_amg_s *M, const hdk_amg_params *prm, int64_t live
 
 // live_max_rows >= 0: the hierarchy is the global one of a multi-rank setup; levels with more
 // rows are only sliced into slabs afterwards, so they get no SpMV analysis and no solve data
-static int setup_serial(const hdk_csr_s *A0, const hdk_amg_params *prm, hdk_amg_s **out, bool keep_f2c,
-                        int64_t live_max_rows = -1)
+int setup_serial(const hdk_csr_s *A0, const hdk_amg_params *prm, hdk_amg_s **out, bool keep_f2c,
+                 int64_t live_max_rows)
 {
    hdk_amg_s *M = new hdk_amg_s();
    M->prm       = *prm;
@@ -1745,13 +1809,13 @@ static int setup_serial(const hdk_csr_s *A0, const hdk_amg_params *prm, hdk_amg_
       dfree(flag);
       if (nc == 0 || nc == n || nc < prm->min_coarse_size) { dfree(f2c); break; }
       DevCSR P, R, C;
-      rc = build_interp(A.diag, L.S, L.cf, f2c, nc, prm->max_nnz_row, prm->trunc_factor, P);
+      rc = build_interp(A.diag, L.S, L.cf, f2c, nc, prm->max_nnz_row, prm->trunc_factor, P, -1, -1);
       stage_mark("interp", level);
       if (keep_f2c) L.f2c = f2c; else dfree(f2c);
       if (rc) break;
       if ((rc = csr_transpose(P, R))) break;
       stage_mark("transpose", level);
-      if ((rc = build_rap(R, A.diag, P, C))) break;
+      if ((rc = build_rap(R, A.diag, P, C, -1, -1))) break;
       stage_mark("rap", level);
       C.coarse_op = true;
       if (live_max_rows < 0 || n <= live_max_rows)
@@ -1881,8 +1945,7 @@ static int setup_distributed(const hdk_csr_s *A0, const hdk_amg_params *prm, hdk
       HDK_TRY(bcast_bytes(gcj + koff[(size_t)r], sizeof(int64_t) * (size_t)nnz_all[(size_t)r], r));
       HDK_TRY(bcast_bytes(gva + koff[(size_t)r], sizeof(double) * (size_t)nnz_all[(size_t)r], r));
    }
-   static int64_t rep_rows = -1;
-   if (rep_rows < 0) { const char *e = getenv("HDK_REPLICATE_ROWS"); rep_rows = e ? atoll(e) : 262144; }
+   const int64_t rep_rows = tune_replicate_rows();
    hdk_csr_s *G = nullptr;
    int rc = parcsr_build(0, N - 1, 0, N - 1, N, N, true, false, false, gip, gcj, gva, &G, N <= rep_rows);
    dfree(gip); dfree(gcj); dfree(gva);
@@ -1959,7 +2022,7 @@ static int setup_distributed(const hdk_csr_s *A0, const hdk_amg_params *prm, hdk
       M->tail_n   = Mg->lev[(size_t)tail_level].n;
       M->tail_off = starts[(size_t)tail_level][(size_t)me];
       M->tail_cnt = starts[(size_t)tail_level][(size_t)me + 1] - M->tail_off;
-      rc = finalize_levels(M, prm);
+      rc = finalize_levels(M, prm, -1);
       double vb = M->vcycle_bytes;
       // per-rank byte count: distributed levels (local) + replicated tail
       for (int l = tail_level; l < nl; l++)
@@ -2003,17 +2066,31 @@ int hdk_amg_setup(const hdk_csr *A0, const hdk_amg_params *prm, hdk_amg **out)
    if (prm->interp_type != 6) return set_error(HDK_ERR_UNSUPPORTED, "interpolation type %d: only extended+i (6) has a device kernel", prm->interp_type);
    if (prm->trunc_factor < 0.0 || prm->trunc_factor >= 1.0) return set_error(HDK_ERR_INVALID, "interpolation trunc_factor must be in [0, 1)");
    g_timing = getenv("HDK_SETUP_TIMING") && atoi(getenv("HDK_SETUP_TIMING")) == 1;
-   if (g.nranks > 1) return setup_distributed(A0, prm, out);
-   return setup_serial(A0, prm, out, false);
+   // row-distributed setup (hdk_amg_dist.cu); HDK_SETUP_REPLICATED=1 selects the round-1 scheme that
+   // rebuilds the global hierarchy on every rank (kept for comparison)
+   const bool replicated = getenv("HDK_SETUP_REPLICATED") && atoi(getenv("HDK_SETUP_REPLICATED")) == 1;
+   const bool force_dist = getenv("HDK_SETUP_DIST_FORCE") && atoi(getenv("HDK_SETUP_DIST_FORCE")) == 1;
+   if (g.nranks > 1 && replicated) return setup_distributed(A0, prm, out);
+   if (g.nranks > 1 || (force_dist && A0->orig_indptr)) return setup_distributed_rows(A0, prm, out);
+   return setup_serial(A0, prm, out, false, -1);
 }
 
 int hdk_amg_num_levels(const hdk_amg *M) { return M ? M->nlev + (M->tail ? M->tail->nlev - M->tail_level : 0) : 0; }
+int hdk_amg_num_dist_levels(const hdk_amg *M) { return (M && M->tail) ? M->nlev : 0; } // N > 1: row-distributed levels
 double hdk_amg_operator_complexity(const hdk_amg *M) { return M ? M->op_complexity : 0.0; }
 double hdk_amg_vcycle_bytes(const hdk_amg *M) { return M ? M->vcycle_bytes : 0.0; }
 
+// levels [0, nlev) are this rank's slabs of the distributed levels; the following ones live in the
+// replicated tail hierarchy
+static const hdk_amg_s *resolve_level(const hdk_amg *M, int &level)
+{
+   if (M && M->tail && level >= M->nlev) { level = level - M->nlev + M->tail_level; return M->tail; }
+   return M;
+}
+
 int hdk_amg_level_info(const hdk_amg *M, int level, int64_t *rows, int64_t *nnz_A, int64_t *nnz_P)
 {
-   if (M && M->tail && level >= M->nlev) return hdk_amg_level_info(M->tail, level, rows, nnz_A, nnz_P);
+   M = resolve_level(M, level);
    if (!M || level < 0 || level >= M->nlev) return set_error(HDK_ERR_INVALID, "level out of range");
    const AmgLevel &L = M->lev[(size_t)level];
    if (rows) *rows = L.n;
@@ -2025,6 +2102,7 @@ int hdk_amg_level_info(const hdk_amg *M, int level, int64_t *rows, int64_t *nnz_
 int hdk_amg_get_matrix(const hdk_amg *M, int level, int which, int32_t *rowptr_h, int32_t *col_h, double *val_h)
 {
    HDK_TRY(require_init());
+   M = resolve_level(M, level);
    if (!M || level < 0 || level >= M->nlev) return set_error(HDK_ERR_INVALID, "level out of range");
    const AmgLevel &L = M->lev[(size_t)level];
    const DevCSR   *D = nullptr;
@@ -2048,16 +2126,19 @@ static int get_level_array(const hdk_amg *M, int level, const void *src, size_t 
 }
 int hdk_amg_get_cf(const hdk_amg *M, int level, int32_t *cf_h)
 {
+   M = resolve_level(M, level);
    if (!M || level < 0 || level >= M->nlev) return set_error(HDK_ERR_INVALID, "level out of range");
    return get_level_array(M, level, M->lev[(size_t)level].cf, sizeof(int) * (size_t)M->lev[(size_t)level].n, cf_h);
 }
 int hdk_amg_get_measure(const hdk_amg *M, int level, double *m_h)
 {
+   M = resolve_level(M, level);
    if (!M || level < 0 || level >= M->nlev) return set_error(HDK_ERR_INVALID, "level out of range");
    return get_level_array(M, level, M->lev[(size_t)level].measure, sizeof(double) * (size_t)M->lev[(size_t)level].n, m_h);
 }
 int hdk_amg_get_l1(const hdk_amg *M, int level, double *l1_h)
 {
+   M = resolve_level(M, level);
    if (!M || level < 0 || level >= M->nlev) return set_error(HDK_ERR_INVALID, "level out of range");
    return get_level_array(M, level, M->lev[(size_t)level].l1_down, sizeof(double) * (size_t)M->lev[(size_t)level].n, l1_h);
 }

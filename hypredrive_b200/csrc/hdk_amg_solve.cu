@@ -283,9 +283,10 @@ int hdk_time_kernel(const hdk_csr *A, hdk_amg *M, int kernel, int reps, double *
    if (!A) return set_error(HDK_ERR_INVALID, "null matrix");
    const int64_t n = A->diag.nrows;
    const double  nnz = (double)A->diag.nnz + A->offd.nnz;
-   double *x, *y, *b, *d;
+   double *x, *y, *b, *d, *z;
    HDK_TRY(dalloc(&x, (size_t)n + 8)); HDK_TRY(dalloc(&y, (size_t)n + 8));
    HDK_TRY(dalloc(&b, (size_t)n + 8)); HDK_TRY(dalloc(&d, (size_t)n + 8));
+   HDK_TRY(dalloc(&z, (size_t)n + 8));
    HDK_TRY(hdk_vec_random(x, n, A->row_start, 1));
    HDK_TRY(hdk_vec_random(b, n, A->row_start, 2));
    HDK_TRY(vec_fill(d, 6.0, n));
@@ -305,10 +306,14 @@ int hdk_time_kernel(const hdk_csr *A, hdk_amg *M, int kernel, int reps, double *
             case 0: rc = parcsr_matvec(*A, SPMV_SET, a); by = 12.0 * nnz + 4.0 * (n + 1) + 16.0 * n; break;
             case 1: rc = parcsr_matvec(*A, SPMV_JACOBI, a); by = 12.0 * nnz + 4.0 * (n + 1) + 32.0 * n; break;
             case 2: rc = parcsr_matvec(*A, SPMV_RESIDUAL, a); by = 12.0 * nnz + 4.0 * (n + 1) + 24.0 * n; break;
-            case 3:
+            case 3: // the variant the PCG solve runs: x/r update + <r,r> + the V-cycle's first sweep z0 = (w r)/l1
                rc = vec_fill(g.dscal + S_ALPHA, 1e-3, 1);
-               if (rc == HDK_OK) rc = pcg_update_xr(y, b, x, d, n, g.dscal);
-               by = 48.0 * n; break;
+               if (rc == HDK_OK) rc = pcg_update_xr(y, b, x, d, n, g.dscal, FIN_IPROD, nullptr, z, d, 1.0);
+               by = 64.0 * n; break;
+            case 5: // p = z + beta p
+               rc = vec_fill(g.dscal + S_BETA, 0.5, 1);
+               if (rc == HDK_OK) rc = pcg_update_p(y, x, n, g.dscal);
+               by = 24.0 * n; break;
             case 4:
                if (!M) rc = set_error(HDK_ERR_INVALID, "V-cycle timing needs a hierarchy");
                else { rc = amg_precond(M, b, y, FIN_NONE, nullptr); by = M->vcycle_bytes; }
@@ -326,7 +331,7 @@ int hdk_time_kernel(const hdk_csr *A, hdk_amg *M, int kernel, int reps, double *
       if (avg_ms) *avg_ms = (double)ms / (reps > 0 ? reps : 1);
       if (bytes) *bytes = by;
    }
-   dfree(x); dfree(y); dfree(b); dfree(d);
+   dfree(x); dfree(y); dfree(b); dfree(d); dfree(z);
    return rc;
 }
 

@@ -207,6 +207,39 @@ int allgatherv_bytes(void *base_d, const int64_t *offs)
    return HDK_OK;
 }
 
+int allreduce_i32_dev(int *buf_d, int count)
+{
+   if (g.nranks <= 1) return HDK_OK;
+   HDK_NCCL(nccl.AllReduce(buf_d, buf_d, (size_t)count, NCCL_INT32, NCCL_SUM, (ncclComm_p)g.nccl, g.stream));
+   return HDK_OK;
+}
+
+// personalised all-to-all of byte segments on the compute stream: segment [soff[r], soff[r+1]) of
+// `send` goes to rank r and lands in [roff[q], roff[q+1]) of `recv` on rank q's side for sender q.
+// Both sides know every size (count matrices are exchanged first), empty pairs are skipped, the
+// segment to oneself is a device copy.
+int alltoallv_bytes(const void *send_d, const int64_t *soff, void *recv_d, const int64_t *roff)
+{
+   const char *sb = static_cast<const char *>(send_d);
+   char       *rb = static_cast<char *>(recv_d);
+   const int   me = g.rank;
+   if (soff[me + 1] - soff[me] != roff[me + 1] - roff[me])
+      return set_error(HDK_ERR_COMM, "alltoallv: self segment sizes differ");
+   if (soff[me + 1] > soff[me])
+      HDK_CUDA(cudaMemcpyAsync(rb + roff[me], sb + soff[me], (size_t)(soff[me + 1] - soff[me]), cudaMemcpyDeviceToDevice, g.stream));
+   if (g.nranks <= 1) return HDK_OK;
+   HDK_NCCL(nccl.GroupStart());
+   for (int r = 0; r < g.nranks; r++)
+   {
+      if (r == me) continue;
+      size_t sbytes = (size_t)(soff[r + 1] - soff[r]), rbytes = (size_t)(roff[r + 1] - roff[r]);
+      if (sbytes) HDK_NCCL(nccl.Send(sb + soff[r], sbytes, 0 /* ncclInt8 */, r, (ncclComm_p)g.nccl, g.stream));
+      if (rbytes) HDK_NCCL(nccl.Recv(rb + roff[r], rbytes, 0 /* ncclInt8 */, r, (ncclComm_p)g.nccl, g.stream));
+   }
+   HDK_NCCL(nccl.GroupEnd());
+   return HDK_OK;
+}
+
 int allreduce_max_dev(double *buf_d, int count)
 {
    if (g.nranks <= 1) return HDK_OK;

@@ -197,7 +197,8 @@ int parcsr_build(int64_t rs, int64_t re, int64_t cs, int64_t ce, int64_t grows, 
       HDK_CUDA(cudaStreamSynchronize(g.stream));
    }
    A->global_nnz = (int64_t)loc;
-   if (keep_orig && distributed && g.nranks > 1)
+   static const bool force_dist = getenv("HDK_SETUP_DIST_FORCE") && atoi(getenv("HDK_SETUP_DIST_FORCE")) == 1;
+   if (keep_orig && distributed && (g.nranks > 1 || force_dist))
    {
       int64_t nnz = (int64_t)tot[0] + tot[1];
       HDK_TRY(dalloc(&A->orig_indptr, (size_t)n + 1));

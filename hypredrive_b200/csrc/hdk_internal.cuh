@@ -114,6 +114,7 @@ void csr_free(DevCSR &A);
 int  csr_analyze(DevCSR &A);
 int  tune_set(const char *key, double value);
 bool tune_amg_keep_debug();
+int64_t tune_replicate_rows();
 
 // epilogue selectors of the fused SpMV family (see hdk_spmv.cu)
 enum SpmvMode
@@ -288,6 +289,9 @@ int parcsr_build(int64_t rs, int64_t re, int64_t cs, int64_t ce, int64_t grows, 
 int allreduce_max_dev(double *buf_d, int count);
 int bcast_bytes(void *buf_d, size_t bytes, int root);                 // NCCL broadcast on the compute stream
 int allgather_i64_host(int64_t mine, std::vector<int64_t> &all);
+int allgather_i32_host(const int *mine, int cnt, std::vector<int> &all); // all[r*cnt + i]
+int allreduce_i32_dev(int *buf_d, int count);
+int alltoallv_bytes(const void *send_d, const int64_t *soff /* nranks+1 */, void *recv_d, const int64_t *roff /* nranks+1 */);
 int allgatherv_bytes(void *base_d, const int64_t *byte_offs /* nranks+1 */); // in place, compute stream
 void halo_plan_free(HaloPlan &H);
 IpcRecvArgs halo_recv_args(const hdk_csr_s &A, const double **xh); // after halo_exchange_begin

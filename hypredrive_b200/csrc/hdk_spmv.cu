@@ -40,6 +40,7 @@ struct Tune
    double sell_min_avg  = 0.0;      // HDK_SELL_MIN_AVG     ... and more than this many non-zeros per row
    double sell_sort     = 1;        // HDK_SELL_SORT        sort the columns of coarse operators in the slices
    double amg_keep_debug = 0;       // HDK_AMG_KEEP_DEBUG   keep S and the PMIS measures of every level (introspection)
+   double replicate_rows = 262144;  // HDK_REPLICATE_ROWS   N > 1: levels with at most this many global rows form the replicated tail
    bool   env_read      = false;
 };
 static Tune tune;
@@ -48,6 +49,7 @@ static const struct { const char *key, *env; double Tune::*field; } tune_keys[] 
    {"spmv_lpr", "HDK_SPMV_LPR", &Tune::lpr},                   {"sell_min_rows", "HDK_SELL_MIN_ROWS", &Tune::sell_min_rows},
    {"sell_min_rows_dist", "HDK_SELL_MIN_ROWS_DIST", &Tune::sell_min_rows_dist},
    {"amg_keep_debug", "HDK_AMG_KEEP_DEBUG", &Tune::amg_keep_debug},
+   {"replicate_rows", "HDK_REPLICATE_ROWS", &Tune::replicate_rows},
    {"sell_min_avg", "HDK_SELL_MIN_AVG", &Tune::sell_min_avg},  {"sell_sort", "HDK_SELL_SORT", &Tune::sell_sort}};
 static Tune &tunables()
 {
@@ -63,6 +65,7 @@ static Tune &tunables()
    return tune;
 }
 bool tune_amg_keep_debug() { return tunables().amg_keep_debug != 0.0; }
+int64_t tune_replicate_rows() { return (int64_t)tunables().replicate_rows; }
 
 int tune_set(const char *key, double value)
 {

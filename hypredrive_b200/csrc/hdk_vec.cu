@@ -112,6 +112,10 @@ __device__ __forceinline__ double pcg_xr_row(double alpha, double xi, double pi,
    return rn * rn;
 }
 
+// 128-bit accesses: each thread owns two consecutive rows per trip (ld/st.global.v2.f64) and runs
+// two trips per loop iteration with all loads issued before the first store, i.e. 4 rows x 5 input
+// streams = 20 independent 16-byte loads in flight per thread.  `n2` = number of row pairs; an odd
+// last row is handled by the scalar tail of block 0.
 template <bool PREFILL>
 __global__ void __launch_bounds__(VT) k_pcg_xr(double *x, double *r, const double *p, const double *s, int64_t n,
                                                double *partials, unsigned *ticket, double *scal, int fin, double *fin_out,
@@ -121,19 +125,104 @@ __global__ void __launch_bounds__(VT) k_pcg_xr(double *x, double *r, const doubl
    __shared__ int    flag;
    const double      alpha = scal[S_ALPHA];
    double            acc   = 0.0;
-   const int64_t     stride = (int64_t)gridDim.x * VT;
+   const int64_t     n2 = n >> 1, stride = (int64_t)gridDim.x * VT;
+   double2          *x2 = reinterpret_cast<double2 *>(x), *r2 = reinterpret_cast<double2 *>(r);
+   const double2    *p2 = reinterpret_cast<const double2 *>(p), *s2 = reinterpret_cast<const double2 *>(s);
+   double2          *z2 = reinterpret_cast<double2 *>(z0);
+   const double2    *d2 = reinterpret_cast<const double2 *>(zd);
    int64_t           i = blockIdx.x * (int64_t)VT + threadIdx.x;
-   for (; i + stride < n; i += 2 * stride)
+   for (; i + stride < n2; i += 2 * stride)
    {
       const int64_t j = i + stride;
-      const double  xi = x[i], pi = p[i], ri = r[i], si = s[i];
-      const double  xj = x[j], pj = p[j], rj = r[j], sj = s[j];
-      double        di = 0.0, dj = 0.0;
-      if (PREFILL) { di = zd[i]; dj = zd[j]; }
-      acc += pcg_xr_row<PREFILL>(alpha, xi, pi, ri, si, di, zw, x, r, z0, i);
-      acc += pcg_xr_row<PREFILL>(alpha, xj, pj, rj, sj, dj, zw, x, r, z0, j);
+      const double2 xi = x2[i], pi = p2[i], ri = r2[i], si = s2[i];
+      const double2 xj = x2[j], pj = p2[j], rj = r2[j], sj = s2[j];
+      double2       di = make_double2(0.0, 0.0), dj = di;
+      if (PREFILL) { di = d2[i]; dj = d2[j]; }
+      double2 xo, ro, zo;
+      xo.x = __dadd_rn(xi.x, __dmul_rn(alpha, pi.x)); xo.y = __dadd_rn(xi.y, __dmul_rn(alpha, pi.y));
+      ro.x = __dadd_rn(ri.x, -__dmul_rn(alpha, si.x)); ro.y = __dadd_rn(ri.y, -__dmul_rn(alpha, si.y));
+      x2[i] = xo; r2[i] = ro;
+      if (PREFILL)
+      {
+         zo.x = (di.x != 0.0) ? __ddiv_rn(__dmul_rn(zw, ro.x), di.x) : 0.0;
+         zo.y = (di.y != 0.0) ? __ddiv_rn(__dmul_rn(zw, ro.y), di.y) : 0.0;
+         z2[i] = zo;
+      }
+      acc += ro.x * ro.x; acc += ro.y * ro.y;
+      xo.x = __dadd_rn(xj.x, __dmul_rn(alpha, pj.x)); xo.y = __dadd_rn(xj.y, __dmul_rn(alpha, pj.y));
+      ro.x = __dadd_rn(rj.x, -__dmul_rn(alpha, sj.x)); ro.y = __dadd_rn(rj.y, -__dmul_rn(alpha, sj.y));
+      x2[j] = xo; r2[j] = ro;
+      if (PREFILL)
+      {
+         zo.x = (dj.x != 0.0) ? __ddiv_rn(__dmul_rn(zw, ro.x), dj.x) : 0.0;
+         zo.y = (dj.y != 0.0) ? __ddiv_rn(__dmul_rn(zw, ro.y), dj.y) : 0.0;
+         z2[j] = zo;
+      }
+      acc += ro.x * ro.x; acc += ro.y * ro.y;
    }
-   if (i < n)
+   if (i < n2)
+   {
+      const double2 xi = x2[i], pi = p2[i], ri = r2[i], si = s2[i];
+      double2       di = make_double2(0.0, 0.0);
+      if (PREFILL) di = d2[i];
+      double2 xo, ro, zo;
+      xo.x = __dadd_rn(xi.x, __dmul_rn(alpha, pi.x)); xo.y = __dadd_rn(xi.y, __dmul_rn(alpha, pi.y));
+      ro.x = __dadd_rn(ri.x, -__dmul_rn(alpha, si.x)); ro.y = __dadd_rn(ri.y, -__dmul_rn(alpha, si.y));
+      x2[i] = xo; r2[i] = ro;
+      if (PREFILL)
+      {
+         zo.x = (di.x != 0.0) ? __ddiv_rn(__dmul_rn(zw, ro.x), di.x) : 0.0;
+         zo.y = (di.y != 0.0) ? __ddiv_rn(__dmul_rn(zw, ro.y), di.y) : 0.0;
+         z2[i] = zo;
+      }
+      acc += ro.x * ro.x; acc += ro.y * ro.y;
+   }
+   if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0)
+   {
+      const int64_t k  = n - 1;
+      const double  dk = PREFILL ? zd[k] : 0.0;
+      acc += pcg_xr_row<PREFILL>(alpha, x[k], p[k], r[k], s[k], dk, zw, x, r, z0, k);
+   }
+   double bs = block_sum<VT>(acc, sm);
+   __syncthreads();
+   grid_finish<VT>(bs, partials, ticket, fin, fin_out, scal, sm, &flag);
+}
+
+// PCG: p = z + beta p   (128-bit accesses, two row pairs per trip)
+__global__ void __launch_bounds__(VT) k_pcg_p(double *__restrict__ p, const double *__restrict__ z,
+                                              int64_t n, const double *__restrict__ scal)
+{
+   const double   beta = scal[S_BETA];
+   const int64_t  n2 = n >> 1, stride = (int64_t)gridDim.x * VT;
+   double2       *p2 = reinterpret_cast<double2 *>(p);
+   const double2 *z2 = reinterpret_cast<const double2 *>(z);
+   int64_t        i = blockIdx.x * (int64_t)VT + threadIdx.x;
+   for (; i + stride < n2; i += 2 * stride)
+   {
+      const int64_t j = i + stride;
+      const double2 pi = p2[i], zi = z2[i], pj = p2[j], zj = z2[j];
+      p2[i] = make_double2(__dadd_rn(zi.x, __dmul_rn(beta, pi.x)), __dadd_rn(zi.y, __dmul_rn(beta, pi.y)));
+      p2[j] = make_double2(__dadd_rn(zj.x, __dmul_rn(beta, pj.x)), __dadd_rn(zj.y, __dmul_rn(beta, pj.y)));
+   }
+   if (i < n2)
+   {
+      const double2 pi = p2[i], zi = z2[i];
+      p2[i] = make_double2(__dadd_rn(zi.x, __dmul_rn(beta, pi.x)), __dadd_rn(zi.y, __dmul_rn(beta, pi.y)));
+   }
+   if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) p[n - 1] = __dadd_rn(z[n - 1], __dmul_rn(beta, p[n - 1]));
+}
+
+// scalar forms for operands that are not 16-byte aligned (sub-vectors at odd offsets)
+template <bool PREFILL>
+__global__ void __launch_bounds__(VT) k_pcg_xr_scalar(double *x, double *r, const double *p, const double *s, int64_t n,
+                                                      double *partials, unsigned *ticket, double *scal, int fin, double *fin_out,
+                                                      double *z0, const double *zd, double zw)
+{
+   __shared__ double sm[VT / 32];
+   __shared__ int    flag;
+   const double      alpha = scal[S_ALPHA];
+   double            acc   = 0.0;
+   for (int64_t i = blockIdx.x * (int64_t)VT + threadIdx.x; i < n; i += (int64_t)gridDim.x * VT)
    {
       const double di = PREFILL ? zd[i] : 0.0;
       acc += pcg_xr_row<PREFILL>(alpha, x[i], p[i], r[i], s[i], di, zw, x, r, z0, i);
@@ -142,10 +231,8 @@ __global__ void __launch_bounds__(VT) k_pcg_xr(double *x, double *r, const doubl
    __syncthreads();
    grid_finish<VT>(bs, partials, ticket, fin, fin_out, scal, sm, &flag);
 }
-
-// PCG: p = z + beta p
-__global__ void __launch_bounds__(VT) k_pcg_p(double *__restrict__ p, const double *__restrict__ z,
-                                              int64_t n, const double *__restrict__ scal)
+__global__ void __launch_bounds__(VT) k_pcg_p_scalar(double *__restrict__ p, const double *__restrict__ z,
+                                                     int64_t n, const double *__restrict__ scal)
 {
    const double beta = scal[S_BETA];
    for (int64_t i = blockIdx.x * (int64_t)VT + threadIdx.x; i < n; i += (int64_t)gridDim.x * VT)
@@ -231,9 +318,22 @@ int vec_copy_dot(double *z, const double *r, int64_t n, int fin, double *out_d)
    HDK_LAUNCH_CHECK();
    return HDK_OK;
 }
+static inline bool aligned16(const void *a, const void *b = nullptr, const void *c = nullptr, const void *d = nullptr,
+                             const void *e = nullptr, const void *f = nullptr)
+{
+   return (((uintptr_t)a | (uintptr_t)b | (uintptr_t)c | (uintptr_t)d | (uintptr_t)e | (uintptr_t)f) & 15u) == 0;
+}
+
 int pcg_update_xr(double *x, double *r, const double *p, const double *s, int64_t n, double *scal, int fin, double *fin_out,
                   double *z0, const double *zd, double zw)
 {
+   if (!aligned16(x, r, p, s, z0, zd))
+   {
+      if (z0) k_pcg_xr_scalar<true><<<vec_grid(n), VT, 0, g.stream>>>(x, r, p, s, n, g.partials, g.counters, scal, fin, fin_out, z0, zd, zw);
+      else k_pcg_xr_scalar<false><<<vec_grid(n), VT, 0, g.stream>>>(x, r, p, s, n, g.partials, g.counters, scal, fin, fin_out, z0, zd, zw);
+      HDK_LAUNCH_CHECK();
+      return HDK_OK;
+   }
    if (z0) k_pcg_xr<true><<<vec_grid(n), VT, 0, g.stream>>>(x, r, p, s, n, g.partials, g.counters, scal, fin, fin_out, z0, zd, zw);
    else k_pcg_xr<false><<<vec_grid(n), VT, 0, g.stream>>>(x, r, p, s, n, g.partials, g.counters, scal, fin, fin_out, z0, zd, zw);
    HDK_LAUNCH_CHECK();
@@ -242,7 +342,8 @@ int pcg_update_xr(double *x, double *r, const double *p, const double *s, int64_
 int pcg_update_p(double *p, const double *z, int64_t n, const double *scal)
 {
    if (n <= 0) return HDK_OK;
-   k_pcg_p<<<vec_grid(n), VT, 0, g.stream>>>(p, z, n, scal);
+   if (!aligned16(p, z)) k_pcg_p_scalar<<<vec_grid(n), VT, 0, g.stream>>>(p, z, n, scal);
+   else k_pcg_p<<<vec_grid(n), VT, 0, g.stream>>>(p, z, n, scal);
    HDK_LAUNCH_CHECK();
    return HDK_OK;
 }

@@ -341,6 +341,28 @@ def time_kernel(A: DCsr, M: DAmg | None, kernel: int, reps: int = 20):
     return ms.value, by.value
 
 
+def amg_rows(hM, level: int, which: int):
+    """This rank's rows of A_l (which=0) / P_l (which=1) of a row-distributed hierarchy with GLOBAL
+    columns in the serial storage order (needs tune("amg_keep_debug", 1) before the setup).
+    Returns (row0, indptr, cols, vals)."""
+    L = lib()
+    L.hdk_amg_get_rows.argtypes = [C.c_void_p, C.c_int, C.c_int] + [C.POINTER(C.c_int64)] * 3 + [C.c_void_p] * 3
+    r0, nr, nz = C.c_int64(), C.c_int64(), C.c_int64()
+    check(L.hdk_amg_get_rows(hM, level, which, C.byref(r0), C.byref(nr), C.byref(nz), None, None, None))
+    ip = np.empty(nr.value + 1, dtype=np.int64)
+    cj = np.empty(max(nz.value, 1), dtype=np.int64)
+    va = np.empty(max(nz.value, 1), dtype=np.float64)
+    check(L.hdk_amg_get_rows(hM, level, which, None, None, None, ip.ctypes.data, cj.ctypes.data, va.ctypes.data))
+    return int(r0.value), ip, cj[:nz.value], va[:nz.value]
+
+
+def amg_local_levels(hM):
+    """(number of row-distributed levels, total number of levels) of a hierarchy handle."""
+    L = lib()
+    L.hdk_amg_num_dist_levels.argtypes = [C.c_void_p]
+    return int(L.hdk_amg_num_dist_levels(hM)), int(L.hdk_amg_num_levels(hM))
+
+
 def tune(key: str, value: float):
     """Kernel-selection tunable (hdk_tune), e.g. tune("sell_min_rows", 0)."""
     L = lib()

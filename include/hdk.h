@@ -140,10 +140,16 @@ int  hdk_amg_vcycle(hdk_amg *M, const double *f_d, double *u_d);
 
 /* hierarchy introspection (parity tests, statistics) */
 int hdk_amg_num_levels(const hdk_amg *M);
+int hdk_amg_num_dist_levels(const hdk_amg *M); /* N > 1: leading levels that are row-distributed (the rest is replicated) */
 int hdk_amg_level_info(const hdk_amg *M, int level, int64_t *rows, int64_t *nnz_A, int64_t *nnz_P);
 /* which: 0 = A_l, 1 = P_l, 2 = R_l, 3 = S_l (pattern; val_h may be NULL) -- local diag block */
 int hdk_amg_get_matrix(const hdk_amg *M, int level, int which, int32_t *rowptr_h,
                        int32_t *col_h, double *val_h);
+/* N > 1 (row-distributed setup), tunable amg_keep_debug set before the setup: this rank's rows of
+ * A_l (which = 0) or P_l (which = 1) with GLOBAL 64-bit columns in the serial storage order, so the
+ * slabs of all ranks concatenate to the one-rank matrix.  Any output pointer may be NULL. */
+int hdk_amg_get_rows(const hdk_amg *M, int level, int which, int64_t *row0, int64_t *nrows, int64_t *nnz,
+                     int64_t *indptr_h, int64_t *cols_h, double *vals_h);
 int hdk_amg_get_cf(const hdk_amg *M, int level, int32_t *cf_h);
 int hdk_amg_get_measure(const hdk_amg *M, int level, double *measure_h);
 int hdk_amg_get_l1(const hdk_amg *M, int level, double *l1_h);
@@ -186,14 +192,16 @@ int hdk_bicgstab(const hdk_csr *A, hdk_amg *M, const double *b_d, double *x_d, h
 /* ---- measurement helpers: average kernel time in ms over `reps` back-to-back launches of
  * one hot kernel on the compute stream, CUDA-event timed (bench.py roofline leg).
  * kernel: 0 = SpMV y=Ax, 1 = l1-Jacobi sweep fused with residual, 2 = residual r=b-Ax,
- *         3 = PCG fused x/r update + <r,r>, 4 = V-cycle */
+ *         3 = PCG fused x/r update + <r,r> + first V-cycle sweep (the 64 B/row variant the solve runs),
+ *         4 = V-cycle, 5 = PCG p = z + beta p */
 int hdk_time_kernel(const hdk_csr *A, hdk_amg *M, int kernel, int reps, double *avg_ms,
                     double *algorithmic_bytes);
 /* number of kernel launches issued by this library since the last call (and reset) */
 int64_t hdk_launch_count_reset(void);
 /* kernel-selection tunables for matrices analysed after the call (same names as the HDK_*
  * environment variables, lower case without the prefix): spmv_rows_mult, spmv_tgt_max, spmv_lpr,
- * sell_min_rows, sell_min_rows_dist, sell_min_avg, sell_sort, amg_keep_debug (keep the strength
+ * sell_min_rows, sell_min_rows_dist, sell_min_avg, sell_sort, replicate_rows (N > 1: levels with
+ * at most this many global rows are replicated on every rank), amg_keep_debug (keep the strength
  * pattern and PMIS measures of every level for hdk_amg_get_matrix(...,'S') / get_measure).
  * Unknown key -> HDK_ERR_INVALID. */
 int hdk_tune(const char *key, double value);

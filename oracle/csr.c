@@ -6,6 +6,20 @@
 #include <stdlib.h>
 #include <string.h>
 #include <math.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+int oracle_set_threads(int n)
+{
+#ifdef _OPENMP
+   if (n > 0) omp_set_num_threads(n);
+   return omp_get_max_threads();
+#else
+   (void)n;
+   return 1;
+#endif
+}
 
 ocsr *ocsr_alloc(int nrows, int ncols, int64_t nnz, int with_values)
 {

@@ -81,6 +81,8 @@ def lib():
         L.ovec_dot.restype = C.c_double
         L.ovec_dot.argtypes = [C.c_int, PD, PD]
         L.oracle_rand_stream.argtypes = [C.c_int, C.c_int, PD]
+        L.oracle_set_threads.restype = C.c_int
+        L.oracle_set_threads.argtypes = [C.c_int]
         L.oamg_default_params.argtypes = [C.POINTER(Params), C.c_int]
         L.oamg_strength.restype = PO
         L.oamg_strength.argtypes = [PO, C.c_double, C.c_double]
@@ -176,6 +178,11 @@ def gen(kind: str, nx: int, ny: int, nz: int, c=(1.0, 1.0, 1.0), diag_first: boo
     A = from_ocsr(p)
     L.ocsr_free(p)
     return A, b
+
+
+def set_threads(n: int = 0) -> int:
+    """Set (n > 0) and return the OpenMP team size of the oracle's parallel loops."""
+    return int(lib().oracle_set_threads(int(n)))
 
 
 def rand_stream(seed: int, n: int) -> np.ndarray:

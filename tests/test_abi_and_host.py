@@ -226,13 +226,22 @@ def test_bench_reference_arm_contract():
     import json
     import subprocess
     import sys
-    env = dict(os.environ, HDK_BENCH_CPU_EDGE="40")
-    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
-                       capture_output=True, text=True, env=env, timeout=300)
+    # torchrun exports OMP_NUM_THREADS=1 to its children: the arm must override it by assignment
+    env = dict(os.environ, OMP_NUM_THREADS="1")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "2", "--warmup", "1",
+                        "--n", "40"], capture_output=True, text=True, env=env, timeout=300)
     assert r.returncode == 0, r.stderr[-2000:]
     line = json.loads(r.stdout.strip().splitlines()[-1])
     assert line["impl"] == "reference" and line["unit"] == "DOF*iters/s" and line["value"] > 0
     assert line["higher_is_better"] is True and line["vs_baseline"] is None and line["dtype"] == "f64"
     assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0
-    assert "workload" in line["config"]
+    assert "workload" in line["config"] and "40x40x40" in line["config"]["workload"]
+    assert line["steps"] == 2 and line["warmup"] == 1
+    assert line["cpu_baseline"]["cores"] == len(os.sched_getaffinity(0))
+    # the two arms must print the same metric / unit / direction or the driver cannot form a ratio
+    sys.path.insert(0, ROOT)
+    import bench
+    assert line["metric"] == bench.CONFIGS["lap7_256"]["metric"]
+    for name, cfg in bench.CONFIGS.items():
+        assert cfg["scaling"] in ("weak", "strong") and cfg["solver"] in ("pcg", "gmres"), name

@@ -1,6 +1,8 @@
-"""GPU test of the N > 1 path: spawns one process per GPU with torchrun and checks parity of the
-distributed solve (halo exchange, allreduce, sliced hierarchy + replicated tail) against the
-oracle.  Needs at least two GPUs on the box; skipped otherwise."""
+"""GPU test of the N > 1 path: spawns one process per rank with torchrun and checks parity of the
+row-distributed setup (hierarchy bit-identical to the oracle's, slab by slab) and of the
+distributed solve (halo exchange, allreduce, replicated tail) against the oracle.  With fewer GPUs
+than ranks (the driver's 1-GPU box) the ranks share cuda:0 and talk through NCCL's socket
+transport (tests/mp_gpu_check.py), so nothing here is skipped."""
 import os
 import subprocess
 import sys
@@ -35,11 +37,9 @@ def _run(world, args, env_extra=None):
     ("lap7", ("14", "9", "7"), "40", "ragged"), ("lap27", ("8", "8", "6"), "30", "ragged-sell"),
     ("convdif", ("16", "8", "6"), "40", "ragged-nccl")])
 def test_two_rank_solve_matches_oracle(gpu, kind, dims, rep, share):
-    if gpu.device_count() < 2:
-        pytest.skip("needs two GPUs")
     env = {"HDK_REPLICATE_ROWS": rep}
     if share == "off":
-        env["HDK_SETUP_SHARE"] = "0"
+        env["HDK_SETUP_REPLICATED"] = "1"        # the round-1 scheme: global hierarchy rebuilt on every rank
     elif share == "nccl":
         env["HDK_HALO_IPC"] = "0"
     elif share.startswith("ragged"):
@@ -62,3 +62,21 @@ def test_two_rank_solve_matches_oracle(gpu, kind, dims, rep, share):
     r = _run(2, [kind, *dims], env)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert "ok=True" in r.stdout
+    if share != "off":
+        assert "hier=bit-identical" in r.stdout, r.stdout[-500:]
+
+
+@pytest.mark.parametrize("world,kind,dims,rep,ragged", [
+    (3, "lap7", ("16", "14", "7"), "60", "1"), (4, "lap27", ("10", "9", "5"), "50", "0"),
+    (4, "convdif", ("16", "10", "5"), "60", "1"), (2, "lap7", ("40", "36", "20"), "2000", "0"),
+    # every level distributed down to the coarsest (replicate_rows below max_coarse_size)
+    (2, "lap7", ("20", "18", "9"), "10", "1"),
+    # the whole hierarchy replicated (fine level below replicate_rows)
+    (2, "lap7", ("10", "9", "4"), "100000", "0")])
+def test_row_distributed_setup_matches_oracle(gpu, world, kind, dims, rep, ragged):
+    """Row-distributed setup on 2-4 ranks: per-level C/F splitting, P and A_c slabs (global columns)
+    concatenate to the oracle's matrices bit for bit; solve parity as above."""
+    env = {"HDK_REPLICATE_ROWS": rep, "MPCHECK_RAGGED": ragged, "MPCHECK_HIER": "1"}
+    r = _run(world, [kind, *dims], env)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "ok=True" in r.stdout and "hier=bit-identical" in r.stdout, r.stdout[-500:]
