@@ -16,6 +16,7 @@ struct AmgLevel
    double    *measure = nullptr;
    double    *l1_down = nullptr, *l1_up = nullptr; // smoother diagonals (may alias)
    double    *u = nullptr, *f = nullptr, *t = nullptr;
+   double    *gs1 = nullptr, *gs2 = nullptr; // two-stage GS: correction vectors of the inner steps
    DevCSR     L;            // strict lower triangle (two-stage GS only)
    int        n = 0;
    // distributed setup, amg_keep_debug: my rows of P_l and A_l with GLOBAL columns in the serial
@@ -67,7 +68,6 @@ int build_interp(const DevCSR &A, const DevCSR &S, int *cf, const int *f2c, int 
                  DevCSR &P, int row_lo, int row_hi);
 int build_rap(const DevCSR &R, const DevCSR &A, const DevCSR &P, DevCSR &C, int row_lo, int row_hi);
 int csr_transpose(const DevCSR &A, DevCSR &T);
-int exclusive_scan_i64(const int *in, int64_t *out, int n);
 hdk_csr_s *wrap_local(DevCSR &D, int64_t grows);
 void destroy_local(hdk_csr_s *A);
 void setup_stage_mark(const char *name, int level);
@@ -77,6 +77,8 @@ void setup_stage_mark(const char *name, int level);
 int amg_precond(hdk_amg_s *M, const double *r, double *z, int fin, double *fin_out);
 // V-cycle over levels [l0, nlev) of M; level l0 uses the caller's vectors
 int amg_cycle(hdk_amg_s *M, const double *f, double *u, bool zero_guess, int fin, double *fin_out, int l0 = 0);
-int exclusive_scan_int(const int *in, int *out, int n);
+int exclusive_scan_int(const int *in, int *out, int n);       // hdk_csr.cu (hand-written reduce-then-scan)
+int exclusive_scan_i64(const int *in, int64_t *out, int n);
+int exclusive_scan_i64_i64(const int64_t *in, int64_t *out, int64_t n);
 bool amg_prefill_target(hdk_amg_s *M, double *z, double **buf, const double **d, double *w);
 } // namespace hdk

@@ -9,7 +9,6 @@
 // (oracle/amg_setup.c), and so are the floating-point values, because every row is
 // accumulated by one thread in the oracle's order with separately rounded multiply/add.
 #include "hdk_amg.cuh"
-#include <cub/cub.cuh>
 #include <algorithm>
 #include <math.h>
 #include <stdlib.h>
@@ -83,12 +82,6 @@ static int share_entries(const int *rowptr_d, int n, void *a, size_t ea, void *b
 // =====================================================================================
 // small utilities
 // =====================================================================================
-__global__ void k_cast_i64(const int *in, int64_t *out, int n)
-{
-   int i = blockIdx.x * blockDim.x + threadIdx.x;
-   if (i < n) out[i] = (int64_t)in[i];
-}
-
 // sum of n non-negative ints in 64 bits: the row counts of a product must fit the int32 row
 // pointers before they are scanned (a 640^3 7-point problem overflows at level 1)
 __global__ void k_sum_i64(const int *v, int n, unsigned long long *out)
@@ -111,20 +104,6 @@ static int check_fits_int32(const int *cnt, int n, const char *what)
    HDK_CUDA(cudaStreamSynchronize(g.stream));
    if (h > 2000000000ULL)
       return set_error(HDK_ERR_UNSUPPORTED, "%s would have %llu non-zeros: more than the int32 row pointers of this setup hold", what, h);
-   return HDK_OK;
-}
-
-int exclusive_scan_i64(const int *in, int64_t *out, int n)
-{
-   k_cast_i64<<<cdiv(n, 256), 256, 0, g.stream>>>(in, out, n);
-   HDK_LAUNCH_CHECK();
-   size_t bytes = 0;
-   HDK_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, bytes, out, out, n, g.stream));
-   char *tmp;
-   HDK_TRY(dalloc(&tmp, bytes));
-   HDK_CUDA(cub::DeviceScan::ExclusiveSum(tmp, bytes, out, out, n, g.stream));
-   g.launches++;
-   dfree(tmp);
    return HDK_OK;
 }
 
@@ -1096,32 +1075,41 @@ int build_interp(const DevCSR &A, const DevCSR &S, int *cf, const int *f2c, int 
 // =====================================================================================
 // R = P^T (hypre_CSRMatrixTranspose order: ascending fine row inside each coarse row)
 // =====================================================================================
-__global__ void k_expand_rows(const int *rp, int n, int *rowid)
+// Counting transpose: per-column counts (atomics on distinct addresses), scan, scatter through
+// per-column cursors, then every row of the transpose is put in ascending order of the source row
+// by the thread that owns it (interpolation transposes have ~10-30 entries per row; the source
+// rows are unique inside a row, so the result is deterministic whatever order the atomics ran in).
+__global__ void k_tr_count(const int *col, int nnz, int *cnt)
+{
+   int k = blockIdx.x * blockDim.x + threadIdx.x;
+   if (k < nnz) atomicAdd(cnt + col[k], 1);
+}
+__global__ void k_tr_place(const int *rp, const int *col, const double *val, int n, const int *trp, int *cursor, int *tcol, double *tval)
 {
    int i = blockIdx.x * blockDim.x + threadIdx.x;
    if (i >= n) return;
-   for (int k = rp[i]; k < rp[i + 1]; k++) rowid[k] = i;
+   for (int k = rp[i]; k < rp[i + 1]; k++)
+   {
+      int c = col[k];
+      int p = trp[c] + atomicAdd(cursor + c, 1);
+      tcol[p] = i;
+      if (val) tval[p] = val[k];
+   }
 }
-__global__ void k_iota(int *v, int n)
-{
-   int i = blockIdx.x * blockDim.x + threadIdx.x;
-   if (i < n) v[i] = i;
-}
-__global__ void k_transpose_fill(const int *perm, const int *rowid, const double *val, int nnz, int *tcol, double *tval)
-{
-   int k = blockIdx.x * blockDim.x + threadIdx.x;
-   if (k >= nnz) return;
-   int s = perm[k];
-   tcol[k] = rowid[s];
-   if (val) tval[k] = val[s];
-}
-__global__ void k_rowptr_from_sorted(const int *keys, int nnz, int nrows, int *rp)
+__global__ void k_tr_sort_rows(const int *trp, int nrows, int *tcol, double *tval)
 {
    int r = blockIdx.x * blockDim.x + threadIdx.x;
-   if (r > nrows) return;
-   int lo = 0, hi = nnz; // first k with keys[k] >= r
-   while (lo < hi) { int mid = (lo + hi) >> 1; if (keys[mid] >= r) hi = mid; else lo = mid + 1; }
-   rp[r] = lo;
+   if (r >= nrows) return;
+   int b = trp[r], e = trp[r + 1];
+   for (int a = b + 1; a < e; a++)
+   {
+      int    c = tcol[a];
+      double v = tval ? tval[a] : 0.0;
+      int    j = a - 1;
+      while (j >= b && tcol[j] > c) { tcol[j + 1] = tcol[j]; if (tval) tval[j + 1] = tval[j]; j--; }
+      tcol[j + 1] = c;
+      if (tval) tval[j + 1] = v;
+   }
 }
 
 int csr_transpose(const DevCSR &A, DevCSR &T)
@@ -1129,28 +1117,19 @@ int csr_transpose(const DevCSR &A, DevCSR &T)
    int nnz = A.nnz;
    HDK_TRY(csr_alloc(T, A.ncols, A.nrows, nnz, A.val != nullptr));
    if (nnz == 0) { HDK_CUDA(cudaMemsetAsync(T.rowptr, 0, sizeof(int) * ((size_t)T.nrows + 1), g.stream)); return HDK_OK; }
-   int *rowid, *idx, *keys_out, *perm;
-   HDK_TRY(dalloc(&rowid, (size_t)nnz));
-   HDK_TRY(dalloc(&idx, (size_t)nnz));
-   HDK_TRY(dalloc(&keys_out, (size_t)nnz));
-   HDK_TRY(dalloc(&perm, (size_t)nnz));
-   k_expand_rows<<<cdiv(A.nrows, 256), 256, 0, g.stream>>>(A.rowptr, A.nrows, rowid);
+   int *cnt, *cursor;
+   HDK_TRY(dalloc(&cnt, (size_t)T.nrows + 1));
+   HDK_TRY(dalloc(&cursor, (size_t)T.nrows + 1));
+   HDK_CUDA(cudaMemsetAsync(cnt, 0, sizeof(int) * ((size_t)T.nrows + 1), g.stream));
+   HDK_CUDA(cudaMemsetAsync(cursor, 0, sizeof(int) * ((size_t)T.nrows + 1), g.stream));
+   k_tr_count<<<cdiv(nnz, 256), 256, 0, g.stream>>>(A.col, nnz, cnt);
    HDK_LAUNCH_CHECK();
-   k_iota<<<cdiv(nnz, 256), 256, 0, g.stream>>>(idx, nnz);
+   HDK_TRY(exclusive_scan_int(cnt, T.rowptr, T.nrows + 1));
+   k_tr_place<<<cdiv(A.nrows, 256), 256, 0, g.stream>>>(A.rowptr, A.col, A.val, A.nrows, T.rowptr, cursor, T.col, T.val);
    HDK_LAUNCH_CHECK();
-   int bits = 1;
-   while ((1LL << bits) < (long long)A.ncols + 1 && bits < 31) bits++;
-   size_t bytes = 0;
-   HDK_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, bytes, A.col, keys_out, idx, perm, nnz, 0, bits, g.stream));
-   char *tmp;
-   HDK_TRY(dalloc(&tmp, bytes));
-   HDK_CUDA(cub::DeviceRadixSort::SortPairs(tmp, bytes, A.col, keys_out, idx, perm, nnz, 0, bits, g.stream)); // stable
-   g.launches++;
-   k_transpose_fill<<<cdiv(nnz, 256), 256, 0, g.stream>>>(perm, rowid, A.val, nnz, T.col, T.val);
+   k_tr_sort_rows<<<cdiv(T.nrows, 128), 128, 0, g.stream>>>(T.rowptr, T.nrows, T.col, T.val);
    HDK_LAUNCH_CHECK();
-   k_rowptr_from_sorted<<<cdiv(T.nrows + 1, 256), 256, 0, g.stream>>>(keys_out, nnz, T.nrows, T.rowptr);
-   HDK_LAUNCH_CHECK();
-   dfree(tmp); dfree(rowid); dfree(idx); dfree(keys_out); dfree(perm);
+   dfree(cnt); dfree(cursor);
    return HDK_OK;
 }
 
@@ -1712,7 +1691,7 @@ int hdk_amg_destroy(hdk_amg *M)
          dfree(L.cf); dfree(L.measure); dfree(L.f2c);
          if (L.l1_up != L.l1_down) dfree(L.l1_up);
          dfree(L.l1_down);
-         dfree(L.u); dfree(L.f); dfree(L.t);
+         dfree(L.u); dfree(L.f); dfree(L.t); dfree(L.gs1); dfree(L.gs2);
          for (int w = 0; w < 2; w++) { dfree(L.dbg_ip[w]); dfree(L.dbg_col[w]); dfree(L.dbg_val[w]); }
       }
       dfree(M->ge_inv); dfree(M->full_f); dfree(M->full_u);
@@ -1744,6 +1723,7 @@ int finalize_levels(hdk_amg_s *M, const hdk_amg_params *prm, int64_t live_max_ro
       }
       bool tsgs = (prm->relax_down == 11 || prm->relax_down == 12 || prm->relax_up == 11 || prm->relax_up == 12);
       if (tsgs && (rc = build_lower(L.A->diag, L.L))) break;
+      if (tsgs && ((rc = dalloc(&L.gs1, (size_t)n + 8)) || (rc = dalloc(&L.gs2, (size_t)n + 8)))) break;
       // algorithmic bytes of one V-cycle: zero-guess pre-smooth 24n, residual,
       // restriction, prolongation, post-smooth
       double nnzA = (double)L.A->diag.nnz + L.A->offd.nnz;

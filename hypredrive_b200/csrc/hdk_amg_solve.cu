@@ -37,30 +37,53 @@ static int relax_sweep(hdk_amg_s *M, int l, int type, const double *l1, const do
    }
    if (type == 11 || type == 12)
    {
-      // two-stage GS: r = w D^{-1}(f - A u); u += r; then r <- D^{-1} L r, u += (-1)^k r
-      double *r, *r2;
-      HDK_TRY(dalloc(&r, (size_t)L.n + 8));
-      HDK_TRY(dalloc(&r2, (size_t)L.n + 8));
-      a.y = r;                                 // r = w D^{-1} (f - A u_old)
-      HDK_TRY(parcsr_matvec(*L.A, SPMV_JACOBI_R, a));
-      HDK_TRY(vec_copy(out, in, L.n));         // out = u_old
-      HDK_TRY(vec_axpy(1.0, r, out, L.n));     // out = u_old + r
-      int    inner = (type == 11) ? 1 : 2;
-      double mult  = 1.0;
-      double *cur = r, *nxt = r2;
-      for (int it = 0; it < inner; it++)
+      // two-stage GS (hypre_BoomerAMGRelaxTwoStageGaussSeidel): r = w D^{-1}(f - A u); u += r; then
+      // k = 1..inner: r <- D^{-1} L r, u += (-1)^k r.  Fused: ONE pass over A produces both r and
+      // u + r, and each inner step is one pass over the strict lower triangle whose epilogue divides
+      // by the diagonal and applies the signed update -- 2 (type 11) or 3 (type 12) kernels per sweep,
+      // no scratch allocation.  (hypre applies L in place bottom-up, which reads only entries not yet
+      // updated, i.e. the same Jacobi-type product as this out-of-place form.)
+      const int inner = (type == 11) ? 1 : 2;
+      if (L.gs1 && parcsr_single_kernel(*L.A))
       {
-         // nxt = D^{-1} L cur  (out-of-place strict-lower SpMV; hypre does this in place
-         // bottom-up, which reads only not-yet-updated entries, i.e. the same Jacobi-type product)
-         SpmvArgs b2;
-         b2.x = cur; b2.y = nxt;
-         HDK_TRY(spmv_launch(L.L, SPMV_SET, b2));
-         HDK_TRY(vec_scaled_div(nxt, nxt, l1, 1.0, L.n));
-         mult = -mult;
-         HDK_TRY(vec_axpy(mult, nxt, out, L.n));
-         double *tmp = cur; cur = nxt; nxt = tmp;
+         a.y = out; a.y2 = L.gs1;
+         HDK_TRY(parcsr_matvec(*L.A, SPMV_JACOBI2, a));
+         double *cur = L.gs1, *nxt = L.gs2;
+         double  mult = 1.0;
+         for (int it = 0; it < inner; it++)
+         {
+            mult = -mult;
+            SpmvArgs b2;
+            b2.x = cur; b2.y = out; b2.d = l1; b2.alpha = mult;
+            b2.y2 = (it + 1 < inner) ? nxt : nullptr;
+            HDK_TRY(spmv_launch(L.L, SPMV_GS_STEP, b2));
+            double *tmp = cur; cur = nxt; nxt = tmp;
+         }
       }
-      dfree(r); dfree(r2);
+      else
+      {
+         // rows whose off-rank part is added by a separate correction kernel: unfused form
+         double *r, *r2;
+         HDK_TRY(dalloc(&r, (size_t)L.n + 8));
+         HDK_TRY(dalloc(&r2, (size_t)L.n + 8));
+         a.y = r;                                 // r = w D^{-1} (f - A u_old)
+         HDK_TRY(parcsr_matvec(*L.A, SPMV_JACOBI_R, a));
+         HDK_TRY(vec_copy(out, in, L.n));         // out = u_old
+         HDK_TRY(vec_axpy(1.0, r, out, L.n));     // out = u_old + r
+         double mult  = 1.0;
+         double *cur = r, *nxt = r2;
+         for (int it = 0; it < inner; it++)
+         {
+            SpmvArgs b2;
+            b2.x = cur; b2.y = nxt;
+            HDK_TRY(spmv_launch(L.L, SPMV_SET, b2));
+            HDK_TRY(vec_scaled_div(nxt, nxt, l1, 1.0, L.n));
+            mult = -mult;
+            HDK_TRY(vec_axpy(mult, nxt, out, L.n));
+            double *tmp = cur; cur = nxt; nxt = tmp;
+         }
+         dfree(r); dfree(r2);
+      }
       if (fin != FIN_NONE) HDK_TRY(vec_dot_dev(f, out, L.n, fin, fin_out));
       return HDK_OK;
    }
@@ -317,6 +340,17 @@ int hdk_time_kernel(const hdk_csr *A, hdk_amg *M, int kernel, int reps, double *
             case 4:
                if (!M) rc = set_error(HDK_ERR_INVALID, "V-cycle timing needs a hierarchy");
                else { rc = amg_precond(M, b, y, FIN_NONE, nullptr); by = M->vcycle_bytes; }
+               break;
+            case 6: // one two-stage Gauss-Seidel sweep on the fine level (hierarchy set up with relax 11 or 12)
+               if (!M || M->nlev < 1 || !M->lev[0].L.rowptr) rc = set_error(HDK_ERR_INVALID, "two-stage GS timing needs a hierarchy set up with relaxation 11 or 12");
+               else
+               {
+                  const int    type = (M->prm.relax_down == 12 || M->prm.relax_up == 12) ? 12 : 11;
+                  const double nnzL = (double)M->lev[0].L.nnz;
+                  rc = relax_sweep(M, 0, type, M->lev[0].l1_down, b, x, y, FIN_NONE, nullptr);
+                  // stage 1 reads A, u, f, d and writes r, u+r; every inner step reads L, r, d, u and writes u (and r)
+                  by = 12.0 * nnz + 4.0 * (n + 1) + 40.0 * n + (type == 11 ? 1 : 2) * (12.0 * nnzL + 4.0 * (n + 1) + 32.0 * n) + (type == 12 ? 8.0 * n : 0.0);
+               }
                break;
             default: rc = set_error(HDK_ERR_INVALID, "unknown kernel id %d", kernel);
          }

@@ -64,17 +64,75 @@ __global__ void k_map_offd(const int64_t *gcol, int nnz, const int64_t *map, int
    col[k] = lo;
 }
 
-int exclusive_scan_int(const int *in, int *out, int n)
+// ---- exclusive prefix sums (hand-written reduce-then-scan: block sums -> scan of the block sums
+// (recursive) -> block-local scan + offset).  1024 items per block, 4 per thread; in == out allowed.
+constexpr int SCAN_T = 256, SCAN_ITEMS = 4, SCAN_B = SCAN_T * SCAN_ITEMS;
+
+template <class TI, class TO>
+__global__ void __launch_bounds__(SCAN_T) k_scan_sums(const TI *in, int64_t n, TO *bsum)
 {
-   size_t bytes = 0;
-   HDK_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, bytes, in, out, n, g.stream));
-   char *tmp;
-   HDK_TRY(dalloc(&tmp, bytes));
-   HDK_CUDA(cub::DeviceScan::ExclusiveSum(tmp, bytes, in, out, n, g.stream));
-   g.launches++;
-   dfree(tmp);
+   __shared__ TO sm[SCAN_T / 32];
+   const int64_t base = (int64_t)blockIdx.x * SCAN_B + (int64_t)threadIdx.x * SCAN_ITEMS;
+   TO            s = 0;
+#pragma unroll
+   for (int k = 0; k < SCAN_ITEMS; k++) if (base + k < n) s += (TO)in[base + k];
+   for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
+   if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = s;
+   __syncthreads();
+   if (threadIdx.x == 0)
+   {
+      TO t = 0;
+      for (int w = 0; w < SCAN_T / 32; w++) t += sm[w];
+      bsum[blockIdx.x] = t;
+   }
+}
+
+template <class TI, class TO>
+__global__ void __launch_bounds__(SCAN_T) k_scan_apply(const TI *in, TO *out, int64_t n, const TO *boff)
+{
+   __shared__ TO sm[SCAN_T / 32];
+   const int64_t base = (int64_t)blockIdx.x * SCAN_B + (int64_t)threadIdx.x * SCAN_ITEMS;
+   const int     lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+   TO            v[SCAN_ITEMS], s = 0;
+#pragma unroll
+   for (int k = 0; k < SCAN_ITEMS; k++) { v[k] = (base + k < n) ? (TO)in[base + k] : (TO)0; s += v[k]; }
+   TO incl = s;                                  // inclusive scan of the thread sums inside the warp
+#pragma unroll
+   for (int o = 1; o < 32; o <<= 1) { TO u = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += u; }
+   if (lane == 31) sm[w] = incl;
+   __syncthreads();
+   TO woff = 0;
+   for (int q = 0; q < w; q++) woff += sm[q];
+   TO run = (boff ? boff[blockIdx.x] : (TO)0) + woff + incl - s;
+#pragma unroll
+   for (int k = 0; k < SCAN_ITEMS; k++) { if (base + k < n) out[base + k] = run; run += v[k]; }
+}
+
+template <class TI, class TO>
+static int exclusive_scan_t(const TI *in, TO *out, int64_t n)
+{
+   if (n <= 0) return HDK_OK;
+   const int64_t nb = (n + SCAN_B - 1) / SCAN_B;
+   if (nb == 1)
+   {
+      k_scan_apply<TI, TO><<<1, SCAN_T, 0, g.stream>>>(in, out, n, nullptr);
+      HDK_LAUNCH_CHECK();
+      return HDK_OK;
+   }
+   TO *bsum;
+   HDK_TRY(dalloc(&bsum, (size_t)nb));
+   k_scan_sums<TI, TO><<<(unsigned)nb, SCAN_T, 0, g.stream>>>(in, n, bsum);
+   HDK_LAUNCH_CHECK();
+   HDK_TRY((exclusive_scan_t<TO, TO>(bsum, bsum, nb)));
+   k_scan_apply<TI, TO><<<(unsigned)nb, SCAN_T, 0, g.stream>>>(in, out, n, bsum);
+   HDK_LAUNCH_CHECK();
+   dfree(bsum);
    return HDK_OK;
 }
+
+int exclusive_scan_int(const int *in, int *out, int n) { return exclusive_scan_t<int, int>(in, out, n); }
+int exclusive_scan_i64(const int *in, int64_t *out, int n) { return exclusive_scan_t<int, int64_t>(in, out, n); }
+int exclusive_scan_i64_i64(const int64_t *in, int64_t *out, int64_t n) { return exclusive_scan_t<int64_t, int64_t>(in, out, n); }
 
 int build_halo_plan(hdk_csr_s &A, int64_t *gcol_sorted_unique, int n_halo); // hdk_comm.cu
 
@@ -240,6 +298,15 @@ static bool fuse_offd_enabled(int nrows)
       if (getenv("HDK_FUSE_OFFD_MAX_ROWS")) max_rows = atoll(getenv("HDK_FUSE_OFFD_MAX_ROWS"));
    }
    return on == 1 && nrows <= max_rows;
+}
+
+// true when parcsr_matvec runs as ONE kernel (no off-rank block, or the block fused into the
+// sliced-ELL kernel): then every fused epilogue sees the complete row sum
+bool parcsr_single_kernel(const hdk_csr_s &A)
+{
+   bool exch = g.nranks > 1 && (A.halo.n_send > 0 || A.halo.n_halo > 0);
+   if (!exch || A.offd.nnz == 0) return true;
+   return A.halo.ipc.on && A.diag.kind == 2 && A.diag.sl_offd_flags && fuse_offd_enabled(A.diag.nrows);
 }
 
 int parcsr_matvec(const hdk_csr_s &A, int mode, SpmvArgs a)
@@ -539,15 +606,11 @@ int hdk_csr_stencil(int kind, int nx, int ny, int nz, const double c[3], int64_t
    HDK_TRY(dalloc(&ip, (size_t)n + 1));
    k_stencil_count<<<cdiv(n + 1, 256), 256, 0, g.stream>>>(kind, nx, ny, nz, row_start, n, cnt);
    HDK_LAUNCH_CHECK();
-   size_t bytes = 0;
-   HDK_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, bytes, cnt, ip, n + 1, g.stream));
-   char *tmp;
-   HDK_TRY(dalloc(&tmp, bytes));
-   HDK_CUDA(cub::DeviceScan::ExclusiveSum(tmp, bytes, cnt, ip, n + 1, g.stream));
+   HDK_TRY(exclusive_scan_i64_i64(cnt, ip, (int64_t)n + 1));
    int64_t nnz = 0;
    HDK_CUDA(cudaMemcpyAsync(&nnz, ip + n, sizeof(int64_t), cudaMemcpyDeviceToHost, g.stream));
    HDK_CUDA(cudaStreamSynchronize(g.stream));
-   dfree(tmp); dfree(cnt);
+   dfree(cnt);
    int64_t *cols;
    double  *vals;
    HDK_TRY(dalloc(&cols, (size_t)nnz + 1));

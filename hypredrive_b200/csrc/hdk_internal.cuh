@@ -125,7 +125,9 @@ enum SpmvMode
    SPMV_ADD = 3,      // y = y + A x        (s = y; s += a*x in CSR order)
    SPMV_AXPBY = 4,    // y = alpha*(A x) + beta*y
    SPMV_JACOBI_R = 5, // y = w*(b - A x)/d  (two-stage GS first stage)
-   SPMV_SET_DIV = 6   // y = A x ; y2 = w*y/d  (restriction fused with the next level's first l1-Jacobi sweep)
+   SPMV_SET_DIV = 6,  // y = A x ; y2 = w*y/d  (restriction fused with the next level's first l1-Jacobi sweep)
+   SPMV_JACOBI2 = 7,  // y2 = w*(b - A x)/d ; y = x + y2   (two-stage GS, first stage: correction AND updated iterate)
+   SPMV_GS_STEP = 8   // t = (A x)/d ; y2 = t ; y = y + alpha*t   (two-stage GS inner step on the strict lower triangle)
 };
 
 // what the last block does with a fused dot product
@@ -283,6 +285,7 @@ struct hdk_csr_s
 
 namespace hdk {
 int parcsr_matvec(const hdk_csr_s &A, int mode, SpmvArgs a); // halo exchange + diag + offd
+bool parcsr_single_kernel(const hdk_csr_s &A);
 int parcsr_build(int64_t rs, int64_t re, int64_t cs, int64_t ce, int64_t grows, int64_t gcols, bool square,
                  bool distributed, bool keep_orig, const int64_t *indptr, const int64_t *cols, const double *vals,
                  hdk_csr_s **out, bool analyze = true);

@@ -129,6 +129,30 @@ __device__ __forceinline__ void store_y2(const SpmvDev &a, int r, double yn, dou
 {
    if (MODE == SPMV_SET_DIV) a.y2[r] = (dd != 0.0) ? __ddiv_rn(__dmul_rn(a.w, yn), dd) : 0.0;
 }
+// writes the outputs of row r and returns the value of y (what a fused dot multiplies).  `v` is the
+// result of the row epilogue: y for most modes, the correction w(b - Ax)/d for JACOBI2, A x for GS_STEP.
+template <int MODE>
+__device__ __forceinline__ double store_out(const SpmvDev &a, int r, double v, double dd, double xo)
+{
+   if (MODE == SPMV_JACOBI2)
+   {
+      const double yn = __dadd_rn(xo, v);
+      a.y2[r] = v;
+      a.y[r]  = yn;
+      return yn;
+   }
+   if (MODE == SPMV_GS_STEP)
+   {
+      const double t  = (dd != 0.0) ? __ddiv_rn(v, dd) : 0.0;
+      const double yn = __dadd_rn(a.y[r], __dmul_rn(a.alpha, t));
+      if (a.y2) a.y2[r] = t;
+      a.y[r] = yn;
+      return yn;
+   }
+   a.y[r] = v;
+   store_y2<MODE>(a, r, v, dd);
+   return v;
+}
 
 struct BlkMeta { int r0, r1, k0, k1; };
 __device__ __forceinline__ BlkMeta blk_meta(const SpmvDev &a, int b)
@@ -153,9 +177,9 @@ __device__ __forceinline__ void row_load(const SpmvDev &a, int r, int ka, RowOps
 {
    o.s = __ldg(a.rowptr + r) - ka;
    o.e = __ldg(a.rowptr + r + 1) - ka;
-   if (MODE == SPMV_RESIDUAL || MODE == SPMV_JACOBI || MODE == SPMV_JACOBI_R) o.b = a.b[r];
-   if (MODE == SPMV_JACOBI || MODE == SPMV_JACOBI_R || MODE == SPMV_SET_DIV) o.d = a.d[r];
-   if (MODE == SPMV_JACOBI) o.xo = a.x[r];
+   if (MODE == SPMV_RESIDUAL || MODE == SPMV_JACOBI || MODE == SPMV_JACOBI_R || MODE == SPMV_JACOBI2) o.b = a.b[r];
+   if (MODE == SPMV_JACOBI || MODE == SPMV_JACOBI_R || MODE == SPMV_SET_DIV || MODE == SPMV_JACOBI2 || MODE == SPMV_GS_STEP) o.d = a.d[r];
+   if (MODE == SPMV_JACOBI || MODE == SPMV_JACOBI2) o.xo = a.x[r];
    if (MODE == SPMV_ADD || MODE == SPMV_AXPBY) o.yo = a.y[r];
    if (DOT) o.dv = a.dotv[r];
 }
@@ -164,7 +188,7 @@ __device__ __forceinline__ void row_load(const SpmvDev &a, int r, int ka, RowOps
 template <int MODE>
 __device__ __forceinline__ double row_compute(const SpmvDev &a, const RowOps &o, const double *vs, const int *cs)
 {
-   constexpr bool SUB = (MODE == SPMV_RESIDUAL || MODE == SPMV_JACOBI || MODE == SPMV_JACOBI_R);
+   constexpr bool SUB = (MODE == SPMV_RESIDUAL || MODE == SPMV_JACOBI || MODE == SPMV_JACOBI_R || MODE == SPMV_JACOBI2);
    double acc = SUB ? o.b : ((MODE == SPMV_ADD) ? o.yo : 0.0);
    int    k = o.s;
    // groups of four: issue the gathers together, then accumulate in order
@@ -187,12 +211,12 @@ __device__ __forceinline__ double row_compute(const SpmvDev &a, const RowOps &o,
       if (k + 1 < o.e) { double p1 = __dmul_rn(vs[k + 1], x1); acc = __dadd_rn(acc, SUB ? -p1 : p1); }
       if (k + 2 < o.e) { double p2 = __dmul_rn(vs[k + 2], x2); acc = __dadd_rn(acc, SUB ? -p2 : p2); }
    }
-   if (MODE == SPMV_SET || MODE == SPMV_SET_DIV || MODE == SPMV_ADD || MODE == SPMV_RESIDUAL) return acc;
+   if (MODE == SPMV_SET || MODE == SPMV_SET_DIV || MODE == SPMV_ADD || MODE == SPMV_RESIDUAL || MODE == SPMV_GS_STEP) return acc;
    if (MODE == SPMV_AXPBY)
       return (a.beta == 0.0) ? __dmul_rn(a.alpha, acc) : __dadd_rn(__dmul_rn(a.alpha, acc), __dmul_rn(a.beta, o.yo));
    if (MODE == SPMV_JACOBI)
       return (o.d != 0.0) ? __dadd_rn(o.xo, __ddiv_rn(__dmul_rn(a.w, acc), o.d)) : o.xo;
-   /* SPMV_JACOBI_R */
+   /* SPMV_JACOBI_R, SPMV_JACOBI2: the correction */
    return (o.d != 0.0) ? __ddiv_rn(__dmul_rn(a.w, acc), o.d) : 0.0;
 }
 
@@ -219,7 +243,7 @@ __device__ __forceinline__ double row_partial(const SpmvDev &a, int k, int e, co
 template <int MODE>
 __device__ __forceinline__ double row_finish(const SpmvDev &a, const RowOps &o, double total)
 {
-   if (MODE == SPMV_SET || MODE == SPMV_SET_DIV) return total;
+   if (MODE == SPMV_SET || MODE == SPMV_SET_DIV || MODE == SPMV_GS_STEP) return total;
    if (MODE == SPMV_ADD) return __dadd_rn(o.yo, total);
    if (MODE == SPMV_AXPBY)
       return (a.beta == 0.0) ? __dmul_rn(a.alpha, total) : __dadd_rn(__dmul_rn(a.alpha, total), __dmul_rn(a.beta, o.yo));
@@ -311,9 +335,7 @@ __global__ void __launch_bounds__(ST, 4) k_spmv_tma(SpmvDev a, int nblk, int cap
             int r = cur.r0 + tid + j * ST;
             if (r < cur.r1)
             {
-               double yn = row_compute<MODE>(a, ro[j], vs, cs);
-               a.y[r]    = yn;
-               store_y2<MODE>(a, r, yn, ro[j].d);
+               double yn = store_out<MODE>(a, r, row_compute<MODE>(a, ro[j], vs, cs), ro[j].d, ro[j].xo);
                if (DOT) dacc += ro[j].dv * yn;
             }
          }
@@ -321,9 +343,7 @@ __global__ void __launch_bounds__(ST, 4) k_spmv_tma(SpmvDev a, int nblk, int cap
          {
             RowOps o;
             row_load<MODE, DOT>(a, r, ka, o);
-            double yn = row_compute<MODE>(a, o, vs, cs);
-            a.y[r]    = yn;
-            store_y2<MODE>(a, r, yn, o.d);
+            double yn = store_out<MODE>(a, r, row_compute<MODE>(a, o, vs, cs), o.d, o.xo);
             if (DOT) dacc += o.dv * yn;
          }
       }
@@ -340,9 +360,7 @@ __global__ void __launch_bounds__(ST, 4) k_spmv_tma(SpmvDev a, int nblk, int cap
             for (int o = LPR / 2; o > 0; o >>= 1) part = __dadd_rn(part, __shfl_xor_sync(0xffffffffu, part, o));
             if (valid && sub == 0)
             {
-               double yn = row_finish<MODE>(a, ro[j], part);
-               a.y[r]    = yn;
-               store_y2<MODE>(a, r, yn, ro[j].d);
+               double yn = store_out<MODE>(a, r, row_finish<MODE>(a, ro[j], part), ro[j].d, ro[j].xo);
                if (DOT) dacc += ro[j].dv * yn;
             }
          }
@@ -358,9 +376,7 @@ __global__ void __launch_bounds__(ST, 4) k_spmv_tma(SpmvDev a, int nblk, int cap
             for (int w = LPR / 2; w > 0; w >>= 1) part = __dadd_rn(part, __shfl_xor_sync(0xffffffffu, part, w));
             if (valid && sub == 0)
             {
-               double yn = row_finish<MODE>(a, o, part);
-               a.y[r]    = yn;
-               store_y2<MODE>(a, r, yn, o.d);
+               double yn = store_out<MODE>(a, r, row_finish<MODE>(a, o, part), o.d, o.xo);
                if (DOT) dacc += o.dv * yn;
             }
          }
@@ -392,7 +408,7 @@ constexpr int SELL_OFFD_BIT = 32; // sl_meta = len << 6 | offd flag << 5 | row o
 template <int MODE>
 __device__ __forceinline__ double row_epilogue(const SpmvDev &a, const RowOps &o, double acc)
 {
-   if (MODE == SPMV_SET || MODE == SPMV_SET_DIV || MODE == SPMV_ADD || MODE == SPMV_RESIDUAL) return acc;
+   if (MODE == SPMV_SET || MODE == SPMV_SET_DIV || MODE == SPMV_ADD || MODE == SPMV_RESIDUAL || MODE == SPMV_GS_STEP) return acc;
    if (MODE == SPMV_AXPBY)
       return (a.beta == 0.0) ? __dmul_rn(a.alpha, acc) : __dadd_rn(__dmul_rn(a.alpha, acc), __dmul_rn(a.beta, o.yo));
    if (MODE == SPMV_JACOBI)
@@ -403,7 +419,9 @@ __device__ __forceinline__ double row_epilogue(const SpmvDev &a, const RowOps &o
 template <int MODE, bool DOT, bool OFFD>
 __device__ __forceinline__ void sell_body(const SpmvDev &a)
 {
-   constexpr bool SUB = (MODE == SPMV_RESIDUAL || MODE == SPMV_JACOBI || MODE == SPMV_JACOBI_R);
+   constexpr bool SUB  = (MODE == SPMV_RESIDUAL || MODE == SPMV_JACOBI || MODE == SPMV_JACOBI_R || MODE == SPMV_JACOBI2);
+   constexpr bool DIAG = (MODE == SPMV_JACOBI || MODE == SPMV_JACOBI_R || MODE == SPMV_SET_DIV || MODE == SPMV_JACOBI2 || MODE == SPMV_GS_STEP);
+   constexpr bool XOLD = (MODE == SPMV_JACOBI || MODE == SPMV_JACOBI2);
    __shared__ double red[SELL_T / 32];
    __shared__ int    flag;
    const int lane = threadIdx.x & 31;
@@ -425,8 +443,8 @@ __device__ __forceinline__ void sell_body(const SpmvDev &a)
       if (valid)
       {
          if (SUB) o.b = a.b[r];
-         if (!LATE && (MODE == SPMV_JACOBI || MODE == SPMV_JACOBI_R || MODE == SPMV_SET_DIV)) o.d = a.d[r];
-         if (!LATE && MODE == SPMV_JACOBI) o.xo = a.x[r];
+         if (!LATE && DIAG) o.d = a.d[r];
+         if (!LATE && XOLD) o.xo = a.x[r];
          if (MODE == SPMV_AXPBY) o.yo = a.y[r];
       }
       double        acc = SUB ? o.b : 0.0;
@@ -477,15 +495,13 @@ __device__ __forceinline__ void sell_body(const SpmvDev &a)
       }
       if (valid)
       {
-         if (LATE && (MODE == SPMV_JACOBI || MODE == SPMV_JACOBI_R || MODE == SPMV_SET_DIV)) o.d = a.d[r];
-         if (LATE && MODE == SPMV_JACOBI) o.xo = a.x[r];
+         if (LATE && DIAG) o.d = a.d[r];
+         if (LATE && XOLD) o.xo = a.x[r];
          if (DOT) o.dv = a.dotv[r];
          // y += A x: y is read only now (live across the loop it costs 10 registers = 3 CTAs per SM),
          // so the sum is y + (a_0 x_0 + a_1 x_1 + ...) -- rounding-level difference to the CSR-order sum
          if (MODE == SPMV_ADD) acc = __dadd_rn(a.y[r], acc);
-         double yn = row_epilogue<MODE>(a, o, acc);
-         a.y[r]    = yn;
-         store_y2<MODE>(a, r, yn, o.d);
+         double yn = store_out<MODE>(a, r, row_epilogue<MODE>(a, o, acc), o.d, o.xo);
          if (DOT) dacc += o.dv * yn;
       }
    }
@@ -626,7 +642,7 @@ __global__ void __launch_bounds__(ST) k_spmv_vector(SpmvDev a)
       if (lane == 0)
       {
          double yn;
-         if (MODE == SPMV_SET || MODE == SPMV_SET_DIV) yn = acc;
+         if (MODE == SPMV_SET || MODE == SPMV_SET_DIV || MODE == SPMV_GS_STEP) yn = acc;
          else if (MODE == SPMV_AXPBY) yn = (a.beta == 0.0) ? a.alpha * acc : a.alpha * acc + a.beta * a.y[r];
          else if (MODE == SPMV_ADD) yn = a.y[r] + acc;
          else
@@ -640,8 +656,8 @@ __global__ void __launch_bounds__(ST) k_spmv_vector(SpmvDev a)
                else yn = (dd != 0.0) ? (a.w * res) / dd : 0.0;
             }
          }
-         a.y[r] = yn;
-         if (MODE == SPMV_SET_DIV) store_y2<MODE>(a, r, yn, a.d[r]);
+         constexpr bool NEED_D = (MODE == SPMV_SET_DIV || MODE == SPMV_GS_STEP);
+         yn = store_out<MODE>(a, r, yn, NEED_D ? a.d[r] : 0.0, MODE == SPMV_JACOBI2 ? a.x[r] : 0.0);
          if (DOT) dacc += a.dotv[r] * yn;
       }
    }
@@ -735,6 +751,8 @@ int spmv_launch(const DevCSR &A, int mode, const SpmvArgs &s, const OffdFuse *of
       case SPMV_AXPBY: return launch_mode<SPMV_AXPBY>(A, d, dot);
       case SPMV_JACOBI_R: return launch_mode<SPMV_JACOBI_R>(A, d, dot);
       case SPMV_SET_DIV: return launch_mode<SPMV_SET_DIV>(A, d, dot);
+      case SPMV_JACOBI2: return launch_mode<SPMV_JACOBI2>(A, d, dot);
+      case SPMV_GS_STEP: return launch_mode<SPMV_GS_STEP>(A, d, dot);
    }
    return set_error(HDK_ERR_INVALID, "unknown spmv mode %d", mode);
 }

@@ -193,7 +193,7 @@ int hdk_bicgstab(const hdk_csr *A, hdk_amg *M, const double *b_d, double *x_d, h
  * one hot kernel on the compute stream, CUDA-event timed (bench.py roofline leg).
  * kernel: 0 = SpMV y=Ax, 1 = l1-Jacobi sweep fused with residual, 2 = residual r=b-Ax,
  *         3 = PCG fused x/r update + <r,r> + first V-cycle sweep (the 64 B/row variant the solve runs),
- *         4 = V-cycle, 5 = PCG p = z + beta p */
+ *         4 = V-cycle, 5 = PCG p = z + beta p, 6 = one fused two-stage Gauss-Seidel sweep (relax 11/12) */
 int hdk_time_kernel(const hdk_csr *A, hdk_amg *M, int kernel, int reps, double *avg_ms,
                     double *algorithmic_bytes);
 /* number of kernel launches issued by this library since the last call (and reset) */
