@@ -1375,6 +1375,13 @@ int build_rap(const DevCSR &R, const DevCSR &A, const DevCSR &P, DevCSR &C, int 
 {
    stage_mark(nullptr, -1);
    int nc = R.nrows, n = A.nrows;
+   if (row_lo >= 0 && row_hi <= row_lo)
+   {
+      // no row to compute here (a rank of the distributed setup that owns no coarse point)
+      HDK_TRY(csr_alloc(C, nc, nc, 0));
+      HDK_CUDA(cudaMemsetAsync(C.rowptr, 0, sizeof(int) * ((size_t)nc + 1), g.stream));
+      return HDK_OK;
+   }
    int *q, *cap, *cnt, *crp;
    int64_t *off;
    HDK_TRY(dalloc(&q, (size_t)n + 1));

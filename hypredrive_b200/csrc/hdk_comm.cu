@@ -71,6 +71,9 @@ static int nccl_load()
 struct IpcState
 {
    bool                on = false;
+   long long           tmo = 0;              // wait budget of the in-kernel waits (clock64 ticks)
+   int                *err_h = nullptr;      // pinned, mapped: raised by a kernel whose wait ran out
+   int                *err_d = nullptr;
    char               *base = nullptr;
    size_t              size = 0;
    std::vector<char *> peer;                 // peer[r] = rank r's arena in my address space
@@ -119,7 +122,22 @@ static int ipc_setup()
    cudaIpcMemHandle_t mine;
    memset(&mine, 0, sizeof(mine));
    if (cudaMalloc((void **)&ipc.base, mb << 20) != cudaSuccess) { ok = 0; ipc.base = nullptr; cudaGetLastError(); }
-   if (ok && cudaMemset(ipc.base, 0, mb << 20) != cudaSuccess) ok = 0;
+   // zeroed on the stream the flags are used on (the allgather below orders it before any peer's store)
+   if (ok && cudaMemsetAsync(ipc.base, 0, mb << 20, g.stream) != cudaSuccess) ok = 0;
+   if (ok && !ipc.err_h)
+   {
+      if (cudaHostAlloc((void **)&ipc.err_h, sizeof(int), cudaHostAllocMapped) != cudaSuccess) { ok = 0; ipc.err_h = nullptr; cudaGetLastError(); }
+      else
+      {
+         *ipc.err_h = 0;
+         if (cudaHostGetDevicePointer((void **)&ipc.err_d, ipc.err_h, 0) != cudaSuccess) { ok = 0; cudaGetLastError(); }
+      }
+      double secs = 300.0;
+      if (getenv("HDK_IPC_TIMEOUT_S")) secs = atof(getenv("HDK_IPC_TIMEOUT_S"));
+      int khz = 0;
+      cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, g.device);
+      ipc.tmo = secs > 0.0 ? (long long)(secs * 1000.0 * (double)(khz > 0 ? khz : 1900000)) : 0;
+   }
    if (ok && cudaIpcGetMemHandle(&mine, ipc.base) != cudaSuccess) { ok = 0; cudaGetLastError(); }
    // exchange the handles (and whether every rank got this far)
    const size_t   hb = sizeof(cudaIpcMemHandle_t) + 8;
@@ -156,6 +174,7 @@ static int ipc_setup()
       for (int r = 0; r < g.nranks; r++)
          if (r != g.rank && ipc.peer[(size_t)r]) cudaIpcCloseMemHandle(ipc.peer[(size_t)r]);
       if (ipc.base) cudaFree(ipc.base);
+      if (ipc.err_h) cudaFreeHost(ipc.err_h);
       ipc = IpcState();
       cudaGetLastError();
       return HDK_OK; // NCCL send/recv path stays in use
@@ -174,7 +193,17 @@ static void ipc_teardown()
    for (int r = 0; r < (int)ipc.peer.size(); r++)
       if (r != g.rank && ipc.peer[(size_t)r]) cudaIpcCloseMemHandle(ipc.peer[(size_t)r]);
    cudaFree(ipc.base);
+   if (ipc.err_h) cudaFreeHost(ipc.err_h);
    ipc = IpcState();
+}
+
+int comm_check_error()
+{
+   if (!ipc.err_h || !*(volatile int *)ipc.err_h) return HDK_OK;
+   *ipc.err_h = 0;
+   ipc.on = false; // plans built from now on use NCCL send/recv
+   return set_error(HDK_ERR_COMM, "a peer-memory halo wait ran out of its budget (HDK_IPC_TIMEOUT_S): a neighbour rank is late or lost; "
+                                  "results of this operation are invalid.  Use HDK_HALO_IPC=0 under profilers and sanitizers");
 }
 
 int allreduce_dev(double *buf_d, int count)
@@ -284,7 +313,7 @@ int allgather_i32_host(const int *mine, int cnt, std::vector<int> &all)
 __global__ void k_pack_ipc(const double *x, const int *idx, int n, IpcSendArgs a)
 {
    if (threadIdx.x == 0 && a.seq > 2)
-      for (int p = 0; p < a.npeer; p++) wait_seq_sys(a.ack + p, a.seq - 2);
+      for (int p = 0; p < a.npeer; p++) wait_seq_sys(a.ack + p, a.seq - 2, a.tmo, a.err);
    __syncthreads();
    int i = blockIdx.x * blockDim.x + threadIdx.x;
    if (i < n)
@@ -390,6 +419,7 @@ IpcRecvArgs halo_recv_args(const hdk_csr_s &A, const double **xh)
    r.nflag  = (int)H.recv_rank.size();
    r.seq    = I.seq;
    r.ticket = I.tickets + 1;
+   r.tmo = ipc.tmo; r.err = ipc.err_d;
    for (size_t i = 0; i < H.recv_rank.size(); i++) r.ack[i] = I.src_ack[i];
    return r;
 }
@@ -489,6 +519,7 @@ int halo_exchange_begin(const hdk_csr_s &A, const double *x)
          }
          a.off[a.npeer] = H.n_send;
          a.ack = I.ack_flag; a.seq = I.seq; a.ticket = I.tickets;
+         a.tmo = ipc.tmo; a.err = ipc.err_d;
          k_pack_ipc<<<cdiv(H.n_send, 256), 256, 0, g.stream>>>(x, H.send_idx, H.n_send, a);
          HDK_LAUNCH_CHECK();
       }

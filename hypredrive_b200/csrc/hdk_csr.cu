@@ -170,7 +170,9 @@ int parcsr_build(int64_t rs, int64_t re, int64_t cs, int64_t ce, int64_t grows, 
                  bool distributed, bool keep_orig, const int64_t *indptr, const int64_t *cols, const double *vals,
                  hdk_csr_s **out, bool analyze)
 {
-   if (re < rs) return set_error(HDK_ERR_INVALID, "empty local row range [%lld,%lld]", (long long)rs, (long long)re);
+   // a slab of a distributed matrix may be empty (re == rs - 1): a rank that owns no coarse point
+   if (re < rs - 1 || (re < rs && !distributed))
+      return set_error(HDK_ERR_INVALID, "empty local row range [%lld,%lld]", (long long)rs, (long long)re);
    int64_t n64 = re - rs + 1;
    if (n64 > 2000000000LL) return set_error(HDK_ERR_UNSUPPORTED, "local rows exceed int32");
    int        n = (int)n64;
@@ -198,9 +200,12 @@ int parcsr_build(int64_t rs, int64_t re, int64_t cs, int64_t ce, int64_t grows, 
    dfree(A->offd.rowptr); A->offd.rowptr = rp_o;
    int64_t *gcol_o;
    HDK_TRY(dalloc(&gcol_o, (size_t)tot[1] + 1));
-   k_split_fill<<<cdiv(n, 256), 256, 0, g.stream>>>(indptr, cols, vals, n, cs, ce, rp_d, A->diag.col,
-                                                    A->diag.val, rp_o, gcol_o, A->offd.val, square ? 1 : 0);
-   HDK_LAUNCH_CHECK();
+   if (n > 0)
+   {
+      k_split_fill<<<cdiv(n, 256), 256, 0, g.stream>>>(indptr, cols, vals, n, cs, ce, rp_d, A->diag.col,
+                                                       A->diag.val, rp_o, gcol_o, A->offd.val, square ? 1 : 0);
+      HDK_LAUNCH_CHECK();
+   }
    int n_halo = 0;
    int64_t *uniq = nullptr;
    if (tot[1] > 0)
@@ -265,8 +270,11 @@ int parcsr_build(int64_t rs, int64_t re, int64_t cs, int64_t ce, int64_t grows, 
       HDK_CUDA(cudaMemcpyAsync(A->orig_indptr, indptr, sizeof(int64_t) * ((size_t)n + 1), cudaMemcpyDeviceToDevice, g.stream));
       HDK_CUDA(cudaMemcpyAsync(A->orig_cols, cols, sizeof(int64_t) * (size_t)nnz, cudaMemcpyDeviceToDevice, g.stream));
       HDK_CUDA(cudaMemcpyAsync(A->orig_vals, vals, sizeof(double) * (size_t)nnz, cudaMemcpyDeviceToDevice, g.stream));
-      k_orig_diag_first<<<cdiv(n, 256), 256, 0, g.stream>>>(A->orig_indptr, A->orig_cols, A->orig_vals, n, rs);
-      HDK_LAUNCH_CHECK();
+      if (n > 0)
+      {
+         k_orig_diag_first<<<cdiv(n, 256), 256, 0, g.stream>>>(A->orig_indptr, A->orig_cols, A->orig_vals, n, rs);
+         HDK_LAUNCH_CHECK();
+      }
       A->orig_nnz = nnz;
    }
    *out = A;
@@ -376,7 +384,7 @@ __global__ void k_offd_correct(const int *rows, const int *rowptr, const int *co
    if (ipc.seq)
    {
       if (threadIdx.x == 0)
-         for (int p = 0; p < ipc.nflag; p++) wait_seq_sys(ipc.flag + p, ipc.seq);
+         for (int p = 0; p < ipc.nflag; p++) wait_seq_sys(ipc.flag + p, ipc.seq, ipc.tmo, ipc.err);
       __syncthreads();
    }
    int i = blockIdx.x * blockDim.x + threadIdx.x;

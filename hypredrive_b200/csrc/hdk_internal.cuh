@@ -194,6 +194,8 @@ struct IpcSendArgs
    int                 npeer;
    unsigned long long  seq;
    unsigned           *ticket;
+   long long           tmo;             // wait budget in clock64 ticks (0: wait for ever)
+   int                *err;             // host-visible flag raised when a wait ran out of budget
 };
 struct IpcRecvArgs
 {
@@ -202,6 +204,8 @@ struct IpcRecvArgs
    unsigned long long  seq;             // 0: no wait (NCCL path)
    unsigned long long *ack[IPC_MAXP];   // remote "consumed" slot per recv neighbour
    unsigned           *ticket;
+   long long           tmo;             // as in IpcSendArgs
+   int                *err;
 };
 // off-diagonal block fused into the sliced-ELL kernel (peer-memory halo only): rows flagged in
 // sl_meta add their offd entries after waiting for the neighbours' sequence flags in-kernel
@@ -237,20 +241,25 @@ __device__ __forceinline__ void st_release_sys_u64(unsigned long long *p, unsign
 {
    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
-// bounded wait (about 10 s): a lost neighbour ends in a trap -- a loud CUDA error, not a hung GPU
-static __device__ __noinline__ void wait_seq_slow(const unsigned long long *p, unsigned long long want)
+// Wait for a neighbour's sequence flag.  The wait is bounded by a configurable budget
+// (HDK_IPC_TIMEOUT_S, default 300 s, 0 = unbounded): when it runs out the kernel raises a
+// host-visible error flag and carries on with whatever the buffer holds -- the CUDA context stays
+// usable, the host reports HDK_ERR_COMM at the end of the operation (comm_check_error) and later
+// waits return at once.  No trap: a trap would poison the context of this rank and hang its peers.
+static __device__ __noinline__ void wait_seq_slow(const unsigned long long *p, unsigned long long want, long long tmo, int *err)
 {
    const long long t0 = clock64();
    while (ld_acquire_sys_u64(p) < want)
    {
       __nanosleep(64);
-      if (clock64() - t0 > 20000000000LL) __trap();
+      if (err && *(volatile int *)err) return;                  // an earlier wait already gave up
+      if (tmo > 0 && clock64() - t0 > tmo) { if (err) *(volatile int *)err = 1; __threadfence_system(); return; }
    }
 }
-__device__ __forceinline__ void wait_seq_sys(const unsigned long long *p, unsigned long long want)
+__device__ __forceinline__ void wait_seq_sys(const unsigned long long *p, unsigned long long want, long long tmo, int *err)
 {
    if (ld_acquire_sys_u64(p) >= want) return;
-   wait_seq_slow(p, want); // out of line: keeps the waiting kernels' register count down
+   wait_seq_slow(p, want, tmo, err); // out of line: keeps the waiting kernels' register count down
 }
 #endif
 
@@ -300,6 +309,7 @@ void halo_plan_free(HaloPlan &H);
 IpcRecvArgs halo_recv_args(const hdk_csr_s &A, const double **xh); // after halo_exchange_begin
 int halo_exchange_begin(const hdk_csr_s &A, const double *x);
 int halo_exchange_end(const hdk_csr_s &A);
+int comm_check_error(); // HDK_ERR_COMM when a peer-memory wait ran out of its budget since the last call
 
 // ---------------------------------------------------------------------------------------
 // device reduction helper: block sum -> partials -> last block finishes (deterministic)

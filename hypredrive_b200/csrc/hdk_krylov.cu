@@ -163,6 +163,7 @@ done:
    cudaEventElapsedTime(&ms, g.ev_a, g.ev_b);
    k->solve_ms = ms;
    dfree(r); dfree(p); dfree(s);
+   if (rc == HDK_OK) rc = comm_check_error();
    return rc;
 }
 
@@ -330,6 +331,7 @@ done:
    for (auto q : p) dfree(q);
    for (auto q : z) dfree(q);
    dfree(r); dfree(w);
+   if (rc == HDK_OK) rc = comm_check_error();
    return rc;
 }
 
@@ -409,6 +411,7 @@ int hdk_bicgstab(const hdk_csr *A, hdk_amg *M, const double *b, double *x, hdk_k
    cudaEventElapsedTime(&ms, g.ev_a, g.ev_b);
    k->solve_ms = ms;
    for (int j = 0; j < 6; j++) dfree(v[j]);
+   if (rc == HDK_OK) rc = comm_check_error();
    return rc;
 }
 

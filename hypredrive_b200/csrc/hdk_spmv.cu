@@ -484,7 +484,7 @@ __device__ __forceinline__ void sell_body(const SpmvDev &a)
          // flagged row of a lane really waits), then continue the row in stored order
          if (!halo_ready)
          {
-            for (int p = 0; p < a.ipc.nflag; p++) wait_seq_sys(a.ipc.flag + p, a.ipc.seq);
+            for (int p = 0; p < a.ipc.nflag; p++) wait_seq_sys(a.ipc.flag + p, a.ipc.seq, a.ipc.tmo, a.ipc.err);
             halo_ready = true;
          }
          for (int k = __ldg(a.orp + r), e = __ldg(a.orp + r + 1); k < e; ++k)

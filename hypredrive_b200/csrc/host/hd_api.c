@@ -394,10 +394,18 @@ uint32_t HYPREDRV_LinearSystemSetMatrixFromCSR(HYPREDRV_t h, HYPRE_BigInt row_st
    CHECK_OBJ(h);
    if (!indptr) return fail(HYPREDRV_ERROR_INVALID_VAL, "%s", "indptr cannot be NULL");
    if (row_end < row_start) return fail(HYPREDRV_ERROR_INVALID_VAL, "%s", "row_end must be >= row_start");
+   /* row and entry counts must fit HYPRE_Int (32 bit here), reference linsys.c:1226-1262; checked
+    * before indptr[n] is touched (tests/test_setmatrix_from_csr.c:373-384 passes a 2-entry indptr) */
+   if ((long long)row_end - (long long)row_start >= 2147483647LL)
+      return fail(HYPREDRV_ERROR_INVALID_VAL, "%s", "local row count does not fit HYPRE_Int");
    int64_t n = (int64_t)(row_end - row_start + 1);
    if (indptr[0] < 0) return fail(HYPREDRV_ERROR_INVALID_VAL, "%s", "indptr[0] must be nonnegative");
+   if (n == 1 && (long long)indptr[1] - (long long)indptr[0] > 2147483647LL)
+      return fail(HYPREDRV_ERROR_INVALID_VAL, "%s", "local nonzero count does not fit HYPRE_Int");
    for (int64_t i = 0; i < n; i++)
       if (indptr[i + 1] < indptr[i]) return fail(HYPREDRV_ERROR_INVALID_VAL, "%s", "indptr must be nondecreasing");
+   if ((long long)indptr[n] - (long long)indptr[0] > 2147483647LL)
+      return fail(HYPREDRV_ERROR_INVALID_VAL, "%s", "local nonzero count does not fit HYPRE_Int");
    if (indptr[n] > indptr[0] && (!col_indices || !data))
       return fail(HYPREDRV_ERROR_INVALID_VAL, "%s", "col_indices and data cannot be NULL when nnz > 0");
    double   t0 = hd_wtime();

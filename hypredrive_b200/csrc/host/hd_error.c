@@ -81,3 +81,15 @@ void hd_err_describe(uint32_t code)
    hd_err_print_msgs();
    fflush(stderr);
 }
+
+/* ---- the reference's internal error-module entry points that its own unit tests bind directly
+ * (include/internal/error.h:56-79 of the reference; e.g. tests/test_setmatrix_from_csr.c:255):
+ * exported so those tests link against this library unmodified ---- */
+void     hypredrv_ErrorCodeSet(uint32_t bits) { hd_err_set(bits); }
+uint32_t hypredrv_ErrorCodeGet(void) { return hd_err_get(); }
+int      hypredrv_ErrorCodeActive(void) { return hd_err_get() != 0; }
+void     hypredrv_ErrorCodeReset(uint32_t bits) { g_code &= ~bits; }
+void     hypredrv_ErrorCodeResetAll(void) { g_code = 0; }
+void     hypredrv_ErrorStateReset(void) { hd_err_reset(); }
+void     hypredrv_ErrorMsgPrint(void) { hd_err_print_msgs(); }
+void     hypredrv_ErrorMsgClear(void) { hd_err_clear_msgs(); }

@@ -9,6 +9,10 @@
 
 HYPRE_Int HYPRE_Initialize(void) { return hdk_init(-1); }
 HYPRE_Int HYPRE_Finalize(void) { return 0; }
+/* hypre's host/device switches: accepted (callers such as the reference's tests request host
+ * execution for their own assembly); the solve path of this library always runs on the device */
+HYPRE_Int HYPRE_SetMemoryLocation(HYPRE_MemoryLocation loc) { (void)loc; return 0; }
+HYPRE_Int HYPRE_SetExecutionPolicy(HYPRE_ExecutionPolicy policy) { (void)policy; return 0; }
 
 HYPRE_Int HYPRE_IJMatrixCreate(MPI_Comm comm, HYPRE_BigInt ilower, HYPRE_BigInt iupper, HYPRE_BigInt jlower,
                                HYPRE_BigInt jupper, HYPRE_IJMatrix *matrix)

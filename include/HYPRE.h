@@ -17,8 +17,11 @@ typedef long long HYPRE_BigInt;
 typedef double    HYPRE_Real;
 typedef double    HYPRE_Complex;
 typedef int       HYPRE_MemoryLocation;
+typedef int       HYPRE_ExecutionPolicy;
 #define HYPRE_MEMORY_HOST 0
 #define HYPRE_MEMORY_DEVICE 1
+#define HYPRE_EXEC_HOST 0
+#define HYPRE_EXEC_DEVICE 1
 #define HYPRE_PARCSR 5555
 #define HYPRE_USING_GPU 1
 #define HYPRE_USING_CUDA 1
@@ -37,6 +40,9 @@ typedef struct hypre_Solver_struct   *HYPRE_Solver;
 
 HYPRE_Int HYPRE_Initialize(void);
 HYPRE_Int HYPRE_Finalize(void);
+/* accepted and recorded; the solve path of this library always executes on the device */
+HYPRE_Int HYPRE_SetMemoryLocation(HYPRE_MemoryLocation loc);
+HYPRE_Int HYPRE_SetExecutionPolicy(HYPRE_ExecutionPolicy policy);
 
 HYPRE_Int HYPRE_IJMatrixCreate(MPI_Comm comm, HYPRE_BigInt ilower, HYPRE_BigInt iupper, HYPRE_BigInt jlower,
                                HYPRE_BigInt jupper, HYPRE_IJMatrix *matrix);
