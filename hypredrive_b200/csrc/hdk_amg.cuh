@@ -47,6 +47,7 @@ struct hdk_amg_s
    int                        tail_level = 0;   // level of `tail` that continues this hierarchy
    int64_t                    tail_off = 0, tail_cnt = 0, tail_n = 0; // my slice of the first replicated level
    double                    *full_f = nullptr, *full_u = nullptr;
+   hdk::IpcGather             gather;   // peer-memory all-gather of the slices of full_f (replaces the all-reduce)
 };
 
 // pieces of the serial setup (hdk_amg_setup.cu) that the distributed driver (hdk_amg_dist.cu) reuses

@@ -1081,6 +1081,7 @@ extern "C" int setup_distributed_rows(const hdk_csr_s *A0, const hdk_amg_params 
    }
    if (rc == HDK_OK) rc = dalloc(&M->full_f, (size_t)M->tail_n + 8);
    if (rc == HDK_OK) rc = dalloc(&M->full_u, (size_t)M->tail_n + 8);
+   if (rc == HDK_OK && g.nranks > 1 && M->nlev > 0) rc = ipc_gather_alloc(M->gather, M->tail_n);
    if (rc == HDK_OK && cudaStreamSynchronize(g.stream) != cudaSuccess)
       rc = set_error(HDK_ERR_CUDA, "distributed setup sync failed: %s", cudaGetErrorString(cudaGetLastError()));
    setup_stage_mark("finalize", -2);

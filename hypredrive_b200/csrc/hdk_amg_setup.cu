@@ -1702,6 +1702,7 @@ int hdk_amg_destroy(hdk_amg *M)
          for (int w = 0; w < 2; w++) { dfree(L.dbg_ip[w]); dfree(L.dbg_col[w]); dfree(L.dbg_val[w]); }
       }
       dfree(M->ge_inv); dfree(M->full_f); dfree(M->full_u);
+      ipc_gather_free(M->gather);
    }
    if (M->tail) hdk_amg_destroy(M->tail);
    delete M;

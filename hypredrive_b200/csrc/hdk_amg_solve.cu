@@ -208,8 +208,12 @@ int amg_cycle(hdk_amg_s *M, const double *f0, double *u0, bool zero_guess, int f
       else
       {
          // first replicated level: my rows of the coarse right-hand side go into the full vector
-         HDK_TRY(vec_fill(M->full_f, 0.0, M->tail_n));
-         rr.y = M->full_f + M->tail_off;
+         if (M->gather.on) rr.y = ipc_gather_buffer(M->gather) + M->tail_off; // every slice is overwritten by its owner
+         else
+         {
+            HDK_TRY(vec_fill(M->full_f, 0.0, M->tail_n));
+            rr.y = M->full_f + M->tail_off;
+         }
       }
       if (l + 1 < nfine && p.sweeps_down > 0 && is_jacobi(p.relax_down))
       {
@@ -224,8 +228,17 @@ int amg_cycle(hdk_amg_s *M, const double *f0, double *u0, bool zero_guess, int f
    const double *coarse_sol = nullptr; // solution feeding the prolongation of level nfine-1
    if (has_tail)
    {
-      HDK_TRY(allreduce_dev(M->full_f, (int)M->tail_n));
-      HDK_TRY(amg_cycle(M->tail, M->full_f, M->full_u, true, FIN_NONE, nullptr, M->tail_level));
+      // the ranks own disjoint slices of the coarse right-hand side: with the peer-memory arena each
+      // rank stores its slice into every peer's copy (one kernel + a flag wait), else NCCL sums the
+      // zero-padded vectors
+      const double *tf = M->full_f;
+      if (M->gather.on)
+      {
+         HDK_TRY(ipc_gather(M->gather, M->tail_off, M->tail_cnt));
+         tf = M->gather.buf[M->gather.seq & 1];
+      }
+      else HDK_TRY(allreduce_dev(M->full_f, (int)M->tail_n));
+      HDK_TRY(amg_cycle(M->tail, tf, M->full_u, true, FIN_NONE, nullptr, M->tail_level));
       coarse_sol = M->full_u;
    }
    else

@@ -68,9 +68,32 @@ static int nccl_load()
 // IPC at communicator creation.  Halo plans carve their receive buffers and flag slots out of
 // it, so a neighbour can store into them directly over NVLink.
 // ------------------------------------------------------------------------------------------
+// Reduction mailbox (the first MAIL_BYTES of every arena): slot[parity][source rank][MB_VALS] doubles
+// followed by flag[parity][source rank] sequence numbers.  An all-reduce of a few scalars is ONE
+// small kernel: every rank stores its partial into every peer's mailbox over NVLink, raises the
+// flag, waits for the peers' flags in its own mailbox and adds the R partials in rank order --
+// the same order on every rank, so all ranks hold bit-identical sums (and take identical
+// decisions), and the scalar recurrence of the Krylov driver (apply_fin) runs in the same kernel.
+constexpr int    MB_MAXR = 16, MB_VALS = 4;
+constexpr size_t MAIL_SLOT_BYTES = (size_t)2 * MB_MAXR * MB_VALS * sizeof(double);
+constexpr size_t MAIL_BYTES = 8192; // slots (1 KB) + flags (256 B), padded
+struct MailArgs
+{
+   double             *peer_slot[MB_MAXR];
+   unsigned long long *peer_flag[MB_MAXR];
+   double             *my_slot;
+   unsigned long long *my_flag;
+   int                 R, me;
+   unsigned long long  seq;
+   long long           tmo;
+   int                *err;
+};
+
 struct IpcState
 {
    bool                on = false;
+   bool                mail_on = false;
+   unsigned long long  mail_seq = 0;
    long long           tmo = 0;              // wait budget of the in-kernel waits (clock64 ticks)
    int                *err_h = nullptr;      // pinned, mapped: raised by a kernel whose wait ran out
    int                *err_d = nullptr;
@@ -181,8 +204,10 @@ static int ipc_setup()
    }
    ipc.size = mb << 20;
    ipc.free_.clear();
-   ipc.free_.emplace(0, ipc.size);
+   ipc.free_.emplace(MAIL_BYTES, ipc.size - MAIL_BYTES); // the first bytes of every arena are its reduction mailbox
    ipc.on = true;
+   ipc.mail_seq = 0;
+   ipc.mail_on = g.nranks <= MB_MAXR && !(getenv("HDK_MAILBOX") && atoi(getenv("HDK_MAILBOX")) == 0);
    return HDK_OK;
 }
 
@@ -206,10 +231,168 @@ int comm_check_error()
                                   "results of this operation are invalid.  Use HDK_HALO_IPC=0 under profilers and sanitizers");
 }
 
+__global__ void k_apply_fin_comm(int fin, const double *v, double *out, double *scal) { apply_fin(fin, v[0], out, scal); }
+
+__global__ void __launch_bounds__(32) k_mailbox_allreduce(double *vals, int count, MailArgs a, int fin, double *fin_out, double *scal)
+{
+   const int lane = threadIdx.x, par = (int)(a.seq & 1ull);
+   if (lane < a.R)
+   {
+      double *dst = a.peer_slot[lane] + ((size_t)par * MB_MAXR + a.me) * MB_VALS;
+      for (int c = 0; c < count; c++) dst[c] = vals[c];
+      __threadfence_system();
+      st_release_sys_u64(a.peer_flag[lane] + par * MB_MAXR + a.me, a.seq);
+      wait_seq_sys(a.my_flag + par * MB_MAXR + lane, a.seq, a.tmo, a.err);
+   }
+   __syncwarp();
+   if (lane == 0)
+   {
+      for (int c = 0; c < count; c++)
+      {
+         double s = 0.0;
+         for (int p = 0; p < a.R; p++) s += __ldcg(a.my_slot + ((size_t)par * MB_MAXR + p) * MB_VALS + c); // rank order
+         if (fin != FIN_NONE && c == 0) apply_fin(fin, s, fin_out, scal);
+         else vals[c] = s;
+      }
+   }
+}
+
+static MailArgs mail_args()
+{
+   MailArgs a;
+   memset(&a, 0, sizeof(a));
+   a.R = g.nranks; a.me = g.rank; a.seq = ++ipc.mail_seq; a.tmo = ipc.tmo; a.err = ipc.err_d;
+   for (int p = 0; p < g.nranks; p++)
+   {
+      a.peer_slot[p] = reinterpret_cast<double *>(ipc.peer[(size_t)p]);
+      a.peer_flag[p] = reinterpret_cast<unsigned long long *>(ipc.peer[(size_t)p] + MAIL_SLOT_BYTES);
+   }
+   a.my_slot = a.peer_slot[g.rank]; a.my_flag = a.peer_flag[g.rank];
+   return a;
+}
+
+// sum over ranks of buf_d[0..count) in place; with fin != FIN_NONE the sum of buf_d[0] is handed to
+// the Krylov scalar recurrence (apply_fin) instead of being stored
+int allreduce_fin_dev(double *buf_d, int count, int fin, double *fin_out)
+{
+   if (g.nranks <= 1)
+   {
+      if (fin != FIN_NONE) { k_apply_fin_comm<<<1, 1, 0, g.stream>>>(fin, buf_d, fin_out, g.dscal); HDK_LAUNCH_CHECK(); }
+      return HDK_OK;
+   }
+   if (ipc.on && ipc.mail_on && count <= MB_VALS)
+   {
+      k_mailbox_allreduce<<<1, 32, 0, g.stream>>>(buf_d, count, mail_args(), fin, fin_out, g.dscal);
+      HDK_LAUNCH_CHECK();
+      return HDK_OK;
+   }
+   HDK_NCCL(nccl.AllReduce(buf_d, buf_d, (size_t)count, NCCL_FLOAT64, NCCL_SUM, (ncclComm_p)g.nccl, g.stream));
+   if (fin != FIN_NONE) { k_apply_fin_comm<<<1, 1, 0, g.stream>>>(fin, buf_d, fin_out, g.dscal); HDK_LAUNCH_CHECK(); }
+   return HDK_OK;
+}
+
 int allreduce_dev(double *buf_d, int count)
 {
    if (g.nranks <= 1) return HDK_OK;
-   HDK_NCCL(nccl.AllReduce(buf_d, buf_d, (size_t)count, NCCL_FLOAT64, NCCL_SUM, (ncclComm_p)g.nccl, g.stream));
+   return allreduce_fin_dev(buf_d, count, FIN_NONE, nullptr);
+}
+
+// ---- all-gather of the ranks' slices of a replicated vector through peer stores ---------------
+// (the restricted right-hand side of the first replicated level: every rank owns a disjoint slice,
+// so the sum over ranks is an all-gather).  buf lives in the arena, two halves by sequence parity.
+struct GatherArgs
+{
+   double             *peer_buf[MB_MAXR];   // peer's vector (current half)
+   unsigned long long *peer_flag[MB_MAXR];  // peer's flag slot for me
+   const unsigned long long *my_flag;       // my flag slots, one per source rank
+   int                 R, me;
+   unsigned long long  seq;
+   unsigned           *ticket;
+   long long           tmo;
+   int                *err;
+};
+__global__ void k_ipc_gather_send(const double *mine, int64_t off, int64_t cnt, GatherArgs a)
+{
+   const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+   if (i < cnt)
+   {
+      const double v = mine[off + i];
+      for (int p = 0; p < a.R; p++) if (p != a.me) a.peer_buf[p][off + i] = v;
+   }
+   __threadfence_system();
+   __syncthreads();
+   if (threadIdx.x == 0)
+   {
+      unsigned t = atomicInc(a.ticket, gridDim.x - 1);
+      if (t == gridDim.x - 1)
+      {
+         __threadfence_system();
+         for (int p = 0; p < a.R; p++) if (p != a.me) st_release_sys_u64(a.peer_flag[p], a.seq);
+      }
+   }
+}
+__global__ void __launch_bounds__(32) k_ipc_gather_wait(GatherArgs a)
+{
+   const int lane = threadIdx.x;
+   if (lane < a.R && lane != a.me) wait_seq_sys(a.my_flag + lane, a.seq, a.tmo, a.err);
+}
+
+int ipc_gather_alloc(IpcGather &G, int64_t n)
+{
+   G = IpcGather();
+   if (!ipc.on || !ipc.mail_on || g.nranks > MB_MAXR) return HDK_OK;
+   arena_collect();
+   const size_t half = (((size_t)n + 15) & ~(size_t)15) * sizeof(double);
+   const size_t bytes = 256 + 2 * half;
+   int64_t off = arena_alloc(bytes);
+   if (off >= 0) HDK_CUDA(cudaMemsetAsync(ipc.base + off, 0, 256, g.stream));
+   std::vector<int64_t> offs;
+   HDK_TRY(allgather_i64_host(off, offs)); // also orders the memset before any peer's first store
+   bool all_ok = true;
+   for (int64_t v : offs) if (v < 0) all_ok = false;
+   if (!all_ok)
+   {
+      if (off >= 0) arena_release_now((size_t)off, (bytes + 255) & ~(size_t)255);
+      return HDK_OK;
+   }
+   G.on = true; G.n = n; G.region_off = off; G.region_bytes = (bytes + 255) & ~(size_t)255; G.seq = 0;
+   G.flags = reinterpret_cast<unsigned long long *>(ipc.base + off);
+   G.buf[0] = reinterpret_cast<double *>(ipc.base + off + 256);
+   G.buf[1] = reinterpret_cast<double *>(ipc.base + off + 256 + half);
+   for (int p = 0; p < g.nranks; p++)
+   {
+      char *rb = ipc.peer[(size_t)p] + offs[(size_t)p];
+      G.peer_buf[0][p] = reinterpret_cast<double *>(rb + 256);
+      G.peer_buf[1][p] = reinterpret_cast<double *>(rb + 256 + half);
+      G.peer_flag[p]   = reinterpret_cast<unsigned long long *>(rb) + g.rank;
+   }
+   HDK_TRY(dalloc(&G.ticket, 1));
+   HDK_CUDA(cudaMemsetAsync(G.ticket, 0, sizeof(unsigned), g.stream));
+   return HDK_OK;
+}
+void ipc_gather_free(IpcGather &G)
+{
+   if (!G.on) return;
+   dfree(G.ticket);
+   if (ipc.on) ipc.pending.emplace_back((size_t)G.region_off, G.region_bytes);
+   G = IpcGather();
+}
+// the half the next gather fills (the owner writes its own slice there before calling ipc_gather)
+double *ipc_gather_buffer(IpcGather &G) { return G.buf[(G.seq + 1) & 1]; }
+// my slice [off, off + cnt) of the current buffer goes to every peer; returns when all slices are in
+int ipc_gather(IpcGather &G, int64_t off, int64_t cnt)
+{
+   G.seq++;
+   GatherArgs a;
+   memset(&a, 0, sizeof(a));
+   a.R = g.nranks; a.me = g.rank; a.seq = G.seq; a.ticket = G.ticket; a.tmo = ipc.tmo; a.err = ipc.err_d;
+   a.my_flag = G.flags;
+   for (int p = 0; p < g.nranks; p++) { a.peer_buf[p] = G.peer_buf[G.seq & 1][p]; a.peer_flag[p] = G.peer_flag[p]; }
+   const int grid = cnt > 0 ? cdiv(cnt, 256) : 1;
+   k_ipc_gather_send<<<grid, 256, 0, g.stream>>>(G.buf[G.seq & 1], off, cnt, a);
+   HDK_LAUNCH_CHECK();
+   k_ipc_gather_wait<<<1, 32, 0, g.stream>>>(a);
+   HDK_LAUNCH_CHECK();
    return HDK_OK;
 }
 

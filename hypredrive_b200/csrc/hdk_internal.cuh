@@ -176,7 +176,8 @@ int pcg_update_xr(double *x, double *r, const double *p, const double *s, int64_
                   double *z0 = nullptr, const double *zd = nullptr, double zw = 1.0); // optional z0 = (zw r)/zd
 int pcg_update_p(double *p, const double *z, int64_t n, const double *scal);
 int vec_copy_dot(double *z, const double *r, int64_t n, int fin, double *out_d);      // z=r, <r,r>
-int allreduce_dev(double *buf_d, int count);                                          // NCCL sum (no-op on 1 rank)
+int allreduce_dev(double *buf_d, int count);                                          // sum over ranks (no-op on 1 rank)
+int allreduce_fin_dev(double *buf_d, int count, int fin, double *fin_out);            // ... + Krylov scalar recurrence, one kernel
 
 // ---------------------------------------------------------------------------------------
 // ParCSR of one rank: diag + offd blocks, halo bookkeeping
@@ -262,6 +263,24 @@ __device__ __forceinline__ void wait_seq_sys(const unsigned long long *p, unsign
    wait_seq_slow(p, want, tmo, err); // out of line: keeps the waiting kernels' register count down
 }
 #endif
+
+// all-gather of a replicated vector's slices through peer stores (hdk_comm.cu)
+struct IpcGather
+{
+   bool                on = false;
+   int64_t             n = 0, region_off = -1;
+   size_t              region_bytes = 0;
+   unsigned long long  seq = 0;
+   unsigned long long *flags = nullptr;        // my flag slots, one per source rank
+   double             *buf[2] = {nullptr, nullptr};
+   double             *peer_buf[2][16];
+   unsigned long long *peer_flag[16];
+   unsigned           *ticket = nullptr;
+};
+int     ipc_gather_alloc(IpcGather &G, int64_t n); // collective; G.on stays false without the peer-memory arena
+void    ipc_gather_free(IpcGather &G);
+double *ipc_gather_buffer(IpcGather &G);
+int     ipc_gather(IpcGather &G, int64_t off, int64_t cnt);
 
 struct HaloPlan
 {

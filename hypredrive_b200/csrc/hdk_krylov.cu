@@ -11,20 +11,13 @@
 
 namespace hdk {
 
-__global__ void k_apply_fin(int fin, const double *v, double *out, double *scal)
-{
-   apply_fin(fin, v[0], out, scal);
-}
-
 // with one rank the last block of the producing kernel applies `fin`; with several ranks the
-// local partial sits in S_TMP0 and is summed over NVLink first
+// local partial sits in S_TMP0 and one mailbox kernel sums it over NVLink (rank order, identical on
+// every rank) and applies the recurrence
 static int finish_dot(int fin, double *out)
 {
    if (g.nranks <= 1) return HDK_OK;
-   HDK_TRY(allreduce_dev(g.dscal + S_TMP0, 1));
-   k_apply_fin<<<1, 1, 0, g.stream>>>(fin, g.dscal + S_TMP0, out, g.dscal);
-   HDK_LAUNCH_CHECK();
-   return HDK_OK;
+   return allreduce_fin_dev(g.dscal + S_TMP0, 1, fin, out);
 }
 static inline int local_fin(int fin) { return g.nranks <= 1 ? fin : FIN_STORE; }
 static inline double *local_out(double *out) { return g.nranks <= 1 ? out : g.dscal + S_TMP0; }

@@ -623,7 +623,7 @@ uint32_t HYPREDRV_LinearSystemReadMatrix(HYPREDRV_t h)
       hdk_csr_info(h->A, &lr, &gr, &ln, &gn);
       printf("====================================================================================\n");
       printf("Solving linear system #%d with %lld rows and %lld nonzeros...\n", h->stats->ls_id + 1, (long long)gr, (long long)gn);
-      printf("====================================================================================\n");
+      /* the closing rule is printed by the statistics summary (reference stats.c:1231) */
       fflush(stdout);
    }
    h->stats->ls_id++;

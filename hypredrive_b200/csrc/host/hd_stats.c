@@ -26,14 +26,19 @@ hd_stats *hd_stats_create(void)
 
 void hd_stats_print(const hd_stats *s, FILE *fp)
 {
-   const char  *unit = s->use_millisec ? "[ms]" : " [s]";
+   /* header cells are right-aligned in their column width like the reference's PrintHeader
+    * (src/internal/stats.c:564-595): "   times [s]" / "  times [ms]" */
+   char         unit[32];
    const double f    = s->use_millisec ? 1000.0 : 1.0;
+   snprintf(unit, sizeof(unit), "times %s", s->use_millisec ? "[ms]" : "[s]");
    const char  *div  = "+--------+-------------+-------------+-------------+------------+------------+--------+\n";
+   for (int i = 0; i < 84; i++) fputc('=', fp); /* PRINT_EQUAL_LINE, stats.c:1231; width as in the golden outputs under examples/refOutput */
+   fputc('\n', fp);
    if (s->name[0]) fprintf(fp, "\n\nSTATISTICS SUMMARY for %s:\n\n", s->name);
    else fprintf(fp, "\n\nSTATISTICS SUMMARY:\n\n");
    fprintf(fp, "%s", div);
    fprintf(fp, "|        |    LS build |       setup |       solve |    initial |   relative |        |\n");
-   fprintf(fp, "|  Entry |  times %s |  times %s |  times %s |  res. norm |  res. norm |  iters |\n", unit, unit, unit);
+   fprintf(fp, "|  Entry | %11s | %11s | %11s |  res. norm |  res. norm |  iters |\n", unit, unit, unit);
    fprintf(fp, "%s", div);
    int shown = 0;
    for (int i = 0; i <= s->counter && i < HD_STATS_MAX; i++)

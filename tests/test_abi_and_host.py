@@ -18,6 +18,7 @@ INVALID_SOLVER, INVALID_PRECON, UNKNOWN_OBJ, NOT_INIT = 0x20000, 0x40000, 0x2000
 def _declared(header, prefix):
     text = open(os.path.join(ROOT, "include", header)).read()
     text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    text = "\n".join(l for l in text.splitlines() if not l.lstrip().startswith("#"))   # macros are not exports
     return sorted(set(re.findall(r"\b(%s\w+)\s*\(" % prefix, text)))
 
 
@@ -213,9 +214,10 @@ def test_sliced_ell_kernel_register_budget():
     lib = os.path.join(ROOT, "hypredrive_b200", "lib", "libHYPREDRV.so")
     out = subprocess.run([cuobjdump, "--dump-resource-usage", lib], capture_output=True, text=True).stdout
     found = re.findall(r"Function _ZN3hdk11k_spmv_sellILi(\d)ELb([01])ELb([01])EEEvNS_7SpmvDevE:\s*\n\s*REG:(\d+) STACK:(\d+)", out)
-    assert len(found) >= 28, len(found)
+    assert len(found) >= 36, len(found)               # 9 epilogue modes x fused dot x fused off-diagonal block
     for mode, dot, offd, reg, stack in found:
-        limit = 32 if (dot == "0" and offd == "0") else 40
+        # mode 7 (two-stage GS first stage) writes two vectors per row: 40 registers also when plain
+        limit = 32 if (dot == "0" and offd == "0" and mode != "7") else 40
         assert int(reg) <= limit, (mode, dot, offd, reg)
         assert int(stack) <= 8, (mode, dot, offd, stack)
 
