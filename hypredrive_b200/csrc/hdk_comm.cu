@@ -95,8 +95,8 @@ struct IpcState
    bool                mail_on = false;
    unsigned long long  mail_seq = 0;
    long long           tmo = 0;              // wait budget of the in-kernel waits (clock64 ticks)
-   int                *err_h = nullptr;      // pinned, mapped: raised by a kernel whose wait ran out
-   int                *err_d = nullptr;
+   int                *err_d = nullptr;      // device word raised by a kernel whose wait ran out (polled from
+                                             // L2 by the waiting threads, read by the host at the end of a solve)
    char               *base = nullptr;
    size_t              size = 0;
    std::vector<char *> peer;                 // peer[r] = rank r's arena in my address space
@@ -147,14 +147,10 @@ static int ipc_setup()
    if (cudaMalloc((void **)&ipc.base, mb << 20) != cudaSuccess) { ok = 0; ipc.base = nullptr; cudaGetLastError(); }
    // zeroed on the stream the flags are used on (the allgather below orders it before any peer's store)
    if (ok && cudaMemsetAsync(ipc.base, 0, mb << 20, g.stream) != cudaSuccess) ok = 0;
-   if (ok && !ipc.err_h)
+   if (ok && !ipc.err_d)
    {
-      if (cudaHostAlloc((void **)&ipc.err_h, sizeof(int), cudaHostAllocMapped) != cudaSuccess) { ok = 0; ipc.err_h = nullptr; cudaGetLastError(); }
-      else
-      {
-         *ipc.err_h = 0;
-         if (cudaHostGetDevicePointer((void **)&ipc.err_d, ipc.err_h, 0) != cudaSuccess) { ok = 0; cudaGetLastError(); }
-      }
+      if (cudaMalloc((void **)&ipc.err_d, sizeof(int)) != cudaSuccess) { ok = 0; ipc.err_d = nullptr; cudaGetLastError(); }
+      else if (cudaMemsetAsync(ipc.err_d, 0, sizeof(int), g.stream) != cudaSuccess) ok = 0;
       double secs = 300.0;
       if (getenv("HDK_IPC_TIMEOUT_S")) secs = atof(getenv("HDK_IPC_TIMEOUT_S"));
       int khz = 0;
@@ -197,7 +193,7 @@ static int ipc_setup()
       for (int r = 0; r < g.nranks; r++)
          if (r != g.rank && ipc.peer[(size_t)r]) cudaIpcCloseMemHandle(ipc.peer[(size_t)r]);
       if (ipc.base) cudaFree(ipc.base);
-      if (ipc.err_h) cudaFreeHost(ipc.err_h);
+      if (ipc.err_d) cudaFree(ipc.err_d);
       ipc = IpcState();
       cudaGetLastError();
       return HDK_OK; // NCCL send/recv path stays in use
@@ -218,14 +214,18 @@ static void ipc_teardown()
    for (int r = 0; r < (int)ipc.peer.size(); r++)
       if (r != g.rank && ipc.peer[(size_t)r]) cudaIpcCloseMemHandle(ipc.peer[(size_t)r]);
    cudaFree(ipc.base);
-   if (ipc.err_h) cudaFreeHost(ipc.err_h);
+   if (ipc.err_d) cudaFree(ipc.err_d);
    ipc = IpcState();
 }
 
 int comm_check_error()
 {
-   if (!ipc.err_h || !*(volatile int *)ipc.err_h) return HDK_OK;
-   *ipc.err_h = 0;
+   if (!ipc.err_d) return HDK_OK;
+   int flag = 0;
+   HDK_CUDA(cudaMemcpyAsync(&flag, ipc.err_d, sizeof(int), cudaMemcpyDeviceToHost, g.stream));
+   HDK_CUDA(cudaStreamSynchronize(g.stream));
+   if (!flag) return HDK_OK;
+   HDK_CUDA(cudaMemsetAsync(ipc.err_d, 0, sizeof(int), g.stream));
    ipc.on = false; // plans built from now on use NCCL send/recv
    return set_error(HDK_ERR_COMM, "a peer-memory halo wait ran out of its budget (HDK_IPC_TIMEOUT_S): a neighbour rank is late or lost; "
                                   "results of this operation are invalid.  Use HDK_HALO_IPC=0 under profilers and sanitizers");

@@ -196,7 +196,7 @@ struct IpcSendArgs
    unsigned long long  seq;
    unsigned           *ticket;
    long long           tmo;             // wait budget in clock64 ticks (0: wait for ever)
-   int                *err;             // host-visible flag raised when a wait ran out of budget
+   int                *err;             // device flag raised when a wait ran out of budget (read by the host later)
 };
 struct IpcRecvArgs
 {
@@ -243,18 +243,23 @@ __device__ __forceinline__ void st_release_sys_u64(unsigned long long *p, unsign
    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 // Wait for a neighbour's sequence flag.  The wait is bounded by a configurable budget
-// (HDK_IPC_TIMEOUT_S, default 300 s, 0 = unbounded): when it runs out the kernel raises a
-// host-visible error flag and carries on with whatever the buffer holds -- the CUDA context stays
+// (HDK_IPC_TIMEOUT_S, default 300 s, 0 = unbounded): when it runs out the kernel raises an
+// error flag in device memory and carries on with whatever the buffer holds -- the CUDA context stays
 // usable, the host reports HDK_ERR_COMM at the end of the operation (comm_check_error) and later
 // waits return at once.  No trap: a trap would poison the context of this rank and hang its peers.
 static __device__ __noinline__ void wait_seq_slow(const unsigned long long *p, unsigned long long want, long long tmo, int *err)
 {
    const long long t0 = clock64();
+   unsigned        spins = 0;
    while (ld_acquire_sys_u64(p) < want)
    {
       __nanosleep(64);
-      if (err && *(volatile int *)err) return;                  // an earlier wait already gave up
-      if (tmo > 0 && clock64() - t0 > tmo) { if (err) *(volatile int *)err = 1; __threadfence_system(); return; }
+      if (tmo > 0 && (++spins & 1023u) == 0)
+      {
+         // the flag lives in device memory: an L2 hit for the other waiters, which give up with it
+         if (clock64() - t0 > tmo) { if (err) *(volatile int *)err = 1; return; }
+         if (err && *(volatile int *)err) return;
+      }
    }
 }
 __device__ __forceinline__ void wait_seq_sys(const unsigned long long *p, unsigned long long want, long long tmo, int *err)

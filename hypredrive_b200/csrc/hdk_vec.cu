@@ -258,16 +258,32 @@ __global__ void __launch_bounds__(VT) k_copy_dot(double *__restrict__ z, const d
    grid_finish<VT>(bs, partials, ticket, fin, out, scal, sm, &flag);
 }
 
-// counter-hash uniform values in [-1,1): splitmix64 of (seed, global index)
-__global__ void __launch_bounds__(VT) k_random(double *x, int64_t n, int64_t off, uint64_t seed)
+// HYPRE_ParVectorSetRandomValues(v, seed) on one rank: hypre_SeedRand(seed), then x_i = 2 hypre_Rand() - 1
+// in index order (hypre seq_mv/vector.c, utilities/random.c -- the Park-Miller generator).  Element i is
+// reached by skip-ahead, s_i = seed * 16807^(i+1) mod (2^31 - 1), with i the GLOBAL index, so the vector
+// does not depend on the partition (hypre itself re-seeds every rank with seed * (rank + 1)).
+__device__ __forceinline__ uint32_t pm_mulmod31(uint32_t a, uint32_t b)
+{
+   const uint64_t M = 2147483647ull;
+   uint64_t p = (uint64_t)a * b;
+   uint64_t r = (p & M) + (p >> 31);
+   r          = (r & M) + (r >> 31);
+   if (r >= M) r -= M;
+   return (uint32_t)r;
+}
+__global__ void __launch_bounds__(VT) k_random(double *x, int64_t n, int64_t off, uint32_t seed0)
 {
    for (int64_t i = blockIdx.x * (int64_t)VT + threadIdx.x; i < n; i += (int64_t)gridDim.x * VT)
    {
-      uint64_t z = (uint64_t)(i + off) + seed * 0x9E3779B97F4A7C15ull + 0x9E3779B97F4A7C15ull;
-      z          = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
-      z          = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
-      z          = z ^ (z >> 31);
-      x[i]       = (double)(z >> 11) * (2.0 / 9007199254740992.0) - 1.0;
+      uint64_t e = (uint64_t)(off + i) + 1;
+      uint32_t base = 16807u, acc = seed0;
+      while (e)
+      {
+         if (e & 1) acc = pm_mulmod31(acc, base);
+         base = pm_mulmod31(base, base);
+         e >>= 1;
+      }
+      x[i] = __dadd_rn(__dmul_rn(2.0, __ddiv_rn((double)acc, 2147483647.0)), -1.0);
    }
 }
 
@@ -419,7 +435,8 @@ int hdk_vec_random(double *x_d, int64_t n, int64_t off, int seed)
 {
    HDK_TRY(require_init());
    if (n <= 0) return HDK_OK;
-   k_random<<<vec_grid(n), VT, 0, g.stream>>>(x_d, n, off, (uint64_t)(uint32_t)seed);
+   const uint32_t s0 = seed < 1 ? 1u : (seed >= 2147483647 ? 2147483646u : (uint32_t)seed); // hypre_SeedRand's clamp
+   k_random<<<vec_grid(n), VT, 0, g.stream>>>(x_d, n, off, s0);
    HDK_LAUNCH_CHECK();
    return HDK_OK;
 }

@@ -23,6 +23,8 @@ struct hypredrv_struct
    int       ls_index; /* 0-based index of the installed linear system (-1: none yet) */
    int64_t   row_start, row_end, n;
    double   *b_d, *x0_d, *x_d;
+   double   *x_prev_d;            /* solution of the system that was replaced (init_guess_mode previous) */
+   int64_t   x_prev_rs, x_prev_re;
    double   *x_host, *b_host;
    hdk_amg  *precon;
    bool      precon_created, precon_is_setup, solver_created;
@@ -153,6 +155,16 @@ static bool precon_reusable_for(HYPREDRV_t h, int ls_id)
           !hd_reuse_should_rebuild(&h->args->reuse, ls_id);
 }
 
+/* init_guess_mode 'previous' (reference linsys.c:2044-2063): the solution of the system that is being
+ * replaced survives as the candidate initial guess of the next one */
+static void stash_previous_solution(HYPREDRV_t h)
+{
+   if (!h->x_d || !h->args || h->args->ls.init_guess_mode != 4) return;
+   if (h->x_prev_d) hdk_vec_free(h->x_prev_d);
+   h->x_prev_d = h->x_d; h->x_prev_rs = h->row_start; h->x_prev_re = h->row_end;
+   h->x_d = NULL;
+}
+
 static void free_system(HYPREDRV_t h)
 {
    drop_precon(h);
@@ -170,6 +182,7 @@ uint32_t HYPREDRV_Destroy(HYPREDRV_t *hp)
    if (!hp || !is_live(*hp)) return fail(HYPREDRV_ERROR_UNKNOWN_HYPREDRV_OBJ, NULL, NULL);
    HYPREDRV_t h = *hp;
    free_system(h);
+   if (h->x_prev_d) { hdk_vec_free(h->x_prev_d); h->x_prev_d = NULL; }
    if (h->sol_handle) { h->sol_handle->data = NULL; free(h->sol_handle); }
    if (h->rhs_handle) { h->rhs_handle->data = NULL; free(h->rhs_handle); }
    free(h->args);
@@ -366,6 +379,7 @@ static void build_timer_add(HYPREDRV_t h, double t0)
 static uint32_t install_matrix(HYPREDRV_t h, hdk_csr *A, int64_t rs, int64_t re)
 {
    const int next = h->ls_index + 1;
+   stash_previous_solution(h);
    if (precon_reusable_for(h, next) && h->row_start == rs && h->row_end == re)
    {
       /* keep the hierarchy (and the matrix its level 0 refers to) for the new system */
@@ -528,6 +542,7 @@ uint32_t HYPREDRV_LinearSystemSetInitialGuess(HYPREDRV_t h, HYPRE_Vector vec)
     * init_guess_mode and a zeroed working solution */
    CHECK_OBJ(h);
    if (!h->A) return fail(HYPREDRV_ERROR_INVALID_VAL, "%s", "the matrix must be set before the initial guess");
+   const bool had_x = (h->x_d != NULL); /* a solve of THIS system already produced a solution */
    if (alloc_vec(&h->x0_d, h->n) || alloc_vec(&h->x_d, h->n)) return hd_err_get();
    int rc = HDK_OK;
    struct hypre_IJVector_struct *v = (struct hypre_IJVector_struct *)vec;
@@ -541,7 +556,14 @@ uint32_t HYPREDRV_LinearSystemSetInitialGuess(HYPREDRV_t h, HYPRE_Vector vec)
       int mode = h->args ? h->args->ls.init_guess_mode : 0;
       if (mode == 1) rc = hdk_vec_fill(h->x0_d, 1.0, h->n);
       else if (mode == 3) rc = hdk_vec_random(h->x0_d, h->n, h->row_start, 2023);
-      else if (mode == 4) rc = hdk_vec_copy(h->x0_d, h->x_d, h->n);
+      else if (mode == 4)
+      {
+         /* previous solution: of this system if it was solved before, else of the system it replaced
+          * when the row range is the same; otherwise zeros (reference linsys.c:2044-2063) */
+         if (had_x) rc = hdk_vec_copy(h->x0_d, h->x_d, h->n);
+         else if (h->x_prev_d && h->x_prev_rs == h->row_start && h->x_prev_re == h->row_end) rc = hdk_vec_copy(h->x0_d, h->x_prev_d, h->n);
+         else rc = hdk_vec_fill(h->x0_d, 0.0, h->n); /* no compatible previous solution; using zeros */
+      }
       else if (mode == 2)
       {
          if (!h->args->ls.x0_filename[0]) return fail(HYPREDRV_ERROR_FILE_NOT_FOUND, "%s", "init_guess_mode 'file' but linear_system.x0_filename is empty");
@@ -767,8 +789,12 @@ static uint32_t do_precon_setup(HYPREDRV_t h)
       hd_amg_to_hdk(&h->args->amg, &p);
       if (p.coarsen_type != 8)
       {
-         if (h->rank == 0 && h->args->amg.print_level > 0)
-            fprintf(stderr, "hypredrive_b200: coarsening type %d has no device kernel; using PMIS (8)\n", p.coarsen_type);
+         /* said once per process, whatever the print level: the CPU-default chain (HMIS) is inherently
+          * sequential; results then follow the reference's GPU-build defaults, not its CPU goldens */
+         static int warned = 0;
+         if (h->rank == 0 && !warned++)
+            fprintf(stderr, "hypredrive_b200: warning: coarsening type %d has no device kernel; using PMIS (8), "
+                            "the reference's HYPRE_USING_GPU default\n", p.coarsen_type);
          p.coarsen_type = 8;
       }
       int rc = hdk_amg_setup(h->A, &p, &h->precon);

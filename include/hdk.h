@@ -69,8 +69,9 @@ int hdk_vec_scale(double alpha, double *x_d, int64_t n);
  * (reference: hypre_ParVectorInnerProd, src/internal/linsys.c:2815-2924) */
 int hdk_vec_dot(const double *x_d, const double *y_d, int64_t n, double *result_h);
 int hdk_vec_norm(const double *x_d, int64_t n, int kind, double *result_h);
-/* uniform pseudo-random fill in [-1,1) from a counter hash of (seed, global index)
- * (reference: HYPRE_ParVectorSetRandomValues, src/internal/linsys.c:1810-1838, 2050-2060) */
+/* HYPRE_ParVectorSetRandomValues-compatible fill: x_i = 2 hypre_Rand() - 1 from the Park-Miller
+ * stream seeded with `seed`, element i taken at position global_offset + i (identical to hypre on
+ * one rank; partition-invariant on several) (reference: src/internal/linsys.c:1810-1838, 2050-2060) */
 int hdk_vec_random(double *x_d, int64_t n, int64_t global_offset, int seed);
 
 /* ---- matrix (reference: HYPRE_IJMatrixCreate/SetValues/Assemble,

@@ -21,6 +21,15 @@ int oracle_set_threads(int n)
 #endif
 }
 
+/* HYPRE_ParVectorSetRandomValues on one rank (hypre seq_mv/vector.c: hypre_SeqVectorSetRandomValues):
+ * hypre_SeedRand(seed); x[i] = 2 hypre_Rand() - 1.  Used by rhs_mode random / randsol and
+ * init_guess_mode random with seed 2023 (reference src/internal/linsys.c:1810-1838, 2034-2040). */
+void ovec_set_random(int seed, int n, double *x)
+{
+   oracle_rand_stream(seed, n, x);
+   for (int i = 0; i < n; i++) x[i] = 2.0 * x[i] - 1.0;
+}
+
 ocsr *ocsr_alloc(int nrows, int ncols, int64_t nnz, int with_values)
 {
    ocsr *A  = (ocsr *)calloc(1, sizeof(ocsr));

@@ -93,6 +93,7 @@ void  ocsr_matvec(double alpha, const ocsr *A, const double *x, double beta, dou
 void  ocsr_residual(const ocsr *A, const double *x, const double *b, double *r);
 double ovec_dot(int n, const double *x, const double *y);
 void  oracle_rand_stream(int seed, int n, double *out);
+void  ovec_set_random(int seed, int n, double *x); /* HYPRE_ParVectorSetRandomValues, one rank */
 /* OpenMP team size used by every parallel loop of the oracle (bench.py reports it as "cores") */
 int   oracle_set_threads(int n); /* n <= 0: leave unchanged; returns the team size in effect */
 

@@ -81,6 +81,7 @@ def lib():
         L.ovec_dot.restype = C.c_double
         L.ovec_dot.argtypes = [C.c_int, PD, PD]
         L.oracle_rand_stream.argtypes = [C.c_int, C.c_int, PD]
+        L.ovec_set_random.argtypes = [C.c_int, C.c_int, PD]
         L.oracle_set_threads.restype = C.c_int
         L.oracle_set_threads.argtypes = [C.c_int]
         L.oamg_default_params.argtypes = [C.POINTER(Params), C.c_int]
@@ -183,6 +184,13 @@ def gen(kind: str, nx: int, ny: int, nz: int, c=(1.0, 1.0, 1.0), diag_first: boo
 def set_threads(n: int = 0) -> int:
     """Set (n > 0) and return the OpenMP team size of the oracle's parallel loops."""
     return int(lib().oracle_set_threads(int(n)))
+
+
+def set_random(seed: int, n: int) -> np.ndarray:
+    """HYPRE_ParVectorSetRandomValues(v, seed) on one rank."""
+    out = np.zeros(n)
+    lib().ovec_set_random(seed, n, _pd(out))
+    return out
 
 
 def rand_stream(seed: int, n: int) -> np.ndarray:

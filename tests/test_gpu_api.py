@@ -235,3 +235,35 @@ def test_api_fgmres_bicgstab(gpu, solver):
     A, b = O.gen("convdif", 20, 8, 8, c=(1e-3, 1.0, 0.1))
     res = hd.solve(A, b, options={"solver": {solver: {"relative_tol": 1.0e-8, "max_iter": 60}}, "preconditioner": "amg"})
     assert res.converged and np.linalg.norm(b - A @ res.x) <= 1e-8 * np.linalg.norm(b) * 1.0001
+
+
+def test_initial_guess_previous_across_two_systems(gpu):
+    """init_guess_mode 'previous' (reference src/internal/linsys.c:2044-2063): the second system
+    starts from the first system's solution -- a slightly perturbed operator then needs fewer
+    iterations than from zeros -- and falls back to zeros when no compatible vector exists."""
+    A, b = O.gen("lap7", 12, 10, 8)
+    A2 = (A + 1e-3 * sp.eye(A.shape[0])).tocsr()
+
+    def run(mode):
+        opts = {"general": {"statistics": False}, "linear_system": {"init_guess_mode": mode},
+                "solver": {"pcg": {"relative_tol": 1e-8, "max_iter": 100}}, "preconditioner": "amg"}
+        its = []
+        with hd.HypreDrive(options=opts) as drv:
+            for M in (A, A2):
+                drv.set_matrix_from_csr(M)
+                drv.set_rhs(b)
+                drv.solve()
+                assert drv.last_converged
+                x = drv.get_solution()
+                assert np.linalg.norm(b - M @ x) <= 1e-8 * np.linalg.norm(b) * 1.0001
+                its.append(drv.last_iterations)
+        return its
+
+    zeros, prev = run("zeros"), run("previous")
+    assert prev[0] == zeros[0]                     # first system: no previous solution -> zeros
+    assert prev[1] < zeros[1]                      # second system: warm start from the first solution
+    # other generated initial guesses still converge to the same solution
+    for mode in ("ones", "random"):
+        res = hd.solve(A, b, options={"general": {"statistics": False}, "linear_system": {"init_guess_mode": mode},
+                                      "solver": {"pcg": {"relative_tol": 1e-9, "max_iter": 100}}, "preconditioner": "amg"})
+        assert res.converged and np.linalg.norm(b - A @ res.x) <= 1e-9 * np.linalg.norm(b) * 1.0001
