@@ -38,7 +38,11 @@ struct hdk_amg_s
    double                     op_complexity = 0.0;
    double                     vcycle_bytes = 0.0;
    bool                       keep_debug = false; // keep S / measure for introspection (tunable amg_keep_debug)
-   bool                       prefilled_l0 = false; // next zero-guess cycle: level-0 first sweep already done by the caller
+   int                        prefilled_at = -1; // next zero-guess cycle from this level: its first sweep is already in place
+   // sub-cycles over the small levels captured into CUDA graphs (hdk_amg_solve.cu)
+   struct CycleGraph { const double *f; double *u; bool zero_guess, prefilled; int level; void *exec; int nodes; };
+   std::vector<CycleGraph>    graphs;
+   bool                       graph_off = false;
    bool                       keep_f2c = false;
    // N > 1: levels [0, nlev) are row-distributed; from level `tail_level` on, the hierarchy is
    // replicated on every rank (`tail`, a serial hierarchy of the GLOBAL problem) and the

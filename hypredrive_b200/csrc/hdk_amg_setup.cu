@@ -1703,6 +1703,8 @@ int hdk_amg_destroy(hdk_amg *M)
       }
       dfree(M->ge_inv); dfree(M->full_f); dfree(M->full_u);
       ipc_gather_free(M->gather);
+      for (auto &G : M->graphs) if (G.exec) cudaGraphExecDestroy((cudaGraphExec_t)G.exec);
+      M->graphs.clear();
    }
    if (M->tail) hdk_amg_destroy(M->tail);
    delete M;

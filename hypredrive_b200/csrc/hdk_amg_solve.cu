@@ -121,10 +121,110 @@ static int coarse_solve(hdk_amg_s *M, int l, const double *f, double *u, double 
    return HDK_OK;
 }
 
+// buffer in which a cycle over levels [l0, nlev) entered with vectors (f, u0) keeps its iterate at
+// the start: chosen so that the result lands in u0 without a copy (default sweeps)
+static double *cycle_start_buffer(hdk_amg_s *M, int l0, double *u0, bool zero_guess)
+{
+   const hdk_amg_params &p = M->prm;
+   const int nfine = M->tail ? M->nlev : M->nlev - 1;
+   int       oop;
+   if (nfine <= l0) oop = 0;
+   else
+   {
+      int down_oop = zero_guess && is_jacobi(p.relax_down) ? (p.sweeps_down > 0 ? p.sweeps_down - 1 : 0) : p.sweeps_down;
+      oop          = down_oop + p.sweeps_up;
+   }
+   const bool start_in_u0 = zero_guess ? (oop % 2 == 0) : true;
+   return start_in_u0 ? u0 : M->lev[(size_t)l0].t;
+}
+
+// ---- CUDA graphs for the latency-bound part of the cycle ------------------------------------------
+// The levels with few rows are a chain of ~20 small dependent kernels (6-40 us each, launch-latency
+// bound).  All their operands are hierarchy-owned buffers, so the sub-cycle from the first small level
+// down to the coarsest solve and back is captured ONCE into a CUDA graph (same kernels, same order:
+// results are bit-identical) and replayed with one launch per V-cycle.  Tunable graph_rows
+// (HDK_GRAPH_ROWS): levels with at most that many rows are replayed from a graph, 0 disables.
+static int amg_cycle_impl(hdk_amg_s *M, const double *f0, double *u0, bool zero_guess, int fin, double *fin_out, int l0, int kg);
+
+static int first_graph_level(hdk_amg_s *M, int l0)
+{
+   if (M->tail || M->graph_off) return -1;               // distributed levels take changing kernel arguments
+   const int64_t rows = tune_graph_rows();
+   if (rows <= 0) return -1;
+   const hdk_amg_params &p = M->prm;
+   if (!is_jacobi(p.relax_down) || !is_jacobi(p.relax_up)) return -1; // (two-stage GS may allocate scratch)
+   for (int l = l0; l < M->nlev; l++)
+      if (M->lev[(size_t)l].n <= rows) return l;
+   return -1;
+}
+
+// run the cycle over [kg, nlev) with vectors (f, u) from a graph captured on first use
+static int cycle_graph_run(hdk_amg_s *M, const double *f, double *u, bool zero_guess, bool prefilled, int kg)
+{
+   for (auto &G : M->graphs)
+      if (G.f == f && G.u == u && G.zero_guess == zero_guess && G.prefilled == prefilled && G.level == kg)
+      {
+         HDK_CUDA(cudaGraphLaunch((cudaGraphExec_t)G.exec, g.stream));
+         g.launches += G.nodes;
+         return HDK_OK;
+      }
+   // capture (the launches below are recorded, not executed)
+   const int64_t before = g.launches;
+   cudaGraph_t   graph = nullptr;
+   if (cudaStreamBeginCapture(g.stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess)
+   {
+      cudaGetLastError();
+      M->graph_off = true;
+      M->prefilled_at = prefilled ? kg : -1;
+      return amg_cycle_impl(M, f, u, zero_guess, FIN_NONE, nullptr, kg, -1);
+   }
+   M->prefilled_at = prefilled ? kg : -1;
+   int         rc = amg_cycle_impl(M, f, u, zero_guess, FIN_NONE, nullptr, kg, -1);
+   cudaError_t e = cudaStreamEndCapture(g.stream, &graph);
+   cudaGraphExec_t exec = nullptr;
+   if (rc == HDK_OK && e == cudaSuccess && graph) e = cudaGraphInstantiate(&exec, graph, 0);
+   if (graph) cudaGraphDestroy(graph);
+   if (rc != HDK_OK || e != cudaSuccess || !exec)
+   {
+      // not capturable here: run directly from now on
+      cudaGetLastError();
+      M->graph_off = true;
+      if (rc != HDK_OK) return rc;
+      M->prefilled_at = prefilled ? kg : -1;
+      return amg_cycle_impl(M, f, u, zero_guess, FIN_NONE, nullptr, kg, -1);
+   }
+   hdk_amg_s::CycleGraph G;
+   G.f = f; G.u = u; G.zero_guess = zero_guess; G.prefilled = prefilled; G.level = kg; G.exec = exec;
+   G.nodes = (int)(g.launches - before);
+   g.launches = before;
+   M->graphs.push_back(G);
+   HDK_CUDA(cudaGraphLaunch(exec, g.stream));
+   g.launches += G.nodes;
+   return HDK_OK;
+}
+
 // One V-cycle over levels [l0, nlev) of M.  Level-l0 vectors are the caller's (f, u); u is also
 // used as scratch.  With a replicated tail (N > 1) every level of M is a "fine" level and the
 // coarsest stage is: sum the restricted right-hand side over ranks, run the serial tail cycle.
 int amg_cycle(hdk_amg_s *M, const double *f0, double *u0, bool zero_guess, int fin, double *fin_out, int l0)
+{
+   int kg = first_graph_level(M, l0);
+   if (kg == l0)
+   {
+      // the whole cycle is small: one graph, unless a fused dot has to come out of its last kernel
+      if (fin == FIN_NONE)
+      {
+         const bool pf = (M->prefilled_at == l0) && zero_guess;
+         M->prefilled_at = -1;
+         return cycle_graph_run(M, f0, u0, zero_guess, pf, l0);
+      }
+      kg = (l0 + 1 < M->nlev) ? l0 + 1 : -1;
+   }
+   return amg_cycle_impl(M, f0, u0, zero_guess, fin, fin_out, l0, kg);
+}
+
+// kg > l0: the levels [kg, nlev) run as a sub-cycle replayed from a CUDA graph; kg < 0: all levels here
+static int amg_cycle_impl(hdk_amg_s *M, const double *f0, double *u0, bool zero_guess, int fin, double *fin_out, int l0, int kg)
 {
    const int             nl = M->nlev;
    const bool            has_tail = (M->tail != nullptr);
@@ -153,16 +253,8 @@ int amg_cycle(hdk_amg_s *M, const double *f0, double *u0, bool zero_guess, int f
    // level-l0 buffer parity so that the result lands in u0 without a copy (default sweeps)
    {
       AmgLevel &L0 = M->lev[(size_t)l0];
-      int       oop;
-      if (nfine <= l0) oop = 0;
-      else
-      {
-         int down_oop = zero_guess && is_jacobi(p.relax_down) ? (p.sweeps_down > 0 ? p.sweeps_down - 1 : 0) : p.sweeps_down;
-         oop          = down_oop + p.sweeps_up;
-      }
-      bool start_in_u0 = zero_guess ? (oop % 2 == 0) : true;
-      cur[(size_t)l0] = start_in_u0 ? u0 : L0.t;
-      alt[(size_t)l0] = start_in_u0 ? L0.t : u0;
+      cur[(size_t)l0] = cycle_start_buffer(M, l0, u0, zero_guess);
+      alt[(size_t)l0] = (cur[(size_t)l0] == u0) ? L0.t : u0;
       rhs[(size_t)l0] = f0;
    }
    for (int l = l0 + 1; l < nl; l++) { cur[(size_t)l] = M->lev[(size_t)l].u; alt[(size_t)l] = M->lev[(size_t)l].t; rhs[(size_t)l] = M->lev[(size_t)l].f; }
@@ -170,9 +262,12 @@ int amg_cycle(hdk_amg_s *M, const double *f0, double *u0, bool zero_guess, int f
    // the first pre-smoothing sweep of a level entered with a zero guess is u = (w f)/d: it is
    // produced by the kernel that produces f (the restriction of the level above, or the PCG
    // residual update for level l0), so it costs no pass of its own
-   bool prefilled = (M->prefilled_l0 && zero_guess && l0 == 0);
-   M->prefilled_l0 = false;
-   for (int l = l0; l < nfine; l++)
+   bool prefilled = (M->prefilled_at == l0) && zero_guess;
+   M->prefilled_at = -1;
+   const bool sub = (kg > l0 && kg < nl);              // levels [kg, nl) replayed from a graph
+   const int  ndown = sub ? kg : nfine;                // levels [l0, ndown) smooth + restrict here
+   if (sub) cur[(size_t)kg] = cycle_start_buffer(M, kg, M->lev[(size_t)kg].u, true); // where the sub-cycle expects its first sweep
+   for (int l = l0; l < ndown; l++)
    {
       AmgLevel &L = M->lev[(size_t)l];
       bool      zg = (l > l0) || zero_guess;
@@ -226,7 +321,13 @@ int amg_cycle(hdk_amg_s *M, const double *f0, double *u0, bool zero_guess, int f
    }
    // coarsest stage
    const double *coarse_sol = nullptr; // solution feeding the prolongation of level nfine-1
-   if (has_tail)
+   if (sub)
+   {
+      AmgLevel &Lk = M->lev[(size_t)kg];
+      HDK_TRY(cycle_graph_run(M, Lk.f, Lk.u, true, prefilled, kg));
+      cur[(size_t)kg] = Lk.u;                          // the sub-cycle leaves its result in u
+   }
+   else if (has_tail)
    {
       // the ranks own disjoint slices of the coarse right-hand side: with the peer-memory arena each
       // rank stores its slice into every peer's copy (one kernel + a flag wait), else NCCL sums the
@@ -250,7 +351,7 @@ int amg_cycle(hdk_amg_s *M, const double *f0, double *u0, bool zero_guess, int f
       if (res != cur[(size_t)Lc]) std::swap(cur[(size_t)Lc], alt[(size_t)Lc]);
       coarse_sol = cur[(size_t)Lc];
    }
-   for (int l = nfine - 1; l >= l0; l--)
+   for (int l = ndown - 1; l >= l0; l--)
    {
       AmgLevel &L = M->lev[(size_t)l];
       // u += P e_c

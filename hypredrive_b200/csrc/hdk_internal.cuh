@@ -115,6 +115,7 @@ int  csr_analyze(DevCSR &A);
 int  tune_set(const char *key, double value);
 bool tune_amg_keep_debug();
 int64_t tune_replicate_rows();
+int64_t tune_graph_rows();
 
 // epilogue selectors of the fused SpMV family (see hdk_spmv.cu)
 enum SpmvMode

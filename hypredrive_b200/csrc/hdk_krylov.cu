@@ -132,7 +132,7 @@ int hdk_pcg(const hdk_csr *A, hdk_amg *M, const double *b, double *x, hdk_krylov
          double        zw = 1.0;
          const bool    pf = M && amg_prefill_target(M, s, &zb, &zd, &zw);
          if ((rc = pcg_update_xr(x, r, p, s, n, S, local_fin(FIN_IPROD), local_out(nullptr), pf ? zb : nullptr, zd, zw))) goto done;
-         if (pf) M->prefilled_l0 = true;
+         if (pf) M->prefilled_at = 0;
       }
       if ((rc = finish_dot(FIN_IPROD, nullptr))) goto done;
       if ((rc = read_scalars(8))) goto done;

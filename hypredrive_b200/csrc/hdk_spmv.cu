@@ -41,6 +41,7 @@ struct Tune
    double sell_sort     = 1;        // HDK_SELL_SORT        sort the columns of coarse operators in the slices
    double amg_keep_debug = 0;       // HDK_AMG_KEEP_DEBUG   keep S and the PMIS measures of every level (introspection)
    double replicate_rows = 262144;  // HDK_REPLICATE_ROWS   N > 1: levels with at most this many global rows form the replicated tail
+   double graph_rows    = 150000;   // HDK_GRAPH_ROWS       V-cycle levels with at most this many rows are replayed from a CUDA graph (0: off)
    bool   env_read      = false;
 };
 static Tune tune;
@@ -50,6 +51,7 @@ static const struct { const char *key, *env; double Tune::*field; } tune_keys[] 
    {"sell_min_rows_dist", "HDK_SELL_MIN_ROWS_DIST", &Tune::sell_min_rows_dist},
    {"amg_keep_debug", "HDK_AMG_KEEP_DEBUG", &Tune::amg_keep_debug},
    {"replicate_rows", "HDK_REPLICATE_ROWS", &Tune::replicate_rows},
+   {"graph_rows", "HDK_GRAPH_ROWS", &Tune::graph_rows},
    {"sell_min_avg", "HDK_SELL_MIN_AVG", &Tune::sell_min_avg},  {"sell_sort", "HDK_SELL_SORT", &Tune::sell_sort}};
 static Tune &tunables()
 {
@@ -66,6 +68,7 @@ static Tune &tunables()
 }
 bool tune_amg_keep_debug() { return tunables().amg_keep_debug != 0.0; }
 int64_t tune_replicate_rows() { return (int64_t)tunables().replicate_rows; }
+int64_t tune_graph_rows() { return (int64_t)tunables().graph_rows; }
 
 int tune_set(const char *key, double value)
 {

@@ -339,3 +339,18 @@ def test_other_krylov_callers_match_oracle(gpu, solver):
     assert info["converged"] and abs(info["iters"] - ir["iters"]) <= 1
     assert np.linalg.norm(dx.get() - xr) <= 1e-8 * np.linalg.norm(xr)
     assert np.linalg.norm(b - A @ dx.get()) <= 1e-9 * np.linalg.norm(b) * 1.0001
+
+
+def test_random_vector_matches_hypre_stream(gpu):
+    """rhs_mode random / init_guess_mode random: HYPRE_ParVectorSetRandomValues(v, 2023) on one rank
+    (Park-Miller stream, x = 2 r - 1), reached by skip-ahead on the device; a slab is a slice of
+    the global stream."""
+    n = 100003
+    dv = gpu.DVec(n)
+    gpu.check(gpu.lib().hdk_vec_random(dv.p, n, 0, 2023))
+    ref = O.set_random(2023, n)
+    assert np.array_equal(dv.get(), ref)
+    assert -1.0 <= ref.min() and ref.max() < 1.0
+    ds = gpu.DVec(1000)
+    gpu.check(gpu.lib().hdk_vec_random(ds.p, 1000, 5000, 2023))
+    assert np.array_equal(ds.get(), ref[5000:6000])
