@@ -85,5 +85,5 @@ int amg_cycle(hdk_amg_s *M, const double *f, double *u, bool zero_guess, int fin
 int exclusive_scan_int(const int *in, int *out, int n);       // hdk_csr.cu (hand-written reduce-then-scan)
 int exclusive_scan_i64(const int *in, int64_t *out, int n);
 int exclusive_scan_i64_i64(const int64_t *in, int64_t *out, int64_t n);
-bool amg_prefill_target(hdk_amg_s *M, double *z, double **buf, const double **d, double *w);
+bool amg_prefill_target(hdk_amg_s *M, double *z, double **buf, const double **d, double *w, const hdk_csr_s **reader = nullptr);
 } // namespace hdk

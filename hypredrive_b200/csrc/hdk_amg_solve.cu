@@ -24,8 +24,9 @@ __global__ void __launch_bounds__(256) k_dense_apply(const double *__restrict__ 
 static bool is_jacobi(int t) { return t == 18 || t == 7 || t == 0; }
 
 // one smoothing sweep u_new = S(u_old); result written to `out` (out != in)
+// export_to: the matrix whose product reads `out` next (its halo is filled by this sweep's kernel)
 static int relax_sweep(hdk_amg_s *M, int l, int type, const double *l1, const double *f, const double *in,
-                       double *out, int fin, double *fin_out)
+                       double *out, int fin, double *fin_out, const hdk_csr_s *export_to = nullptr)
 {
    AmgLevel &L = M->lev[(size_t)l];
    SpmvArgs  a;
@@ -33,6 +34,7 @@ static int relax_sweep(hdk_amg_s *M, int l, int type, const double *l1, const do
    if (is_jacobi(type))
    {
       if (fin != FIN_NONE) { a.dotv = f; a.fin = fin; a.fin_out = fin_out; }
+      a.export_to = export_to;
       return parcsr_matvec(*L.A, SPMV_JACOBI, a);
    }
    if (type == 11 || type == 12)
@@ -275,12 +277,13 @@ static int amg_cycle_impl(hdk_amg_s *M, const double *f0, double *u0, bool zero_
       {
          if (s == 0 && zg && is_jacobi(p.relax_down))
          {
-            if (!prefilled) HDK_TRY(vec_scaled_div(cur[(size_t)l], rhs[(size_t)l], L.l1_down, p.relax_weight, L.n));
+            // (the next product on this level -- another sweep or the residual -- reads this vector)
+            if (!prefilled) HDK_TRY(vec_scaled_div(cur[(size_t)l], rhs[(size_t)l], L.l1_down, p.relax_weight, L.n, L.A));
          }
          else
          {
             if (s == 0 && zg) HDK_TRY(vec_fill(cur[(size_t)l], 0.0, L.n));
-            HDK_TRY(relax_sweep(M, l, p.relax_down, L.l1_down, rhs[(size_t)l], cur[(size_t)l], alt[(size_t)l], FIN_NONE, nullptr));
+            HDK_TRY(relax_sweep(M, l, p.relax_down, L.l1_down, rhs[(size_t)l], cur[(size_t)l], alt[(size_t)l], FIN_NONE, nullptr, L.A));
             std::swap(cur[(size_t)l], alt[(size_t)l]);
          }
       }
@@ -294,6 +297,7 @@ static int amg_cycle_impl(hdk_amg_s *M, const double *f0, double *u0, bool zero_
       {
          SpmvArgs a;
          a.x = cur[(size_t)l]; a.y = alt[(size_t)l]; a.b = rhs[(size_t)l];
+         a.export_to = L.R;                                    // the restriction reads the residual next
          HDK_TRY(parcsr_matvec(*L.A, SPMV_RESIDUAL, a));
       }
       SpmvArgs rr;
@@ -314,6 +318,7 @@ static int amg_cycle_impl(hdk_amg_s *M, const double *f0, double *u0, bool zero_
       {
          // f_{l+1} = R r  and  u_{l+1} = (w f_{l+1})/d_{l+1}  in one kernel
          rr.y2 = cur[(size_t)l + 1]; rr.d = M->lev[(size_t)l + 1].l1_down; rr.w = p.relax_weight;
+         if (!(sub && l + 1 == kg)) { rr.export_to = M->lev[(size_t)l + 1].A; rr.export_y2 = true; } // its first product reads the sweep
          HDK_TRY(parcsr_matvec(*L.R, SPMV_SET_DIV, rr));
          prefilled = true;
       }
@@ -358,12 +363,16 @@ static int amg_cycle_impl(hdk_amg_s *M, const double *f0, double *u0, bool zero_
       SpmvArgs a;
       a.x = (l + 1 < nl) ? cur[(size_t)l + 1] : coarse_sol;
       a.y = cur[(size_t)l];
+      if (p.sweeps_up > 0) a.export_to = L.A;                  // the post-smoothing sweep reads the corrected iterate
+      else if (l > l0) a.export_to = M->lev[(size_t)l - 1].P;
       HDK_TRY(parcsr_matvec(*L.P, SPMV_ADD, a));
       for (int s = 0; s < p.sweeps_up; s++)
       {
          bool last = (l == l0 && s == p.sweeps_up - 1);
          int  f_   = (last && fin != FIN_NONE) ? fin : FIN_NONE;
-         HDK_TRY(relax_sweep(M, l, p.relax_up, L.l1_up, rhs[(size_t)l], cur[(size_t)l], alt[(size_t)l], f_, fin_out));
+         // reader of this sweep's result: the next sweep, or the prolongation of the level above
+         const hdk_csr_s *next = (s + 1 < p.sweeps_up) ? L.A : (l > l0 ? M->lev[(size_t)l - 1].P : nullptr);
+         HDK_TRY(relax_sweep(M, l, p.relax_up, L.l1_up, rhs[(size_t)l], cur[(size_t)l], alt[(size_t)l], f_, fin_out, next));
          std::swap(cur[(size_t)l], alt[(size_t)l]);
          if (f_ != FIN_NONE) fin_done = true;
       }
@@ -375,8 +384,9 @@ static int amg_cycle_impl(hdk_amg_s *M, const double *f0, double *u0, bool zero_
 
 // For a caller that can produce u0 = (w r)/d itself (PCG's fused x/r update): the buffer the
 // V-cycle expects it in, the diagonal and the weight.  false: the cycle does not start that way.
-bool amg_prefill_target(hdk_amg_s *M, double *z, double **buf, const double **d, double *w)
+bool amg_prefill_target(hdk_amg_s *M, double *z, double **buf, const double **d, double *w, const hdk_csr_s **reader)
 {
+   if (reader) *reader = (M->nlev > 0) ? M->lev[0].A : nullptr; // the matrix whose product reads the first sweep
    const hdk_amg_params &p = M->prm;
    const bool has_tail = (M->tail != nullptr);
    const int  nl = M->nlev, nfine = has_tail ? nl : nl - 1;

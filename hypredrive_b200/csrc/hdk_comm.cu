@@ -570,8 +570,8 @@ static int ipc_plan_build(HaloPlan &H, const std::vector<int> &all /* all[r*R+q]
       char *rb = ipc.peer[(size_t)S] + offs[(size_t)S];
       I.src_ack[i] = reinterpret_cast<unsigned long long *>(rb) + 8 + sidx;
    }
-   HDK_TRY(dalloc(&I.tickets, 2));
-   HDK_CUDA(cudaMemsetAsync(I.tickets, 0, 2 * sizeof(unsigned), g.stream));
+   HDK_TRY(dalloc(&I.tickets, 3));
+   HDK_CUDA(cudaMemsetAsync(I.tickets, 0, 3 * sizeof(unsigned), g.stream));
    I.seq = 0;
    I.on  = true;
    return HDK_OK;
@@ -583,7 +583,7 @@ void halo_plan_free(HaloPlan &H)
    H.col_map = nullptr; H.send_idx = nullptr; H.send_buf = nullptr; H.x_halo = nullptr;
    if (H.ipc.on)
    {
-      dfree(H.ipc.tickets);
+      dfree(H.ipc.tickets); dfree(H.ipc.exp_rows); dfree(H.ipc.exp_ptr); dfree(H.ipc.exp_slot);
       if (ipc.on) ipc.pending.emplace_back((size_t)H.ipc.region_off, H.ipc.region_bytes);
       H.ipc = IpcHalo();
    }
@@ -605,6 +605,84 @@ IpcRecvArgs halo_recv_args(const hdk_csr_s &A, const double **xh)
    r.tmo = ipc.tmo; r.err = ipc.err_d;
    for (size_t i = 0; i < H.recv_rank.size(); i++) r.ack[i] = I.src_ack[i];
    return r;
+}
+
+// inverse of the send list (row -> its positions in the concatenated send buffer) for exports folded
+// into the kernel that produces the vector; built once per plan on the host
+static int ipc_export_build(HaloPlan &H)
+{
+   IpcHalo &I = H.ipc;
+   if (!I.on || H.n_send <= 0) return HDK_OK;
+   std::vector<int> idx((size_t)H.n_send);
+   HDK_CUDA(cudaMemcpyAsync(idx.data(), H.send_idx, sizeof(int) * (size_t)H.n_send, cudaMemcpyDeviceToHost, g.stream));
+   HDK_CUDA(cudaStreamSynchronize(g.stream));
+   std::vector<std::pair<int, int>> rs((size_t)H.n_send); // (row, slot)
+   for (int s = 0; s < H.n_send; s++) rs[(size_t)s] = std::make_pair(idx[(size_t)s], s);
+   std::sort(rs.begin(), rs.end());
+   std::vector<int> rows, ptr, slot((size_t)H.n_send);
+   for (int k = 0; k < H.n_send; k++)
+   {
+      if (k == 0 || rs[(size_t)k].first != rs[(size_t)k - 1].first) { rows.push_back(rs[(size_t)k].first); ptr.push_back(k); }
+      slot[(size_t)k] = rs[(size_t)k].second;
+   }
+   ptr.push_back(H.n_send);
+   const int m = (int)rows.size();
+   // widest run of rows without exports (for slabs: everything between the two boundary planes)
+   int lo_end = 0, hi_begin = 0, best = -1;
+   for (int k = 0; k + 1 < m; k++)
+   {
+      const int gap = rows[(size_t)k + 1] - rows[(size_t)k] - 1;
+      if (gap > best) { best = gap; lo_end = rows[(size_t)k] + 1; hi_begin = rows[(size_t)k + 1]; }
+   }
+   if (rows[0] > best) { best = rows[0]; lo_end = 0; hi_begin = rows[0]; }
+   if (best <= 0) { lo_end = hi_begin = 0; }
+   HDK_TRY(dalloc(&I.exp_rows, (size_t)m + 1));
+   HDK_TRY(dalloc(&I.exp_ptr, (size_t)m + 2));
+   HDK_TRY(dalloc(&I.exp_slot, (size_t)H.n_send + 1));
+   HDK_CUDA(cudaMemcpyAsync(I.exp_rows, rows.data(), sizeof(int) * (size_t)m, cudaMemcpyHostToDevice, g.stream));
+   HDK_CUDA(cudaMemcpyAsync(I.exp_ptr, ptr.data(), sizeof(int) * ((size_t)m + 1), cudaMemcpyHostToDevice, g.stream));
+   HDK_CUDA(cudaMemcpyAsync(I.exp_slot, slot.data(), sizeof(int) * (size_t)H.n_send, cudaMemcpyHostToDevice, g.stream));
+   HDK_CUDA(cudaStreamSynchronize(g.stream)); // the host vectors go out of scope
+   I.exp_m = m; I.exp_lo_end = lo_end; I.exp_hi_begin = hi_begin;
+   return HDK_OK;
+}
+
+static bool export_enabled()
+{
+   static int on = -1;
+   if (on < 0) { const char *e = getenv("HDK_HALO_EXPORT"); on = (e && atoi(e) == 0) ? 0 : 1; }
+   return on == 1;
+}
+
+bool halo_export_begin(const hdk_csr_s &A, HaloExport *e)
+{
+   *e = HaloExport();
+   const HaloPlan &H = A.halo;
+   if (g.nranks <= 1 || !H.ipc.on || !export_enabled() || H.ipc.preposted) return false;
+   if (!(H.n_send > 0 || H.n_halo > 0)) return false;    // this rank takes no part in the exchange
+   IpcHalo &I = const_cast<IpcHalo &>(H.ipc);
+   I.seq++;
+   I.preposted = true;
+   if (H.n_send <= 0) return true;                         // receives only: nothing to store, the sequence still advances
+   e->rows = I.exp_rows; e->ptr = I.exp_ptr; e->slot = I.exp_slot; e->m = I.exp_m;
+   e->lo_end = I.exp_lo_end; e->hi_begin = I.exp_hi_begin;
+   e->npeer = (int)H.send_rank.size();
+   for (int p = 0; p < e->npeer; p++)
+   {
+      e->dst[p]  = I.dst[I.seq & 1][p];
+      e->flag[p] = I.dst_flag[p];
+      e->off[p]  = H.send_off[(size_t)p];
+   }
+   e->off[e->npeer] = H.n_send;
+   e->ack = I.ack_flag; e->seq = I.seq; e->ticket = I.tickets + 2; e->tmo = ipc.tmo; e->err = ipc.err_d;
+   return true;
+}
+
+void halo_export_cancel(const hdk_csr_s &A)
+{
+   // the data already sits in the neighbours' buffers under its sequence number; the next exchange
+   // simply uses the following one
+   const_cast<IpcHalo &>(A.halo.ipc).preposted = false;
 }
 
 __global__ void k_ids_to_local(const int64_t *ids, int n, int64_t row_start, int *idx)
@@ -670,7 +748,7 @@ int build_halo_plan(hdk_csr_s &A, int64_t *uniq, int n_halo)
       HDK_LAUNCH_CHECK();
    }
    dfree(req);
-   return HDK_OK;
+   return ipc_export_build(H);
 }
 
 __global__ void k_pack(const double *x, const int *idx, int n, double *buf)
@@ -688,6 +766,7 @@ int halo_exchange_begin(const hdk_csr_s &A, const double *x)
    {
       // peer-memory path: one kernel packs, stores over NVLink and signals; the consumer waits
       IpcHalo &I = const_cast<IpcHalo &>(H.ipc);
+      if (I.preposted) { I.preposted = false; return HDK_OK; } // filled by the kernel that produced x (halo_export_begin)
       I.seq++;
       if (H.n_send > 0)
       {

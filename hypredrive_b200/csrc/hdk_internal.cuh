@@ -148,6 +148,9 @@ enum ScalIdx
    S_TMP0 = 8, S_TMP1 = 9, S_TMP2 = 10, S_TMP3 = 11, S_H0 = 16 /* 16..63: GMRES h column */
 };
 
+} // namespace hdk
+struct hdk_csr_s;
+namespace hdk {
 struct SpmvArgs
 {
    const double *x = nullptr;   // input vector (gathered)
@@ -161,6 +164,10 @@ struct SpmvArgs
    const double *dotv = nullptr;
    int           fin = FIN_NONE;
    double       *fin_out = nullptr;
+   // the matrix whose next product reads this kernel's output (y, or y2 with export_y2): its halo is
+   // filled by this kernel (see HaloExport) when the peer-memory path is on
+   const struct ::hdk_csr_s *export_to = nullptr;
+   bool          export_y2 = false;
 };
 
 
@@ -171,11 +178,13 @@ int vec_axpy(double a, const double *x, double *y, int64_t n);
 int vec_scale(double a, double *x, int64_t n);
 int vec_dot_dev(const double *x, const double *y, int64_t n, int fin, double *out_d); // device result
 int vec_dot_host(const double *x, const double *y, int64_t n, double *out_h);         // + allreduce
-int vec_scaled_div(double *u, const double *f, const double *d, double w, int64_t n); // u = w f / d
+int vec_scaled_div(double *u, const double *f, const double *d, double w, int64_t n,    // u = w f / d
+                   const struct ::hdk_csr_s *export_to = nullptr);                          // (+ halo of export_to's next product)
 int pcg_update_xr(double *x, double *r, const double *p, const double *s, int64_t n, double *scal,
                   int fin = FIN_IPROD, double *fin_out = nullptr, // <r,r> -> fin (FIN_STORE at N > 1)
-                  double *z0 = nullptr, const double *zd = nullptr, double zw = 1.0); // optional z0 = (zw r)/zd
-int pcg_update_p(double *p, const double *z, int64_t n, const double *scal);
+                  double *z0 = nullptr, const double *zd = nullptr, double zw = 1.0, // optional z0 = (zw r)/zd
+                  const struct ::hdk_csr_s *export_z0_to = nullptr);
+int pcg_update_p(double *p, const double *z, int64_t n, const double *scal, const struct ::hdk_csr_s *export_to = nullptr);
 int vec_copy_dot(double *z, const double *r, int64_t n, int fin, double *out_d);      // z=r, <r,r>
 int allreduce_dev(double *buf_d, int count);                                          // sum over ranks (no-op on 1 rank)
 int allreduce_fin_dev(double *buf_d, int count, int fin, double *fin_out);            // ... + Krylov scalar recurrence, one kernel
@@ -209,6 +218,27 @@ struct IpcRecvArgs
    long long           tmo;             // as in IpcSendArgs
    int                *err;
 };
+// Halo export folded into the PRODUCER of a vector: the kernel that writes x stores the rows its
+// neighbours need straight into their halo buffers (peer stores over NVLink) and its last CTA raises
+// the sequence flags, so the consumer's exchange costs no kernel of its own and is complete long
+// before the consumer reaches a boundary row.  rows / ptr / slot: the exported rows (sorted, unique)
+// and, per row, its positions in the concatenated send list (a row may go to several neighbours).
+struct HaloExport
+{
+   const int          *rows = nullptr, *ptr = nullptr, *slot = nullptr;
+   int                 m = 0;              // number of exported rows (0: nothing to export)
+   int                 lo_end = 0, hi_begin = 0; // rows in [lo_end, hi_begin) are never exported (quick reject)
+   double             *dst[IPC_MAXP];
+   unsigned long long *flag[IPC_MAXP];
+   const unsigned long long *ack = nullptr;
+   int                 off[IPC_MAXP + 1];
+   int                 npeer = 0;
+   unsigned long long  seq = 0;            // 0: export off
+   unsigned           *ticket = nullptr;
+   long long           tmo = 0;
+   int                *err = nullptr;
+};
+
 // off-diagonal block fused into the sliced-ELL kernel (peer-memory halo only): rows flagged in
 // sl_meta add their offd entries after waiting for the neighbours' sequence flags in-kernel
 struct OffdFuse
@@ -229,7 +259,11 @@ struct IpcHalo
    double             *dst[2][IPC_MAXP];
    unsigned long long *dst_flag[IPC_MAXP], *src_ack[IPC_MAXP];
    unsigned long long  seq = 0;
-   unsigned           *tickets = nullptr; // two device counters
+   unsigned           *tickets = nullptr; // three device counters: pack, consumer ack, export
+   // inverse of the send list for exports folded into the producer kernel
+   int                *exp_rows = nullptr, *exp_ptr = nullptr, *exp_slot = nullptr;
+   int                 exp_m = 0, exp_lo_end = 0, exp_hi_begin = 0;
+   bool                preposted = false;  // the current sequence was filled by the producer: no pack kernel
 };
 
 #ifdef __CUDACC__
@@ -267,6 +301,38 @@ __device__ __forceinline__ void wait_seq_sys(const unsigned long long *p, unsign
 {
    if (ld_acquire_sys_u64(p) >= want) return;
    wait_seq_slow(p, want, tmo, err); // out of line: keeps the waiting kernels' register count down
+}
+// producer side of a folded halo exchange: row r of the vector just got value v
+__device__ __forceinline__ void export_row(const HaloExport &e, int r, double v)
+{
+   if (e.seq == 0 || (r >= e.lo_end && r < e.hi_begin)) return;
+   int lo = 0, hi = e.m;
+   while (lo < hi) { int mid = (lo + hi) >> 1; if (e.rows[mid] < r) lo = mid + 1; else hi = mid; }
+   if (lo >= e.m || e.rows[lo] != r) return;
+   for (int k = e.ptr[lo]; k < e.ptr[lo + 1]; k++)
+   {
+      const int s = e.slot[k];
+      int       p = 0;
+      while (p + 1 < e.npeer && s >= e.off[p + 1]) p++;
+      if (e.seq > 2) wait_seq_sys(e.ack + p, e.seq - 2, e.tmo, e.err); // the neighbour has read this half
+      e.dst[p][s - e.off[p]] = v;
+   }
+}
+// end of the producer kernel, executed by every CTA: the last one publishes the sequence number
+__device__ __forceinline__ void export_finish(const HaloExport &e)
+{
+   if (e.seq == 0) return;
+   __threadfence_system();
+   __syncthreads();
+   if (threadIdx.x == 0)
+   {
+      unsigned t = atomicInc(e.ticket, gridDim.x - 1);
+      if (t == gridDim.x - 1)
+      {
+         __threadfence_system();
+         for (int p = 0; p < e.npeer; p++) st_release_sys_u64(e.flag[p], e.seq);
+      }
+   }
 }
 #endif
 
@@ -334,6 +400,10 @@ void halo_plan_free(HaloPlan &H);
 IpcRecvArgs halo_recv_args(const hdk_csr_s &A, const double **xh); // after halo_exchange_begin
 int halo_exchange_begin(const hdk_csr_s &A, const double *x);
 int halo_exchange_end(const hdk_csr_s &A);
+// producer-side exchange: fills *e for the kernel that writes the vector A's next product reads and
+// marks the plan as served; false (and e->seq == 0) when the plan is not on the peer-memory path
+bool halo_export_begin(const hdk_csr_s &A, HaloExport *e);
+void halo_export_cancel(const hdk_csr_s &A); // the exported vector will not be consumed after all
 int comm_check_error(); // HDK_ERR_COMM when a peer-memory wait ran out of its budget since the last call
 
 // ---------------------------------------------------------------------------------------

@@ -130,8 +130,9 @@ int hdk_pcg(const hdk_csr *A, hdk_amg *M, const double *b, double *x, hdk_krylov
          double       *zb = nullptr;
          const double *zd = nullptr;
          double        zw = 1.0;
-         const bool    pf = M && amg_prefill_target(M, s, &zb, &zd, &zw);
-         if ((rc = pcg_update_xr(x, r, p, s, n, S, local_fin(FIN_IPROD), local_out(nullptr), pf ? zb : nullptr, zd, zw))) goto done;
+         const hdk_csr_s *zreader = nullptr;
+         const bool    pf = M && amg_prefill_target(M, s, &zb, &zd, &zw, &zreader);
+         if ((rc = pcg_update_xr(x, r, p, s, n, S, local_fin(FIN_IPROD), local_out(nullptr), pf ? zb : nullptr, zd, zw, pf ? zreader : nullptr))) goto done;
          if (pf) M->prefilled_at = 0;
       }
       if ((rc = finish_dot(FIN_IPROD, nullptr))) goto done;
@@ -144,8 +145,8 @@ int hdk_pcg(const hdk_csr *A, hdk_amg *M, const double *b, double *x, hdk_krylov
       i_prod = g.hscal[S_IPROD];
       if (g.hscal[S_SDOTP] == 0.0 || i_prod != i_prod) { break; }
       if (i_prod / bi_prod < eps) { k->converged = 1; break; }
-      // p = s + beta p
-      if ((rc = pcg_update_p(p, s, n, S))) goto done;
+      // p = s + beta p   (the next iteration's A p reads it: its halo is filled here)
+      if ((rc = pcg_update_p(p, s, n, S, i + 1 <= k->max_iter ? A : nullptr))) goto done;
    }
    k->iters        = i;
    k->rel_res_norm = sqrt(i_prod / bi_prod);

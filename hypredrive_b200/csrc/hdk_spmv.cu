@@ -96,6 +96,9 @@ struct SpmvDev
    const int    *orp, *ocol;
    const double *oval, *xh;
    IpcRecvArgs   ipc;
+   // halo of the NEXT product filled by this kernel (see HaloExport); exp_y2: the exported vector is y2
+   HaloExport    exp;
+   int           exp_y2;
 };
 
 // ---- PTX helpers: mbarrier + 1-D bulk tensor-memory-accelerator copies -------------------
@@ -127,34 +130,34 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
 
 // second output of SPMV_SET_DIV: the zero-guess l1-Jacobi sweep of the next level, u = (w*f)/d
 // (same expression as k_scaled_div)
-template <int MODE>
-__device__ __forceinline__ void store_y2(const SpmvDev &a, int r, double yn, double dd)
-{
-   if (MODE == SPMV_SET_DIV) a.y2[r] = (dd != 0.0) ? __ddiv_rn(__dmul_rn(a.w, yn), dd) : 0.0;
-}
 // writes the outputs of row r and returns the value of y (what a fused dot multiplies).  `v` is the
 // result of the row epilogue: y for most modes, the correction w(b - Ax)/d for JACOBI2, A x for GS_STEP.
-template <int MODE>
+// The row of the output that feeds the next product is also handed to the halo export.
+template <int MODE, bool EXP = false>
 __device__ __forceinline__ double store_out(const SpmvDev &a, int r, double v, double dd, double xo)
 {
+   double yn = v, y2 = 0.0;
    if (MODE == SPMV_JACOBI2)
    {
-      const double yn = __dadd_rn(xo, v);
-      a.y2[r] = v;
-      a.y[r]  = yn;
-      return yn;
+      yn = __dadd_rn(xo, v);
+      y2 = v;
+      a.y2[r] = y2;
    }
-   if (MODE == SPMV_GS_STEP)
+   else if (MODE == SPMV_GS_STEP)
    {
-      const double t  = (dd != 0.0) ? __ddiv_rn(v, dd) : 0.0;
-      const double yn = __dadd_rn(a.y[r], __dmul_rn(a.alpha, t));
-      if (a.y2) a.y2[r] = t;
-      a.y[r] = yn;
-      return yn;
+      y2 = (dd != 0.0) ? __ddiv_rn(v, dd) : 0.0;
+      yn = __dadd_rn(a.y[r], __dmul_rn(a.alpha, y2));
+      if (a.y2) a.y2[r] = y2;
    }
-   a.y[r] = v;
-   store_y2<MODE>(a, r, v, dd);
-   return v;
+   else if (MODE == SPMV_SET_DIV)
+   {
+      y2 = (dd != 0.0) ? __ddiv_rn(__dmul_rn(a.w, v), dd) : 0.0;
+      a.y2[r] = y2;
+   }
+   a.y[r] = yn;
+   // (compiled only into the multi-rank sliced-ELL variants: the plain kernels keep their 32 registers)
+   if (EXP && a.exp.seq) export_row(a.exp, r, a.exp_y2 ? y2 : yn);
+   return yn;
 }
 
 struct BlkMeta { int r0, r1, k0, k1; };
@@ -504,10 +507,11 @@ __device__ __forceinline__ void sell_body(const SpmvDev &a)
          // y += A x: y is read only now (live across the loop it costs 10 registers = 3 CTAs per SM),
          // so the sum is y + (a_0 x_0 + a_1 x_1 + ...) -- rounding-level difference to the CSR-order sum
          if (MODE == SPMV_ADD) acc = __dadd_rn(a.y[r], acc);
-         double yn = store_out<MODE>(a, r, row_epilogue<MODE>(a, o, acc), o.d, o.xo);
+         double yn = store_out<MODE, OFFD>(a, r, row_epilogue<MODE>(a, o, acc), o.d, o.xo);
          if (DOT) dacc += o.dv * yn;
       }
    }
+   if (OFFD) export_finish(a.exp);
    if (OFFD && a.ipc.seq)
    {
       // all reads of xh by this CTA are done; the last CTA tells the senders (buffer reuse at seq + 2)
@@ -744,6 +748,9 @@ int spmv_launch(const DevCSR &A, int mode, const SpmvArgs &s, const OffdFuse *of
       if (A.kind != 2 || !A.sl_offd_flags) return set_error(HDK_ERR_INVALID, "fused off-diagonal block needs the sliced-ELL layout");
       d.orp = of->orp; d.ocol = of->ocol; d.oval = of->oval; d.xh = of->xh; d.ipc = of->ipc;
    }
+   d.exp = HaloExport();
+   d.exp_y2 = s.export_y2 ? 1 : 0;
+   if (s.export_to && of) halo_export_begin(*s.export_to, &d.exp); // only the fused multi-rank kernel carries the export code
    bool dot = (s.fin != FIN_NONE && s.dotv != nullptr);
    switch (mode)
    {

@@ -42,13 +42,16 @@ __global__ void __launch_bounds__(VT) k_scale(double a, double *x, int64_t n)
 // u = (w*f)/d : an l1-Jacobi sweep from a zero initial guess (bit-identical to the general
 // sweep with u_old = 0)
 __global__ void __launch_bounds__(VT) k_scaled_div(double *__restrict__ u, const double *__restrict__ f,
-                                                   const double *__restrict__ d, double w, int64_t n)
+                                                   const double *__restrict__ d, double w, int64_t n, const HaloExport ex)
 {
    for (int64_t i = blockIdx.x * (int64_t)VT + threadIdx.x; i < n; i += (int64_t)gridDim.x * VT)
    {
       double dd = d[i];
-      u[i]      = (dd != 0.0) ? __ddiv_rn(__dmul_rn(w, f[i]), dd) : 0.0;
+      double v  = (dd != 0.0) ? __ddiv_rn(__dmul_rn(w, f[i]), dd) : 0.0;
+      u[i]      = v;
+      if (ex.seq) export_row(ex, (int)i, v);
    }
+   export_finish(ex);
 }
 
 // kind: 0 dot(x,y), 1 sum|x|, 2 max|x| (max uses the same tree with fmax)
@@ -119,7 +122,7 @@ __device__ __forceinline__ double pcg_xr_row(double alpha, double xi, double pi,
 template <bool PREFILL>
 __global__ void __launch_bounds__(VT) k_pcg_xr(double *x, double *r, const double *p, const double *s, int64_t n,
                                                double *partials, unsigned *ticket, double *scal, int fin, double *fin_out,
-                                               double *z0, const double *zd, double zw)
+                                               double *z0, const double *zd, double zw, const HaloExport ex)
 {
    __shared__ double sm[VT / 32];
    __shared__ int    flag;
@@ -147,6 +150,7 @@ __global__ void __launch_bounds__(VT) k_pcg_xr(double *x, double *r, const doubl
          zo.x = (di.x != 0.0) ? __ddiv_rn(__dmul_rn(zw, ro.x), di.x) : 0.0;
          zo.y = (di.y != 0.0) ? __ddiv_rn(__dmul_rn(zw, ro.y), di.y) : 0.0;
          z2[i] = zo;
+         if (ex.seq) { export_row(ex, (int)(2 * i), zo.x); export_row(ex, (int)(2 * i + 1), zo.y); }
       }
       acc += ro.x * ro.x; acc += ro.y * ro.y;
       xo.x = __dadd_rn(xj.x, __dmul_rn(alpha, pj.x)); xo.y = __dadd_rn(xj.y, __dmul_rn(alpha, pj.y));
@@ -157,6 +161,7 @@ __global__ void __launch_bounds__(VT) k_pcg_xr(double *x, double *r, const doubl
          zo.x = (dj.x != 0.0) ? __ddiv_rn(__dmul_rn(zw, ro.x), dj.x) : 0.0;
          zo.y = (dj.y != 0.0) ? __ddiv_rn(__dmul_rn(zw, ro.y), dj.y) : 0.0;
          z2[j] = zo;
+         if (ex.seq) { export_row(ex, (int)(2 * j), zo.x); export_row(ex, (int)(2 * j + 1), zo.y); }
       }
       acc += ro.x * ro.x; acc += ro.y * ro.y;
    }
@@ -174,6 +179,7 @@ __global__ void __launch_bounds__(VT) k_pcg_xr(double *x, double *r, const doubl
          zo.x = (di.x != 0.0) ? __ddiv_rn(__dmul_rn(zw, ro.x), di.x) : 0.0;
          zo.y = (di.y != 0.0) ? __ddiv_rn(__dmul_rn(zw, ro.y), di.y) : 0.0;
          z2[i] = zo;
+         if (ex.seq) { export_row(ex, (int)(2 * i), zo.x); export_row(ex, (int)(2 * i + 1), zo.y); }
       }
       acc += ro.x * ro.x; acc += ro.y * ro.y;
    }
@@ -182,7 +188,9 @@ __global__ void __launch_bounds__(VT) k_pcg_xr(double *x, double *r, const doubl
       const int64_t k  = n - 1;
       const double  dk = PREFILL ? zd[k] : 0.0;
       acc += pcg_xr_row<PREFILL>(alpha, x[k], p[k], r[k], s[k], dk, zw, x, r, z0, k);
+      if (PREFILL && ex.seq) export_row(ex, (int)k, z0[k]);
    }
+   if (PREFILL) export_finish(ex);
    double bs = block_sum<VT>(acc, sm);
    __syncthreads();
    grid_finish<VT>(bs, partials, ticket, fin, fin_out, scal, sm, &flag);
@@ -190,7 +198,7 @@ __global__ void __launch_bounds__(VT) k_pcg_xr(double *x, double *r, const doubl
 
 // PCG: p = z + beta p   (128-bit accesses, two row pairs per trip)
 __global__ void __launch_bounds__(VT) k_pcg_p(double *__restrict__ p, const double *__restrict__ z,
-                                              int64_t n, const double *__restrict__ scal)
+                                              int64_t n, const double *__restrict__ scal, const HaloExport ex)
 {
    const double   beta = scal[S_BETA];
    const int64_t  n2 = n >> 1, stride = (int64_t)gridDim.x * VT;
@@ -201,15 +209,29 @@ __global__ void __launch_bounds__(VT) k_pcg_p(double *__restrict__ p, const doub
    {
       const int64_t j = i + stride;
       const double2 pi = p2[i], zi = z2[i], pj = p2[j], zj = z2[j];
-      p2[i] = make_double2(__dadd_rn(zi.x, __dmul_rn(beta, pi.x)), __dadd_rn(zi.y, __dmul_rn(beta, pi.y)));
-      p2[j] = make_double2(__dadd_rn(zj.x, __dmul_rn(beta, pj.x)), __dadd_rn(zj.y, __dmul_rn(beta, pj.y)));
+      const double2 qi = make_double2(__dadd_rn(zi.x, __dmul_rn(beta, pi.x)), __dadd_rn(zi.y, __dmul_rn(beta, pi.y)));
+      const double2 qj = make_double2(__dadd_rn(zj.x, __dmul_rn(beta, pj.x)), __dadd_rn(zj.y, __dmul_rn(beta, pj.y)));
+      p2[i] = qi; p2[j] = qj;
+      if (ex.seq)
+      {
+         export_row(ex, (int)(2 * i), qi.x); export_row(ex, (int)(2 * i + 1), qi.y);
+         export_row(ex, (int)(2 * j), qj.x); export_row(ex, (int)(2 * j + 1), qj.y);
+      }
    }
    if (i < n2)
    {
       const double2 pi = p2[i], zi = z2[i];
-      p2[i] = make_double2(__dadd_rn(zi.x, __dmul_rn(beta, pi.x)), __dadd_rn(zi.y, __dmul_rn(beta, pi.y)));
+      const double2 qi = make_double2(__dadd_rn(zi.x, __dmul_rn(beta, pi.x)), __dadd_rn(zi.y, __dmul_rn(beta, pi.y)));
+      p2[i] = qi;
+      if (ex.seq) { export_row(ex, (int)(2 * i), qi.x); export_row(ex, (int)(2 * i + 1), qi.y); }
    }
-   if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) p[n - 1] = __dadd_rn(z[n - 1], __dmul_rn(beta, p[n - 1]));
+   if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0)
+   {
+      const double q = __dadd_rn(z[n - 1], __dmul_rn(beta, p[n - 1]));
+      p[n - 1] = q;
+      if (ex.seq) export_row(ex, (int)(n - 1), q);
+   }
+   export_finish(ex);
 }
 
 // scalar forms for operands that are not 16-byte aligned (sub-vectors at odd offsets)
@@ -315,10 +337,12 @@ int vec_scale(double a, double *x, int64_t n)
    HDK_LAUNCH_CHECK();
    return HDK_OK;
 }
-int vec_scaled_div(double *u, const double *f, const double *d, double w, int64_t n)
+int vec_scaled_div(double *u, const double *f, const double *d, double w, int64_t n, const hdk_csr_s *export_to)
 {
    if (n <= 0) return HDK_OK;
-   k_scaled_div<<<vec_grid(n), VT, 0, g.stream>>>(u, f, d, w, n);
+   HaloExport ex;
+   if (export_to) halo_export_begin(*export_to, &ex);
+   k_scaled_div<<<vec_grid(n), VT, 0, g.stream>>>(u, f, d, w, n, ex);
    HDK_LAUNCH_CHECK();
    return HDK_OK;
 }
@@ -341,8 +365,10 @@ static inline bool aligned16(const void *a, const void *b = nullptr, const void 
 }
 
 int pcg_update_xr(double *x, double *r, const double *p, const double *s, int64_t n, double *scal, int fin, double *fin_out,
-                  double *z0, const double *zd, double zw)
+                  double *z0, const double *zd, double zw, const hdk_csr_s *export_z0_to)
 {
+   HaloExport ex;
+   if (z0 && export_z0_to && aligned16(x, r, p, s, z0, zd)) halo_export_begin(*export_z0_to, &ex);
    if (!aligned16(x, r, p, s, z0, zd))
    {
       if (z0) k_pcg_xr_scalar<true><<<vec_grid(n), VT, 0, g.stream>>>(x, r, p, s, n, g.partials, g.counters, scal, fin, fin_out, z0, zd, zw);
@@ -350,16 +376,18 @@ int pcg_update_xr(double *x, double *r, const double *p, const double *s, int64_
       HDK_LAUNCH_CHECK();
       return HDK_OK;
    }
-   if (z0) k_pcg_xr<true><<<vec_grid(n), VT, 0, g.stream>>>(x, r, p, s, n, g.partials, g.counters, scal, fin, fin_out, z0, zd, zw);
-   else k_pcg_xr<false><<<vec_grid(n), VT, 0, g.stream>>>(x, r, p, s, n, g.partials, g.counters, scal, fin, fin_out, z0, zd, zw);
+   if (z0) k_pcg_xr<true><<<vec_grid(n), VT, 0, g.stream>>>(x, r, p, s, n, g.partials, g.counters, scal, fin, fin_out, z0, zd, zw, ex);
+   else k_pcg_xr<false><<<vec_grid(n), VT, 0, g.stream>>>(x, r, p, s, n, g.partials, g.counters, scal, fin, fin_out, z0, zd, zw, ex);
    HDK_LAUNCH_CHECK();
    return HDK_OK;
 }
-int pcg_update_p(double *p, const double *z, int64_t n, const double *scal)
+int pcg_update_p(double *p, const double *z, int64_t n, const double *scal, const hdk_csr_s *export_to)
 {
    if (n <= 0) return HDK_OK;
+   HaloExport ex;
+   if (export_to && aligned16(p, z)) halo_export_begin(*export_to, &ex);
    if (!aligned16(p, z)) k_pcg_p_scalar<<<vec_grid(n), VT, 0, g.stream>>>(p, z, n, scal);
-   else k_pcg_p<<<vec_grid(n), VT, 0, g.stream>>>(p, z, n, scal);
+   else k_pcg_p<<<vec_grid(n), VT, 0, g.stream>>>(p, z, n, scal, ex);
    HDK_LAUNCH_CHECK();
    return HDK_OK;
 }
