@@ -1148,19 +1148,27 @@ constexpr int RW_CAP   = 512;  // hash slots per warp
 constexpr int RW_LIMIT = 320;  // longest row handled here; longer rows fall back to k_rap_count/fill
 constexpr int RW_WARPS = 8;
 
-template <bool FILL, int CAP>
+// BUMP (single-pass product): the finished row goes to a bump-allocated position of a staging buffer
+// (one atomicAdd per row) and cnt / rowoff record its length and position; rows that do not fit this
+// table size are flagged (cnt = -1) for the next larger table, a full staging buffer is reported as
+// cnt = -2 (the host then falls back to the two-pass product).
+template <bool FILL, int CAP, bool BUMP = false>
 __global__ void __launch_bounds__(32 * RW_WARPS) k_rap_warp(const int *rrp, const int *rcol, const double *rval,
                                                             const int *arp, const int *acol, const double *aval,
                                                             const int *prp, const int *pcol, const double *pval,
                                                             int nc, int *cnt, const int *crp, int *ccol, double *cval,
-                                                            int row_lo, int len_lo, int len_hi)
+                                                            int row_lo, int len_lo, int len_hi,
+                                                            unsigned long long *bump_cursor = nullptr, long long bump_cap = 0,
+                                                            long long *rowoff = nullptr, int only_flagged = 0)
 {
    extern __shared__ __align__(16) unsigned char rw_smem[];
    const int      lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
    const unsigned FULL = 0xffffffffu;
    const int      ic = row_lo + blockIdx.x * RW_WARPS + wid; // rows [row_lo, nc)
    if (ic >= nc) return;
-   if (FILL) { const int c = cnt[ic]; if (c > RW_LIMIT || c <= len_lo || c > len_hi) return; } // rows of this table size
+   constexpr int LIMIT = BUMP ? (((CAP * 5) / 8 < RW_LIMIT) ? (CAP * 5) / 8 : RW_LIMIT) : RW_LIMIT; // longest row this table takes
+   if (FILL && !BUMP) { const int c = cnt[ic]; if (c > RW_LIMIT || c <= len_lo || c > len_hi) return; } // rows of this table size
+   if (BUMP && only_flagged && cnt[ic] != -1) return;                                             // rows the smaller table gave up on
    int    *keys = reinterpret_cast<int *>(rw_smem) + (size_t)wid * CAP;
    int    *idx  = reinterpret_cast<int *>(rw_smem) + (size_t)RW_WARPS * CAP + (size_t)wid * CAP;
    double *vals = reinterpret_cast<double *>(rw_smem + (size_t)2 * RW_WARPS * CAP * sizeof(int)) + (size_t)wid * CAP;
@@ -1251,7 +1259,7 @@ __global__ void __launch_bounds__(32 * RW_WARPS) k_rap_warp(const int *rrp, cons
             const unsigned newmask = __ballot_sync(FULL, leader && isnew);
             if (FILL && leader && isnew) idx[h] = count + __popc(newmask & ((1u << lane) - 1u));
             count += __popc(newmask);
-            if (count > RW_LIMIT) overflow = true;
+            if (count > LIMIT) overflow = true;
             if (FILL)
             {
                const int maxc = (int)__reduce_max_sync(FULL, leader ? (unsigned)__popc(grp) : 0u);
@@ -1279,9 +1287,40 @@ __global__ void __launch_bounds__(32 * RW_WARPS) k_rap_warp(const int *rrp, cons
       }
    }
    if (!FILL) { if (lane == 0) cnt[ic] = overflow ? -1 : count; return; }
+   if (BUMP)
+   {
+      if (overflow) { if (lane == 0) cnt[ic] = -1; return; }
+      long long off = 0;
+      if (lane == 0) off = (long long)atomicAdd(bump_cursor, (unsigned long long)count);
+      off = __shfl_sync(FULL, off, 0);
+      if (off + count > bump_cap) { if (lane == 0) cnt[ic] = -2; return; }
+      for (int h = lane; h < CAP; h += 32)
+         if (keys[h] >= 0) { int s = idx[h]; ccol[off + s] = keys[h]; cval[off + s] = vals[h]; }
+      if (lane == 0) { cnt[ic] = count; rowoff[ic] = off; }
+      return;
+   }
    const int b = crp[ic];
    for (int h = lane; h < CAP; h += 32)
       if (keys[h] >= 0) { int s = idx[h]; ccol[b + s] = keys[h]; cval[b + s] = vals[h]; }
+}
+
+// staging buffer -> final CSR position (one warp per row; rows longer than RW_LIMIT come from k_rap_fill)
+__global__ void k_rap_compact(const int *cnt, const long long *rowoff, const int *crp, const int *bcol, const double *bval,
+                              int row_lo, int row_hi, int *ccol, double *cval)
+{
+   const int lane = threadIdx.x & 31;
+   const int ic = row_lo + blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+   if (ic >= row_hi) return;
+   const int c = cnt[ic];
+   if (c <= 0 || c > RW_LIMIT) return;
+   const long long o = rowoff[ic];
+   const int       b = crp[ic];
+   for (int k = lane; k < c; k += 32) { ccol[b + k] = bcol[o + k]; cval[b + k] = bval[o + k]; }
+}
+__global__ void k_any_equal(const int *v, int n, int key, int *out)
+{
+   int i = blockIdx.x * blockDim.x + threadIdx.x;
+   if (i < n && v[i] == key) *out = 1;
 }
 
 __global__ void k_max_int(const int *v, int n, int *out)
@@ -1396,11 +1435,77 @@ int build_rap(const DevCSR &R, const DevCSR &A, const DevCSR &P, DevCSR &C, int 
    share_range(nc, lo, hi);
    if (row_lo >= 0) { lo = row_lo; hi = row_hi; }
    if (share_on(nc) || lo != 0 || hi != nc) HDK_CUDA(cudaMemsetAsync(cnt, 0, sizeof(int) * ((size_t)nc + 1), g.stream));
-   // pass 1a: exact row lengths by the warp kernel (rows longer than RW_LIMIT are flagged -1)
-   k_rap_warp<false, RW_CAP><<<cdiv(hi - lo, RW_WARPS), 32 * RW_WARPS, (size_t)RW_WARPS * RW_CAP * sizeof(int), g.stream>>>(
-      R.rowptr, R.col, R.val, A.rowptr, A.col, A.val, P.rowptr, P.col, P.val, hi, cnt, nullptr, nullptr, nullptr, lo, 0, 0);
-   HDK_LAUNCH_CHECK();
-   stage_mark("  rap.warp1", -1);
+   // Single-pass product (default; HDK_RAP_SINGLE=0 selects count + fill): every row is computed ONCE into
+   // a staging buffer, 256-slot tables first, the rows those cannot hold with 512-slot tables; the
+   // row lengths fall out of the same pass, then the rows are copied to their CSR position.  Rows
+   // longer than RW_LIMIT take the one-thread-per-row path below either way.
+   static int rap_single = -1;
+   if (rap_single < 0) { const char *e = getenv("HDK_RAP_SINGLE"); rap_single = (e && atoi(e) == 0) ? 0 : 1; }
+   int       *bcol = nullptr;
+   double    *bval = nullptr;
+   long long *rowoff = nullptr;
+   bool       single = rap_single == 1;
+   if (single)
+   {
+      const long long bump_cap = 2LL * (long long)A.nnz + (1LL << 22);
+      unsigned long long *cursor = reinterpret_cast<unsigned long long *>(g.dscal + S_TMP2);
+      int *flag = reinterpret_cast<int *>(g.dscal + S_TMP3);
+      if (bump_cap > 2000000000LL) single = false;
+      if (single)
+      {
+         static bool attr_b = false;
+         if (!attr_b)
+         {
+            HDK_CUDA(cudaFuncSetAttribute(k_rap_warp<true, 256, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, RW_WARPS * 256 * 16));
+            HDK_CUDA(cudaFuncSetAttribute(k_rap_warp<true, RW_CAP, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, RW_WARPS * RW_CAP * 16));
+            attr_b = true;
+         }
+         HDK_TRY(dalloc(&bcol, (size_t)bump_cap + 8));
+         HDK_TRY(dalloc(&bval, (size_t)bump_cap + 8));
+         HDK_TRY(dalloc(&rowoff, (size_t)nc + 1));
+         HDK_CUDA(cudaMemsetAsync(cursor, 0, sizeof(unsigned long long), g.stream));
+         HDK_CUDA(cudaMemsetAsync(flag, 0, sizeof(int), g.stream));
+         const int nb = cdiv(hi - lo, RW_WARPS);
+         k_rap_warp<true, 256, true><<<nb, 32 * RW_WARPS, (size_t)RW_WARPS * 256 * 16, g.stream>>>(
+            R.rowptr, R.col, R.val, A.rowptr, A.col, A.val, P.rowptr, P.col, P.val, hi, cnt, nullptr, bcol, bval, lo, 0, 0,
+            cursor, bump_cap, rowoff, 0);
+         HDK_LAUNCH_CHECK();
+         k_any_equal<<<cdiv(hi - lo, 256), 256, 0, g.stream>>>(cnt + lo, hi - lo, -1, flag);
+         HDK_LAUNCH_CHECK();
+         int hflag = 0;
+         HDK_CUDA(cudaMemcpyAsync(&hflag, flag, sizeof(int), cudaMemcpyDeviceToHost, g.stream));
+         HDK_CUDA(cudaStreamSynchronize(g.stream));
+         if (hflag)
+         {
+            k_rap_warp<true, RW_CAP, true><<<nb, 32 * RW_WARPS, (size_t)RW_WARPS * RW_CAP * 16, g.stream>>>(
+               R.rowptr, R.col, R.val, A.rowptr, A.col, A.val, P.rowptr, P.col, P.val, hi, cnt, nullptr, bcol, bval, lo, 0, 0,
+               cursor, bump_cap, rowoff, 1);
+            HDK_LAUNCH_CHECK();
+         }
+         // staging buffer exhausted somewhere? then start over with the two-pass product
+         HDK_CUDA(cudaMemsetAsync(flag, 0, sizeof(int), g.stream));
+         k_any_equal<<<cdiv(hi - lo, 256), 256, 0, g.stream>>>(cnt + lo, hi - lo, -2, flag);
+         HDK_LAUNCH_CHECK();
+         HDK_CUDA(cudaMemcpyAsync(&hflag, flag, sizeof(int), cudaMemcpyDeviceToHost, g.stream));
+         HDK_CUDA(cudaStreamSynchronize(g.stream));
+         if (hflag)
+         {
+            single = false;
+            dfree(bcol); dfree(bval); dfree(rowoff);
+            bcol = nullptr; bval = nullptr; rowoff = nullptr;
+            if (lo != 0 || hi != nc) HDK_CUDA(cudaMemsetAsync(cnt, 0, sizeof(int) * ((size_t)nc + 1), g.stream));
+         }
+      }
+      stage_mark("  rap.single", -1);
+   }
+   if (!single)
+   {
+      // pass 1a: exact row lengths by the warp kernel (rows longer than RW_LIMIT are flagged -1)
+      k_rap_warp<false, RW_CAP><<<cdiv(hi - lo, RW_WARPS), 32 * RW_WARPS, (size_t)RW_WARPS * RW_CAP * sizeof(int), g.stream>>>(
+         R.rowptr, R.col, R.val, A.rowptr, A.col, A.val, P.rowptr, P.col, P.val, hi, cnt, nullptr, nullptr, nullptr, lo, 0, 0);
+      HDK_LAUNCH_CHECK();
+      stage_mark("  rap.warp1", -1);
+   }
    // pass 1b: flagged rows through the one-thread-per-row kernel with hash sets in global scratch
    k_rap_cap<<<cdiv(nc + 1, 256), 256, 0, g.stream>>>(R.rowptr, R.col, q, nc, cap, cnt);
    HDK_LAUNCH_CHECK();
@@ -1435,6 +1540,14 @@ int build_rap(const DevCSR &R, const DevCSR &A, const DevCSR &P, DevCSR &C, int 
    HDK_TRY(dalloc(&C.val, (size_t)nnzC + 8));
    HDK_CUDA(cudaMemsetAsync(C.col + nnzC, 0, sizeof(int) * 8, g.stream));
    HDK_CUDA(cudaMemsetAsync(C.val + nnzC, 0, sizeof(double) * 8, g.stream));
+   if (single)
+   {
+      k_rap_compact<<<cdiv(hi - lo, 8), 256, 0, g.stream>>>(cnt, rowoff, crp, bcol, bval, lo, hi, C.col, C.val);
+      HDK_LAUNCH_CHECK();
+      dfree(bcol); dfree(bval); dfree(rowoff);
+      stage_mark("  rap.compact", -1);
+   }
+   else
    {
       // small tables (more resident warps) when every row of the level is short
       int *dmax = reinterpret_cast<int *>(g.dscal + S_TMP3), hmax = 0;

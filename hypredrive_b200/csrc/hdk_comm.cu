@@ -5,6 +5,7 @@
 // dlopen so that a process that already carries torch's libnccl shares that copy.
 #include "hdk_internal.cuh"
 #include <dlfcn.h>
+#include <time.h>
 #include <algorithm>
 #include <map>
 
@@ -838,6 +839,53 @@ int hdk_comm_init(int rank, int nranks, const void *id128_h)
    HDK_NCCL(nccl.CommInitRank(&comm, nranks, id, rank));
    g.nccl = comm; g.rank = rank; g.nranks = nranks;
    return ipc_setup();
+}
+
+// Communicator bootstrap for callers that have no channel of their own for the NCCL unique id (the C
+// API, hypredrive-cli): the launcher's RANK / WORLD_SIZE / LOCAL_RANK say who we are, rank 0 publishes
+// the id in a file every rank can see (HDK_NCCL_ID_FILE, default /tmp/hdk_nccl_id.<MASTER_ADDR>.<MASTER_PORT>),
+// the others wait for it.  No-op with one process or when a communicator already exists.
+int hdk_comm_init_from_env(void)
+{
+   HDK_TRY(require_init());
+   const char *ws = getenv("WORLD_SIZE"), *rk = getenv("RANK");
+   const int   world = ws ? atoi(ws) : 1, rank = rk ? atoi(rk) : 0;
+   if (world <= 1 || g.nccl) return HDK_OK;
+   char path[1024];
+   const char *pf = getenv("HDK_NCCL_ID_FILE");
+   if (pf && *pf) snprintf(path, sizeof(path), "%s", pf);
+   else snprintf(path, sizeof(path), "/tmp/hdk_nccl_id.%s.%s", getenv("MASTER_ADDR") ? getenv("MASTER_ADDR") : "local",
+                 getenv("MASTER_PORT") ? getenv("MASTER_PORT") : "0");
+   unsigned char id[128];
+   if (rank == 0)
+   {
+      HDK_TRY(hdk_comm_unique_id(id));
+      char tmp[1100];
+      snprintf(tmp, sizeof(tmp), "%s.tmp", path);
+      FILE *fp = fopen(tmp, "wb");
+      if (!fp || fwrite(id, 1, 128, fp) != 128) { if (fp) fclose(fp); return set_error(HDK_ERR_COMM, "cannot write the NCCL id file %s", tmp); }
+      fclose(fp);
+      if (rename(tmp, path)) return set_error(HDK_ERR_COMM, "cannot publish the NCCL id file %s", path);
+   }
+   else
+   {
+      bool got = false;
+      for (int tries = 0; tries < 1200 && !got; tries++) // up to 2 minutes
+      {
+         FILE *fp = fopen(path, "rb");
+         if (fp) { got = fread(id, 1, 128, fp) == 128; fclose(fp); }
+         if (!got) { struct timespec ts = {0, 100000000L}; nanosleep(&ts, nullptr); }
+      }
+      if (!got) return set_error(HDK_ERR_COMM, "timed out waiting for the NCCL id file %s (WORLD_SIZE=%d but rank 0 did not publish it)", path, world);
+   }
+   int rc = hdk_comm_init(rank, world, id);
+   if (rc == HDK_OK)
+   {
+      int64_t s = 0;
+      rc = hdk_comm_sum_i64(1, &s); // every rank has read the file
+      if (rank == 0) remove(path);
+   }
+   return rc;
 }
 
 int hdk_comm_max_i64(int64_t local, int64_t *global)

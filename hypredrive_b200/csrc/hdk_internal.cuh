@@ -437,7 +437,9 @@ __device__ __forceinline__ void apply_fin(int fin, double v, double *out, double
    switch (fin)
    {
       case FIN_STORE: out[0] = v; break;
-      case FIN_SDOTP: scal[S_SDOTP] = v; scal[S_ALPHA] = scal[S_GAMMA] / v; break;
+      // <Ap,p> = 0 is a breakdown (hypre_PCGSolve stops before the update): alpha = 0 leaves x and r
+      // untouched, the host sees S_SDOTP == 0 and ends the iteration
+      case FIN_SDOTP: scal[S_SDOTP] = v; scal[S_ALPHA] = (v != 0.0) ? scal[S_GAMMA] / v : 0.0; break;
       case FIN_IPROD: scal[S_IPROD] = v; break;
       case FIN_GAMMA:
       {

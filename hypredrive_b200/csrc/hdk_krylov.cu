@@ -167,7 +167,7 @@ static int gmres_impl(const hdk_csr *A, hdk_amg *M, const double *b, double *x, 
    HDK_TRY(require_init());
    if (!A || !b || !x || !k) return set_error(HDK_ERR_INVALID, "hdk_gmres: null argument");
    const int64_t n  = A->diag.nrows;
-   const int     kd = k->krylov_dim > 0 ? (k->krylov_dim > 46 ? 46 : k->krylov_dim) : 30;
+   const int     kd = k->krylov_dim > 0 ? k->krylov_dim : 30;
    k->iters = 0; k->converged = 0; k->rel_res_norm = 0.0; k->solve_ms = 0.0;
    std::vector<double *> p((size_t)kd + 1, nullptr);
    double *r = nullptr, *w = nullptr;
@@ -181,7 +181,11 @@ static int gmres_impl(const hdk_csr *A, hdk_amg *M, const double *b, double *x, 
    std::vector<double> hh((size_t)(kd + 2) * (kd + 1), 0.0);
 #define HH(a_, b_) hh[(size_t)(a_) * (kd + 1) + (b_)]
    const double epsmac = 1.e-16;
-   double *S = g.dscal;
+   // Hessenberg column of the current inner iteration: kd + 2 coefficients on the device with a host
+   // mirror (sized by krylov_dim, so any restart length works)
+   double *H = nullptr;
+   HDK_TRY(dalloc(&H, (size_t)kd + 2));
+   std::vector<double> hcol((size_t)kd + 2, 0.0);
    HDK_CUDA(cudaEventRecord(g.ev_a, g.stream));
    double b_norm = 0, r_norm = 0, t = 0;
    int    iter = 0;
@@ -227,19 +231,19 @@ static int gmres_impl(const hdk_csr *A, hdk_amg *M, const double *b, double *x, 
             // of the SpMV kernel; step j subtracts h_j p_j and produces h_{j+1} (or <p_i,p_i>) in one pass
             SpmvArgs a;
             a.x = zz; a.y = p[(size_t)i];
-            a.dotv = p[0]; a.fin = FIN_STORE; a.fin_out = S + S_H0;
+            a.dotv = p[0]; a.fin = FIN_STORE; a.fin_out = H;
             if ((rc = parcsr_matvec(*A, SPMV_SET, a))) goto done;
-            if ((rc = allreduce_dev(S + S_H0, 1))) goto done;
+            if ((rc = allreduce_dev(H, 1))) goto done;
             for (int j = 0; j < i; j++)
             {
                const double *znext = (j + 1 < i) ? p[(size_t)j + 1] : p[(size_t)i];
-               if ((rc = axpy_dot_dev(S + S_H0 + j, p[(size_t)j], p[(size_t)i], znext, n, S + S_H0 + j + 1))) goto done;
-               if ((rc = allreduce_dev(S + S_H0 + j + 1, 1))) goto done;
+               if ((rc = axpy_dot_dev(H + j, p[(size_t)j], p[(size_t)i], znext, n, H + j + 1))) goto done;
+               if ((rc = allreduce_dev(H + j + 1, 1))) goto done;
             }
-            HDK_CUDA(cudaMemcpyAsync(g.hscal + S_H0, S + S_H0, sizeof(double) * (size_t)(i + 1), cudaMemcpyDeviceToHost, g.stream));
+            HDK_CUDA(cudaMemcpyAsync(hcol.data(), H, sizeof(double) * (size_t)(i + 1), cudaMemcpyDeviceToHost, g.stream));
             HDK_CUDA(cudaStreamSynchronize(g.stream));
-            for (int j = 0; j < i; j++) HH(j, i - 1) = g.hscal[S_H0 + j];
-            t            = sqrt(g.hscal[S_H0 + i]);
+            for (int j = 0; j < i; j++) HH(j, i - 1) = hcol[(size_t)j];
+            t            = sqrt(hcol[(size_t)i]);
             HH(i, i - 1) = t;
             if (t != 0.0) { if ((rc = vec_scale(1.0 / t, p[(size_t)i], n))) goto done; }
             for (int j = 1; j < i; j++)
@@ -324,7 +328,7 @@ done:
    k->solve_ms = ms;
    for (auto q : p) dfree(q);
    for (auto q : z) dfree(q);
-   dfree(r); dfree(w);
+   dfree(r); dfree(w); dfree(H);
    if (rc == HDK_OK) rc = comm_check_error();
    return rc;
 }

@@ -422,9 +422,33 @@ __device__ __forceinline__ double row_epilogue(const SpmvDev &a, const RowOps &o
    return (o.d != 0.0) ? __ddiv_rn(__dmul_rn(a.w, acc), o.d) : 0.0;
 }
 
+// x gathers of the sliced-ELL kernel.  HDK_XHINT builds tag them with an L2 evict_last policy (the
+// val / col stream is evict_first already): on the big coarse levels the gathered vector is re-read
+// from HBM ~10x because the 1.8 GB operator stream pushes it out of L2 between its first and last use.
+#ifdef HDK_XHINT
+__device__ __forceinline__ uint64_t x_policy()
+{
+   uint64_t pol;
+   asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+   return pol;
+}
+__device__ __forceinline__ double ld_x(const double *p, uint64_t pol)
+{
+   double v;
+   asm volatile("ld.global.nc.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(v) : "l"(p), "l"(pol));
+   return v;
+}
+#define LDX(p) ld_x((p), xpol)
+#else
+#define LDX(p) __ldg(p)
+#endif
+
 template <int MODE, bool DOT, bool OFFD>
 __device__ __forceinline__ void sell_body(const SpmvDev &a)
 {
+#ifdef HDK_XHINT
+   const uint64_t xpol = x_policy();
+#endif
    constexpr bool SUB  = (MODE == SPMV_RESIDUAL || MODE == SPMV_JACOBI || MODE == SPMV_JACOBI_R || MODE == SPMV_JACOBI2);
    constexpr bool DIAG = (MODE == SPMV_JACOBI || MODE == SPMV_JACOBI_R || MODE == SPMV_SET_DIV || MODE == SPMV_JACOBI2 || MODE == SPMV_GS_STEP);
    constexpr bool XOLD = (MODE == SPMV_JACOBI || MODE == SPMV_JACOBI2);
@@ -432,7 +456,10 @@ __device__ __forceinline__ void sell_body(const SpmvDev &a)
    __shared__ int    flag;
    const int lane = threadIdx.x & 31;
    const int wpb  = SELL_T / 32;
-   double    dacc = 0.0;
+   // fused dot: the per-thread partial lives in shared memory, not in a register pair that would be
+   // live across the streaming loop (the loop's register budget decides the occupancy)
+   __shared__ double s_dot[DOT ? SELL_T : 1];
+   if (DOT) s_dot[threadIdx.x] = 0.0;
    bool      halo_ready = false;
    for (int s = blockIdx.x * wpb + (threadIdx.x >> 5); s < a.nslice; s += gridDim.x * wpb)
    {
@@ -467,7 +494,7 @@ __device__ __forceinline__ void sell_body(const SpmvDev &a)
 #pragma unroll 1 // unrolled copies of this software-pipelined body double the register count (occupancy)
       for (int k = 0; k < len; k += 4)
       {
-         const double x0 = __ldg(a.x + c0), x1 = __ldg(a.x + c1), x2 = __ldg(a.x + c2), x3 = __ldg(a.x + c3);
+         const double x0 = LDX(a.x + c0), x1 = LDX(a.x + c1), x2 = LDX(a.x + c2), x3 = LDX(a.x + c3);
          const size_t q  = (size_t)(k + 4) * 32;
          int          n0 = 0, n1 = 0, n2 = 0, n3 = 0;
          double       w0 = 0.0, w1 = 0.0, w2 = 0.0, w3 = 0.0;
@@ -508,7 +535,7 @@ __device__ __forceinline__ void sell_body(const SpmvDev &a)
          // so the sum is y + (a_0 x_0 + a_1 x_1 + ...) -- rounding-level difference to the CSR-order sum
          if (MODE == SPMV_ADD) acc = __dadd_rn(a.y[r], acc);
          double yn = store_out<MODE, OFFD>(a, r, row_epilogue<MODE>(a, o, acc), o.d, o.xo);
-         if (DOT) dacc += o.dv * yn;
+         if (DOT) s_dot[threadIdx.x] += o.dv * yn;
       }
    }
    if (OFFD) export_finish(a.exp);
@@ -528,7 +555,7 @@ __device__ __forceinline__ void sell_body(const SpmvDev &a)
    }
    if (DOT)
    {
-      double bs = block_sum<SELL_T>(dacc, red);
+      double bs = block_sum<SELL_T>(s_dot[threadIdx.x], red);
       __syncthreads();
       grid_finish<SELL_T>(bs, a.partials, a.ticket, a.fin, a.fin_out, a.scal, red, &flag);
    }

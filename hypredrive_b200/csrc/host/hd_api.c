@@ -127,6 +127,14 @@ uint32_t HYPREDRV_Create(MPI_Comm comm, HYPREDRV_t *out)
    if (!h) return fail(HYPREDRV_ERROR_ALLOCATION, NULL, NULL);
    h->magic = HD_OBJ_MAGIC;
    h->comm  = comm;
+   /* several processes (launcher exported WORLD_SIZE > 1) and no communicator yet: bring NCCL up from the
+    * environment, or fail clearly -- never run as N independent single-rank solves */
+   if (comm != MPI_COMM_SELF && getenv("WORLD_SIZE") && atoi(getenv("WORLD_SIZE")) > 1 && hdk_comm_size() <= 1 &&
+       hdk_device_count() > 0)
+   {
+      int rc = hdk_comm_init_from_env();
+      if (rc) { free(h); return hdk_fail(rc); }
+   }
    MPI_Comm_rank(comm, &h->rank);
    MPI_Comm_size(comm, &h->nprocs);
    h->stats     = hd_stats_create();

@@ -107,7 +107,21 @@ static int ij_set(struct hypre_IJMatrix_struct *A, HYPRE_Int nrows, HYPRE_Int *n
    {
       int64_t i = (int64_t)(rows[r] - A->ilower);
       int     nc = ncols[r];
-      if (i < 0 || i >= A->nrows) { off += nc; continue; } /* off-rank rows are ignored */
+      if (i < 0 || i >= A->nrows)
+      {
+         /* hypre ignores SetValues to rows of other ranks, but stashes AddToValues contributions and
+          * ships them in Assemble (the FEM assembly pattern).  This container has no such exchange:
+          * an off-rank AddTo is an error, never a silently wrong operator */
+         if (add)
+         {
+            hd_err_set(HYPREDRV_ERROR_HYPRE_INTERNAL);
+            hd_err_msg("HYPRE_IJMatrixAddToValues: row %lld belongs to another rank; off-process contributions are not supported "
+                       "(assemble each row on its owner)", (long long)rows[r]);
+            return 1;
+         }
+         off += nc;
+         continue;
+      }
       for (int c = 0; c < nc; c++)
       {
          HYPRE_BigInt col = cols[off + c];

@@ -33,7 +33,14 @@ int MPI_Comm_size(MPI_Comm comm, int *size)
    return MPI_SUCCESS;
 }
 
-int MPI_Barrier(MPI_Comm comm) { (void)comm; hdk_sync(); return MPI_SUCCESS; }
+int MPI_Barrier(MPI_Comm comm)
+{
+   /* all ranks meet in a collective of the NCCL communicator when there is one */
+   int64_t sum = 0;
+   hdk_sync();
+   if (comm != MPI_COMM_SELF && hdk_comm_size() > 1) hdk_comm_sum_i64(1, &sum);
+   return MPI_SUCCESS;
+}
 
 int MPI_Abort(MPI_Comm comm, int errorcode)
 {

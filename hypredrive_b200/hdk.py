@@ -11,7 +11,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libHYPREDRV.so")
+LIB_PATH = os.environ.get("HDK_LIB") or os.path.join(_HERE, "lib", "libHYPREDRV.so")   # HDK_LIB: an experimental variant build
 _lib = None
 
 

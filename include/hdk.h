@@ -43,6 +43,10 @@ void       *hdk_stream(void);            /* cudaStream_t of the compute stream *
  * the host program (torch.distributed / any launcher) before hdk_comm_init. */
 int hdk_comm_unique_id(void *id128_h);
 int hdk_comm_init(int rank, int nranks, const void *id128_h);
+/* the same from the launcher's environment alone (RANK, WORLD_SIZE, MASTER_ADDR/PORT): rank 0 publishes
+ * the id through a file (HDK_NCCL_ID_FILE); used by HYPREDRV_Create when WORLD_SIZE > 1 and the host
+ * program has not called hdk_comm_init itself */
+int hdk_comm_init_from_env(void);
 /* halo exchange in use: 0 = single rank, 1 = NCCL send/recv on a communication stream,
  * 2 = peer-memory stores over NVLink (CUDA IPC arena; HDK_HALO_IPC=0 disables) */
 int hdk_comm_halo_mode(void);

@@ -44,8 +44,39 @@ def raw_metrics(rep, out):
         for r in rd[2:]:
             f.write(",".join('"%s"' % r[i] if "," in r[i] else r[i] for _, i in idx) + "\n")
 
+def setup_summary(path, out):
+    """Per-kernel totals of one AMG setup (ncu launch list with a few throughput metrics): time share,
+    launches, and the metrics of each kernel's longest launch."""
+    lines = [l for l in open(path) if not l.startswith("==")]
+    per = collections.defaultdict(lambda: collections.defaultdict(dict))   # name -> id -> metric -> value
+    for r in csv.DictReader(lines):
+        name = re.sub(r"\(.*", "", r["Kernel Name"]).replace("void ", "")
+        try:
+            v = float(r["Metric Value"].replace(",", ""))
+        except ValueError:
+            continue
+        if r["Metric Name"] == "gpu__time_duration.sum":
+            v *= {"ns": 1.0, "us": 1e3, "ms": 1e6, "s": 1e9}.get(r["Metric Unit"], 1.0)
+        per[name][r["ID"]][r["Metric Name"]] = v
+    tot = {k: sum(m.get("gpu__time_duration.sum", 0.0) for m in ids.values()) for k, ids in per.items()}
+    T = sum(tot.values())
+    cols = ["sm__throughput.avg.pct_of_peak_sustained_elapsed", "smsp__issue_active.avg.pct_of_peak_sustained_active",
+            "sm__warps_active.avg.pct_of_peak_sustained_active", "launch__registers_per_thread", "smsp__inst_executed.sum",
+            "dram__bytes_read.sum", "dram__bytes_write.sum"]
+    with open(out, "w") as f:
+        f.write("# ncu launch list of ONE AMG setup (7-pt 256^3, one GPU; cold-cache, serialised: compare shares)\n")
+        f.write(f"# total {T/1e6:.2f} ms over {sum(len(v) for v in per.values())} launches\n")
+        f.write("kernel,launches,total_ms,share_pct,longest_ms," + ",".join(c.split(".")[0] for c in cols) + "\n")
+        for k, v in sorted(tot.items(), key=lambda x: -x[1]):
+            big = max(per[k].values(), key=lambda m: m.get("gpu__time_duration.sum", 0.0))
+            f.write(f"{k},{len(per[k])},{v/1e6:.3f},{100*v/T:.2f},{big.get('gpu__time_duration.sum', 0)/1e6:.3f}," +
+                    ",".join(f"{big.get(c, float('nan')):.6g}" for c in cols) + "\n")
+
+
 if __name__ == "__main__":
     if sys.argv[1] == "launches":
         launch_shares(sys.argv[2], sys.argv[3])
+    elif sys.argv[1] == "setup":
+        setup_summary(sys.argv[2], sys.argv[3])
     else:
         raw_metrics(sys.argv[2], sys.argv[3])

@@ -1,9 +1,10 @@
-"""Host-side description of the row partition and ParCSR split (numpy).
+"""TEST SCAFFOLDING (not product code): a numpy restatement of the row partition and ParCSR split.
 
 The product performs these steps on the device (csrc/hdk_csr.cu: k_split_count / k_split_fill,
-csrc/hdk_comm.cu: build_halo_plan).  This module restates the same bookkeeping on the host so
-that launchers can compute slab ranges and so that the N > 1 logic can be exercised on CPU with
-torch.distributed's gloo backend (tests/test_multirank_gloo.py).  Partition contract: the
+csrc/hdk_comm.cu: build_halo_plan; the device code itself is exercised multi-rank by
+tests/test_gpu_multi.py, also on a 1-GPU box).  This mirror only lets the world_size-2 rendezvous
+and halo bookkeeping be exercised on CPU with torch.distributed's gloo backend
+(tests/test_multirank_gloo.py).  Partition contract: the
 reference's, include/HYPREDRV.h:836-839 -- contiguous inclusive row ranges in rank order.
 """
 from __future__ import annotations

@@ -81,9 +81,33 @@ def test_two_rank_solve_matches_oracle(gpu, kind, dims, rep, share):
     # the whole hierarchy replicated (fine level below replicate_rows)
     (2, "lap7", ("10", "9", "4"), "100000", "0")])
 def test_row_distributed_setup_matches_oracle(gpu, world, kind, dims, rep, ragged):
+    _row_distributed_case(world, kind, dims, rep, ragged, {})
+
+
+@pytest.mark.parametrize("knob", ["HDK_RAP_SINGLE", "HDK_HALO_EXPORT", "HDK_MAILBOX", "HDK_GRAPH_ROWS"])
+def test_fallback_paths_match_oracle(gpu, knob):
+    """Every default-on optimisation switched off in turn (count + fill Galerkin product, pack kernels
+    instead of folded halo exports, NCCL all-reduce instead of the mailbox, no CUDA graph): same bits."""
+    extra = {knob: "0", "HDK_SELL_MIN_ROWS": "0", "HDK_SELL_MIN_ROWS_DIST": "0"}
+    if gpu.device_count() < 2:
+        extra["MPCHECK_SHARED_IPC"] = "1"        # keep the peer-memory path on (two processes, one GPU)
+    _row_distributed_case(2, "lap7", ("16", "16", "10"), "40", "0", extra)
+
+
+def test_peer_memory_path_with_folded_exports(gpu):
+    """The default multi-rank solve path (peer-memory halo, exports folded into the producers, mailbox
+    reductions, all-gather of the tail's right-hand side) on sliced-ELL levels, also when the ranks
+    share one GPU."""
+    extra = {"HDK_SELL_MIN_ROWS": "0", "HDK_SELL_MIN_ROWS_DIST": "0", "MPCHECK_SHARED_IPC": "1"}
+    _row_distributed_case(2, "lap27", ("8", "8", "6"), "30", "0", extra)
+    _row_distributed_case(3, "lap7", ("16", "14", "7"), "60", "1", extra)
+
+
+def _row_distributed_case(world, kind, dims, rep, ragged, extra):
     """Row-distributed setup on 2-4 ranks: per-level C/F splitting, P and A_c slabs (global columns)
     concatenate to the oracle's matrices bit for bit; solve parity as above."""
     env = {"HDK_REPLICATE_ROWS": rep, "MPCHECK_RAGGED": ragged, "MPCHECK_HIER": "1"}
+    env.update(extra)
     r = _run(world, [kind, *dims], env)
     assert r.returncode == 0, _digest(r)
     assert "ok=True" in r.stdout and "hier=bit-identical" in r.stdout, _digest(r)

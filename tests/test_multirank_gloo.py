@@ -12,12 +12,13 @@ import torch.multiprocessing as mp
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 
 def _worker(rank, world, port, kind, dims, out):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
     dist.init_process_group("gloo", rank=rank, world_size=world)
-    from hypredrive_b200 import partition as P
+    import partition_mirror as P
     from oracle import oracle as O
     A, _ = O.gen(kind, *dims, c=(1.0, 1.0, 0.5), diag_first=False)
     n = A.shape[0]
@@ -99,7 +100,7 @@ def test_two_rank_27pt_gloo():
 
 
 def test_slab_ranges_cover_everything():
-    from hypredrive_b200 import partition as P
+    import partition_mirror as P
     for n, w in ((10, 3), (7, 7), (1000, 8), (5, 2)):
         rng = [P.slab_range(n, r, w) for r in range(w)]
         assert rng[0][0] == 0 and rng[-1][1] == n - 1
