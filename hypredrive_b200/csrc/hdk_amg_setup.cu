@@ -974,7 +974,9 @@ int build_interp(const DevCSR &A, const DevCSR &S, int *cf, const int *f2c, int 
    int *slow;
    HDK_TRY(dalloc(&slow, (size_t)n + 1));
    // short rows (fine stencil levels): one thread per row beats one warp per row
-   const int force_slow = ((double)A.nnz / (n > 0 ? n : 1)) <= 10.0 ? 1 : 0;
+   static double slow_avg = -1.0; // HDK_INTERP_THREAD_AVG: rows up to this average length go one thread per row
+   if (slow_avg < 0.0) { const char *e = getenv("HDK_INTERP_THREAD_AVG"); slow_avg = e ? atof(e) : 10.0; }
+   const int force_slow = ((double)A.nnz / (n > 0 ? n : 1)) <= slow_avg ? 1 : 0;
    // this rank's share of the rows (all of them unless the multi-rank setup shares the work);
    // rows outside it keep slow = cnt = rowlen = 0, which every later kernel skips
    int lo, hi;
