@@ -685,7 +685,10 @@ __device__ __forceinline__ int wt_find(const int *keys, const int *idx, int cap,
    }
 }
 
-template <bool FILL>
+// STAGE (single-pass interpolation, max_elmts > 0): discovery AND weights in one launch; the truncated
+// row (at most max_elmts entries) goes to slot i * max_elmts of a staging buffer and cnt / rowlen / slow
+// are set like the counting pass does, so no row is traversed twice.
+template <bool FILL, bool STAGE = false>
 __global__ void __launch_bounds__(32 * IW_WARPS) k_interp_warp(const int *arp, const int *acol, const double *aval,
                                                                const int *srp, const int *scol, const int *cf,
                                                                const int *f2c, int n, int max_elmts, int *cnt, int *rowlen,
@@ -705,13 +708,13 @@ __global__ void __launch_bounds__(32 * IW_WARPS) k_interp_warp(const int *arp, c
    {
       if (lane == 0)
       {
-         if (!FILL) { cnt[i] = 1; rowlen[i] = 1; slow[i] = 0; }
-         else { pcol[prp[i]] = f2c[i]; pval[prp[i]] = 1.0; }
+         if (!FILL || STAGE) { cnt[i] = 1; rowlen[i] = 1; slow[i] = 0; }
+         if (FILL) { const int p1 = STAGE ? i * max_elmts : prp[i]; pcol[p1] = f2c[i]; pval[p1] = 1.0; }
       }
       return;
    }
-   if (ci == SF_PT) { if (!FILL && lane == 0) { cnt[i] = 0; rowlen[i] = 0; slow[i] = 0; } return; }
-   if (FILL && slow[i]) return;
+   if (ci == SF_PT) { if ((!FILL || STAGE) && lane == 0) { cnt[i] = 0; rowlen[i] = 0; slow[i] = 0; } return; }
+   if (FILL && !STAGE && slow[i]) return;
    if (!FILL && force_slow) { if (lane == 0) { slow[i] = 1; cnt[i] = 0; rowlen[i] = 0; } return; }
    int *keys = s_keys[wid], *idx = s_idx[wid], *lc = s_lc[wid];
    double *lv = s_lv[wid];
@@ -759,7 +762,7 @@ __global__ void __launch_bounds__(32 * IW_WARPS) k_interp_warp(const int *arp, c
       }
       __syncwarp();
    }
-   if (!FILL)
+   if (!FILL || STAGE)
    {
       if (lane == 0)
       {
@@ -767,7 +770,7 @@ __global__ void __launch_bounds__(32 * IW_WARPS) k_interp_warp(const int *arp, c
          cnt[i]    = overflow ? 0 : nC;
          rowlen[i] = overflow ? 0 : ((max_elmts > 0 && nC > max_elmts) ? max_elmts : nC);
       }
-      return;
+      if (!FILL || overflow) return; // (single pass: a row this table cannot hold goes to the one-thread path)
    }
    // ---- weights: sequential over the row of A (hypre's order), lanes over the inner look-ups.
    // The per-entry operands (column, value, table look-up, and for strong F neighbours the row
@@ -863,8 +866,19 @@ __global__ void __launch_bounds__(32 * IW_WARPS) k_interp_warp(const int *arp, c
       len = max_elmts;
       __syncwarp();
    }
-   const int p0 = prp[i];
+   const int p0 = STAGE ? i * max_elmts : prp[i];
    for (int k = lane; k < len; k += 32) { pcol[p0 + k] = f2c[lc[k]]; pval[p0 + k] = lv[k]; }
+}
+
+// staged rows (slot i * stride) -> CSR position; rows of the one-thread path are filled by k_interp_fill
+__global__ void k_interp_compact(const int *rowlen, const int *slow, const int *prp, const int *scol, const double *sval, int stride,
+                                 int row_lo, int row_hi, int *pcol, double *pval)
+{
+   int i = row_lo + blockIdx.x * blockDim.x + threadIdx.x;
+   if (i >= row_hi || slow[i]) return;
+   const int len = rowlen[i], p0 = prp[i];
+   const long long s0 = (long long)i * stride;
+   for (int k = 0; k < len; k++) { pcol[p0 + k] = scol[s0 + k]; pval[p0 + k] = sval[s0 + k]; }
 }
 
 __global__ void k_mask_cnt(const int *cnt, const int *slow, int n, int *out)
@@ -988,10 +1002,29 @@ int build_interp(const DevCSR &A, const DevCSR &S, int *cf, const int *f2c, int 
       HDK_CUDA(cudaMemsetAsync(cnt, 0, sizeof(int) * ((size_t)n + 1), g.stream));
       HDK_CUDA(cudaMemsetAsync(rowlen, 0, sizeof(int) * ((size_t)n + 1), g.stream));
    }
-   // pass 1a: |C-hat_i| by the warp kernel (shared-memory hash); rows it cannot hold are flagged
-   k_interp_warp<false><<<cdiv(hi - lo, IW_WARPS), 32 * IW_WARPS, 0, g.stream>>>(A.rowptr, A.col, A.val, S.rowptr, S.col, cf, f2c, hi,
-                                                                                max_elmts, cnt, rowlen, slow, nullptr, nullptr, nullptr, force_slow, lo);
-   HDK_LAUNCH_CHECK();
+   // Single-pass interpolation (rows of at most max_elmts entries, warp path): discovery and weights in
+   // ONE launch into a fixed-stride staging buffer, row lengths from the same launch; the counting pass
+   // below is only needed when rows are unbounded (no truncation) or go one thread per row.
+   static int interp_single = -1;
+   if (interp_single < 0) { const char *e = getenv("HDK_INTERP_SINGLE"); interp_single = (e && atoi(e) == 0) ? 0 : 1; }
+   const bool staged = interp_single == 1 && !force_slow && max_elmts > 0 && (long long)n * max_elmts < 2000000000LL;
+   int    *stg_col = nullptr;
+   double *stg_val = nullptr;
+   if (staged)
+   {
+      HDK_TRY(dalloc(&stg_col, (size_t)n * max_elmts + 8));
+      HDK_TRY(dalloc(&stg_val, (size_t)n * max_elmts + 8));
+      k_interp_warp<true, true><<<cdiv(hi - lo, IW_WARPS), 32 * IW_WARPS, 0, g.stream>>>(A.rowptr, A.col, A.val, S.rowptr, S.col, cf, f2c, hi,
+                                                                                         max_elmts, cnt, rowlen, slow, nullptr, stg_col, stg_val, 0, lo);
+      HDK_LAUNCH_CHECK();
+   }
+   else
+   {
+      // pass 1a: |C-hat_i| by the warp kernel (shared-memory hash); rows it cannot hold are flagged
+      k_interp_warp<false><<<cdiv(hi - lo, IW_WARPS), 32 * IW_WARPS, 0, g.stream>>>(A.rowptr, A.col, A.val, S.rowptr, S.col, cf, f2c, hi,
+                                                                                   max_elmts, cnt, rowlen, slow, nullptr, nullptr, nullptr, force_slow, lo);
+      HDK_LAUNCH_CHECK();
+   }
    // pass 1b: flagged rows, one thread per row, hash sets in global scratch (chunked)
    k_interp_cap<<<cdiv(n + 1, 256), 256, 0, g.stream>>>(S.rowptr, S.col, cf, n, cap, slow);
    HDK_LAUNCH_CHECK();
@@ -1029,9 +1062,18 @@ int build_interp(const DevCSR &A, const DevCSR &S, int *cf, const int *f2c, int 
    // pass 2: weights.  hash maps sized from the exact counts, candidate lists in scratch
    int64_t *loff;
    HDK_TRY(dalloc(&loff, (size_t)n + 1));
-   k_interp_warp<true><<<cdiv(hi - lo, IW_WARPS), 32 * IW_WARPS, 0, g.stream>>>(A.rowptr, A.col, A.val, S.rowptr, S.col, cf, f2c, hi,
-                                                                               max_elmts, cnt, rowlen, slow, prp, P.col, P.val, force_slow, lo);
-   HDK_LAUNCH_CHECK();
+   if (staged)
+   {
+      k_interp_compact<<<cdiv(hi - lo, 256), 256, 0, g.stream>>>(rowlen, slow, prp, stg_col, stg_val, max_elmts, lo, hi, P.col, P.val);
+      HDK_LAUNCH_CHECK();
+      dfree(stg_col); dfree(stg_val);
+   }
+   else
+   {
+      k_interp_warp<true><<<cdiv(hi - lo, IW_WARPS), 32 * IW_WARPS, 0, g.stream>>>(A.rowptr, A.col, A.val, S.rowptr, S.col, cf, f2c, hi,
+                                                                                  max_elmts, cnt, rowlen, slow, prp, P.col, P.val, force_slow, lo);
+      HDK_LAUNCH_CHECK();
+   }
    k_interp_cap2<<<cdiv(n + 1, 256), 256, 0, g.stream>>>(S.rowptr, cf, cnt, n, cap, slow);
    HDK_LAUNCH_CHECK();
    HDK_TRY(exclusive_scan_i64(cap, off, n + 1));

@@ -84,7 +84,7 @@ def test_row_distributed_setup_matches_oracle(gpu, world, kind, dims, rep, ragge
     _row_distributed_case(world, kind, dims, rep, ragged, {})
 
 
-@pytest.mark.parametrize("knob", ["HDK_RAP_SINGLE", "HDK_HALO_EXPORT", "HDK_MAILBOX", "HDK_GRAPH_ROWS"])
+@pytest.mark.parametrize("knob", ["HDK_RAP_SINGLE", "HDK_INTERP_SINGLE", "HDK_HALO_EXPORT", "HDK_MAILBOX", "HDK_GRAPH_ROWS"])
 def test_fallback_paths_match_oracle(gpu, knob):
     """Every default-on optimisation switched off in turn (count + fill Galerkin product, pack kernels
     instead of folded halo exports, NCCL all-reduce instead of the mailbox, no CUDA graph): same bits."""
