@@ -542,7 +542,11 @@ __device__ __forceinline__ void swap2(int *v, double *w, int i, int j)
 
 // hypre_qsort2abs without recursion: the partition of every sub-range is independent of the
 // order sub-ranges are visited in, so an explicit stack gives the identical arrangement.
-__device__ void qsort2abs_dev(int *v, double *w, int n)
+// `keep`: only positions [0, keep) of the result are used by the caller (interpolation truncation keeps
+// the max_elmts largest |w|).  A sub-range that starts at or beyond `keep` can never move an element
+// into [0, keep), so it is not sorted at all -- the leading positions end up exactly as the full
+// quicksort leaves them (ties included) at O(n + keep log keep) instead of O(n log n) swaps.
+__device__ void qsort2abs_dev(int *v, double *w, int n, int keep)
 {
    int stl[40], str[40], sp = 0;
    stl[0] = 0; str[0] = n - 1; sp = 1;
@@ -550,7 +554,7 @@ __device__ void qsort2abs_dev(int *v, double *w, int n)
    {
       sp--;
       int left = stl[sp], right = str[sp];
-      while (left < right)
+      while (left < right && left < keep)
       {
          swap2(v, w, left, (left + right) / 2);
          int last = left;
@@ -561,12 +565,12 @@ __device__ void qsort2abs_dev(int *v, double *w, int n)
          int l1 = left, r1 = last - 1, l2 = last + 1, r2 = right;
          if (r1 - l1 < r2 - l2)
          {
-            if (l2 < r2) { stl[sp] = l2; str[sp] = r2; sp++; }
+            if (l2 < r2 && l2 < keep) { stl[sp] = l2; str[sp] = r2; sp++; }
             left = l1; right = r1;
          }
          else
          {
-            if (l1 < r1) { stl[sp] = l1; str[sp] = r1; sp++; }
+            if (l1 < r1 && l1 < keep) { stl[sp] = l1; str[sp] = r1; sp++; }
             left = l2; right = r2;
          }
       }
@@ -652,7 +656,7 @@ __global__ void k_interp_fill(const int *arp, const int *acol, const double *ava
    {
       double row_sum = 0.0, scale = 0.0;
       for (int k = 0; k < nC; k++) row_sum = __dadd_rn(row_sum, lv[k]);
-      qsort2abs_dev(lc, lv, nC);
+      qsort2abs_dev(lc, lv, nC, max_elmts);
       for (int k = 0; k < max_elmts; k++) scale = __dadd_rn(scale, lv[k]);
       if (scale != 0.0 && scale != row_sum)
       {
@@ -809,6 +813,29 @@ __global__ void __launch_bounds__(32 * IW_WARPS) k_interp_warp(const int *arp, c
             const double sgn = __shfl_sync(FULL, p_sgn, t);
             const int    b1 = __shfl_sync(FULL, p_b1, t), e1 = __shfl_sync(FULL, p_e1, t);
             double       sum = 0.0;
+            if (e1 - b1 <= 32)
+            {
+               // the neighbour's row fits one chunk (the usual case): its entries, signs and table
+               // look-ups are fetched ONCE and serve both the ordered sum and the distribution
+               const int    j1 = b1 + lane;
+               const bool   v1 = j1 < e1;
+               const int    i2 = v1 ? acol[j1] : -1;
+               const double v  = v1 ? aval[j1] : 0.0;
+               const bool   neg = v1 && (sgn * v < 0);
+               const int    m2 = neg ? wt_find(keys, idx, IW_CAP, i2) : -1;
+               unsigned     rem = __ballot_sync(FULL, neg && (i2 == i || m2 >= 0));
+               while (rem) { int src = __ffs(rem) - 1; sum = __dadd_rn(sum, __shfl_sync(FULL, v, src)); rem &= rem - 1u; }
+               if (sum != 0.0)
+               {
+                  const double tt = __dmul_rn(__ddiv_rn(a, sum), v);
+                  if (neg && m2 >= 0) lv[m2] = __dadd_rn(lv[m2], tt);
+                  const unsigned dm = __ballot_sync(FULL, neg && i2 == i);
+                  if (dm) diagonal = __dadd_rn(diagonal, __shfl_sync(FULL, tt, __ffs(dm) - 1));
+               }
+               else diagonal = __dadd_rn(diagonal, a);
+               __syncwarp();
+               continue;
+            }
             for (int base = b1; base < e1; base += 32)
             {
                const int    j1 = base + lane;
@@ -855,7 +882,7 @@ __global__ void __launch_bounds__(32 * IW_WARPS) k_interp_warp(const int *arp, c
       {
          double row_sum = 0.0, scale = 0.0;
          for (int k = 0; k < nC; k++) row_sum = __dadd_rn(row_sum, lv[k]);
-         qsort2abs_dev(lc, lv, nC);
+         qsort2abs_dev(lc, lv, nC, max_elmts);
          for (int k = 0; k < max_elmts; k++) scale = __dadd_rn(scale, lv[k]);
          if (scale != 0.0 && scale != row_sum)
          {
@@ -927,7 +954,7 @@ __global__ void k_trunc_rows(const int *rp, int *col, double *val, int n, double
    {
       double row_sum = 0.0, scale = 0.0;
       for (int k = b; k < e; k++) row_sum = __dadd_rn(row_sum, val[k]);
-      qsort2abs_dev(col + b, val + b, len);
+      qsort2abs_dev(col + b, val + b, len, max_elmts);
       for (int k = 0; k < max_elmts; k++) scale = __dadd_rn(scale, val[b + k]);
       if (scale != 0.0 && scale != row_sum)
       {
