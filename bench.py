@@ -296,6 +296,31 @@ def reference_arm(args):
     return 0
 
 
+def bind_to_gpu_numa(local):
+    """N > 1: run this rank on the CPUs next to its GPU (NVML's ideal CPU set), so that the pinned host
+    buffers of the end-to-end leg are first-touched on the GPU's NUMA node and the 8 concurrent
+    H2D / D2H streams do not cross sockets.  Returns the number of CPUs bound to (0: left unchanged)."""
+    try:
+        import pynvml
+        import torch
+        pynvml.nvmlInit()
+        try:
+            h = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + str(torch.cuda.get_device_properties(local).uuid)).encode())
+        except Exception:
+            h = pynvml.nvmlDeviceGetHandleByIndex(local)
+        words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, words)
+        cpus = [64 * i + b for i, m in enumerate(mask) for b in range(64) if (int(m) >> b) & 1]
+        allowed = os.sched_getaffinity(0)
+        cpus = [c for c in cpus if c in allowed]
+        if cpus and len(cpus) < len(allowed):
+            os.sched_setaffinity(0, cpus)
+            return len(cpus)
+    except Exception:
+        pass
+    return 0
+
+
 def ours(args):
     import numpy as np
     from hypredrive_b200 import hdk, driver
@@ -305,10 +330,12 @@ def ours(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     dist = None
+    numa_cpus = 0
     if world > 1:
         import torch
         import torch.distributed as dist
         torch.cuda.set_device(local)
+        numa_cpus = bind_to_gpu_numa(local)
         dist.init_process_group(backend="nccl", device_id=torch.device("cuda", local))
     if hdk.device_count() <= 0:
         raise SystemExit("bench.py: no CUDA device visible and there is no CPU fallback "
@@ -494,7 +521,8 @@ def ours(args):
                                    f"{SOLVER_DESC[cfg['solver']]}",
                        "name": args.config,
                        "inputs_vs_L2": "operator and vectors exceed the 126 MB L2 (7-pt 256^3: 1.4 GB + 134 MB each); no flush needed",
-                       "assembly": "device (HYPREDRV_LinearSystemSetStencil)"},
+                       "assembly": "device (HYPREDRV_LinearSystemSetStencil)",
+                       "host_cpus_bound_to_gpu_numa_node": numa_cpus},
             "iterations": iters, "solve_s": per_step, "setup_s": setup_s, "setup_s_all": setups, "build_s": build_s,
             "wall_s_timed_region": wall, "levels": nlev, "level_rows_nnzA_nnzP": levels,
             "e2e": {"value": e2e_value, "unit": "DOF*iters/s", "h2d_bytes_per_step": 8 * n_glob,

@@ -584,7 +584,7 @@ void halo_plan_free(HaloPlan &H)
    H.col_map = nullptr; H.send_idx = nullptr; H.send_buf = nullptr; H.x_halo = nullptr;
    if (H.ipc.on)
    {
-      dfree(H.ipc.tickets); dfree(H.ipc.exp_rows); dfree(H.ipc.exp_ptr); dfree(H.ipc.exp_slot);
+      dfree(H.ipc.tickets); dfree(H.ipc.exp_dir); dfree(H.ipc.exp_ptr); dfree(H.ipc.exp_slot);
       if (ipc.on) ipc.pending.emplace_back((size_t)H.ipc.region_off, H.ipc.region_bytes);
       H.ipc = IpcHalo();
    }
@@ -610,7 +610,7 @@ IpcRecvArgs halo_recv_args(const hdk_csr_s &A, const double **xh)
 
 // inverse of the send list (row -> its positions in the concatenated send buffer) for exports folded
 // into the kernel that produces the vector; built once per plan on the host
-static int ipc_export_build(HaloPlan &H)
+static int ipc_export_build(HaloPlan &H, int A_rows /* rows of the vector that is exported */)
 {
    IpcHalo &I = H.ipc;
    if (!I.on || H.n_send <= 0) return HDK_OK;
@@ -635,12 +635,21 @@ static int ipc_export_build(HaloPlan &H)
       const int gap = rows[(size_t)k + 1] - rows[(size_t)k] - 1;
       if (gap > best) { best = gap; lo_end = rows[(size_t)k] + 1; hi_begin = rows[(size_t)k + 1]; }
    }
+   const int nloc = A_rows;
    if (rows[0] > best) { best = rows[0]; lo_end = 0; hi_begin = rows[0]; }
+   if (nloc - 1 - rows[(size_t)m - 1] > best) { best = nloc - 1 - rows[(size_t)m - 1]; lo_end = rows[(size_t)m - 1] + 1; hi_begin = nloc; }
    if (best <= 0) { lo_end = hi_begin = 0; }
-   HDK_TRY(dalloc(&I.exp_rows, (size_t)m + 1));
+   // direct table: rows [0, lo_end) then rows [hi_begin, n) -> index of the exported row or -1
+   std::vector<int> dir((size_t)lo_end + (size_t)(nloc - hi_begin) + 1, -1);
+   for (int k = 0; k < m; k++)
+   {
+      const int r = rows[(size_t)k];
+      dir[(size_t)(r < lo_end ? r : lo_end + (r - hi_begin))] = k;
+   }
+   HDK_TRY(dalloc(&I.exp_dir, dir.size()));
    HDK_TRY(dalloc(&I.exp_ptr, (size_t)m + 2));
    HDK_TRY(dalloc(&I.exp_slot, (size_t)H.n_send + 1));
-   HDK_CUDA(cudaMemcpyAsync(I.exp_rows, rows.data(), sizeof(int) * (size_t)m, cudaMemcpyHostToDevice, g.stream));
+   HDK_CUDA(cudaMemcpyAsync(I.exp_dir, dir.data(), sizeof(int) * dir.size(), cudaMemcpyHostToDevice, g.stream));
    HDK_CUDA(cudaMemcpyAsync(I.exp_ptr, ptr.data(), sizeof(int) * ((size_t)m + 1), cudaMemcpyHostToDevice, g.stream));
    HDK_CUDA(cudaMemcpyAsync(I.exp_slot, slot.data(), sizeof(int) * (size_t)H.n_send, cudaMemcpyHostToDevice, g.stream));
    HDK_CUDA(cudaStreamSynchronize(g.stream)); // the host vectors go out of scope
@@ -665,7 +674,7 @@ bool halo_export_begin(const hdk_csr_s &A, HaloExport *e)
    I.seq++;
    I.preposted = true;
    if (H.n_send <= 0) return true;                         // receives only: nothing to store, the sequence still advances
-   e->rows = I.exp_rows; e->ptr = I.exp_ptr; e->slot = I.exp_slot; e->m = I.exp_m;
+   e->dir = I.exp_dir; e->ptr = I.exp_ptr; e->slot = I.exp_slot; e->m = I.exp_m;
    e->lo_end = I.exp_lo_end; e->hi_begin = I.exp_hi_begin;
    e->npeer = (int)H.send_rank.size();
    for (int p = 0; p < e->npeer; p++)
@@ -749,7 +758,7 @@ int build_halo_plan(hdk_csr_s &A, int64_t *uniq, int n_halo)
       HDK_LAUNCH_CHECK();
    }
    dfree(req);
-   return ipc_export_build(H);
+   return ipc_export_build(H, (int)(A.col_end - A.col_start + 1)); // the exported vector lives in my share of the column space
 }
 
 __global__ void k_pack(const double *x, const int *idx, int n, double *buf)

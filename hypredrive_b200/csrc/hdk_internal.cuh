@@ -221,11 +221,12 @@ struct IpcRecvArgs
 // Halo export folded into the PRODUCER of a vector: the kernel that writes x stores the rows its
 // neighbours need straight into their halo buffers (peer stores over NVLink) and its last CTA raises
 // the sequence flags, so the consumer's exchange costs no kernel of its own and is complete long
-// before the consumer reaches a boundary row.  rows / ptr / slot: the exported rows (sorted, unique)
-// and, per row, its positions in the concatenated send list (a row may go to several neighbours).
+// before the consumer reaches a boundary row.  dir: direct table over the rows outside the export-free
+// middle range -> index of the exported row (or -1); ptr / slot: per exported row, its positions in the
+// concatenated send list (a row may go to several neighbours).
 struct HaloExport
 {
-   const int          *rows = nullptr, *ptr = nullptr, *slot = nullptr;
+   const int          *dir = nullptr, *ptr = nullptr, *slot = nullptr;
    int                 m = 0;              // number of exported rows (0: nothing to export)
    int                 lo_end = 0, hi_begin = 0; // rows in [lo_end, hi_begin) are never exported (quick reject)
    double             *dst[IPC_MAXP];
@@ -261,7 +262,7 @@ struct IpcHalo
    unsigned long long  seq = 0;
    unsigned           *tickets = nullptr; // three device counters: pack, consumer ack, export
    // inverse of the send list for exports folded into the producer kernel
-   int                *exp_rows = nullptr, *exp_ptr = nullptr, *exp_slot = nullptr;
+   int                *exp_dir = nullptr, *exp_ptr = nullptr, *exp_slot = nullptr;
    int                 exp_m = 0, exp_lo_end = 0, exp_hi_begin = 0;
    bool                preposted = false;  // the current sequence was filled by the producer: no pack kernel
 };
@@ -306,10 +307,10 @@ __device__ __forceinline__ void wait_seq_sys(const unsigned long long *p, unsign
 __device__ __forceinline__ void export_row(const HaloExport &e, int r, double v)
 {
    if (e.seq == 0 || (r >= e.lo_end && r < e.hi_begin)) return;
-   int lo = 0, hi = e.m;
-   while (lo < hi) { int mid = (lo + hi) >> 1; if (e.rows[mid] < r) lo = mid + 1; else hi = mid; }
-   if (lo >= e.m || e.rows[lo] != r) return;
-   for (int k = e.ptr[lo]; k < e.ptr[lo + 1]; k++)
+   // direct table over the two row ranges outside [lo_end, hi_begin): index into rows / ptr, or -1
+   const int i = e.dir[r < e.lo_end ? r : e.lo_end + (r - e.hi_begin)];
+   if (i < 0) return;
+   for (int k = e.ptr[i]; k < e.ptr[i + 1]; k++)
    {
       const int s = e.slot[k];
       int       p = 0;
@@ -318,14 +319,16 @@ __device__ __forceinline__ void export_row(const HaloExport &e, int r, double v)
       e.dst[p][s - e.off[p]] = v;
    }
 }
-// end of the producer kernel, executed by every CTA: the last one publishes the sequence number
+// end of the producer kernel, executed by every CTA: the last one publishes the sequence number.
+// One system-scope fence per CTA (thread 0, after the CTA barrier that orders the other threads'
+// peer stores before it) -- a fence per thread costs ~15 us at the tail of a 300 000-thread kernel.
 __device__ __forceinline__ void export_finish(const HaloExport &e)
 {
    if (e.seq == 0) return;
-   __threadfence_system();
    __syncthreads();
    if (threadIdx.x == 0)
    {
+      __threadfence_system();
       unsigned t = atomicInc(e.ticket, gridDim.x - 1);
       if (t == gridDim.x - 1)
       {
