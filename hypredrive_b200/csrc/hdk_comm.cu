@@ -320,10 +320,10 @@ __global__ void k_ipc_gather_send(const double *mine, int64_t off, int64_t cnt, 
       const double v = mine[off + i];
       for (int p = 0; p < a.R; p++) if (p != a.me) a.peer_buf[p][off + i] = v;
    }
-   __threadfence_system();
    __syncthreads();
    if (threadIdx.x == 0)
    {
+      __threadfence_system();
       unsigned t = atomicInc(a.ticket, gridDim.x - 1);
       if (t == gridDim.x - 1)
       {
@@ -506,10 +506,10 @@ __global__ void k_pack_ipc(const double *x, const int *idx, int n, IpcSendArgs a
       while (p + 1 < a.npeer && i >= a.off[p + 1]) p++;
       a.dst[p][i - a.off[p]] = x[idx[i]];
    }
-   __threadfence_system();
-   __syncthreads();
+   __syncthreads(); // then ONE system fence per CTA (thread 0) orders all its peer stores before the flag
    if (threadIdx.x == 0)
    {
+      __threadfence_system();
       unsigned t = atomicInc(a.ticket, gridDim.x - 1);
       if (t == gridDim.x - 1)
       {

@@ -315,9 +315,17 @@ __device__ __forceinline__ void export_row(const HaloExport &e, int r, double v)
       const int s = e.slot[k];
       int       p = 0;
       while (p + 1 < e.npeer && s >= e.off[p + 1]) p++;
-      if (e.seq > 2) wait_seq_sys(e.ack + p, e.seq - 2, e.tmo, e.err); // the neighbour has read this half
       e.dst[p][s - e.off[p]] = v;
    }
+}
+// start of the producer kernel, executed by every CTA: the neighbours must have read the buffer half
+// this sequence overwrites (their acknowledgement of sequence - 2); one acquire per CTA, not per row
+__device__ __forceinline__ void export_begin_cta(const HaloExport &e)
+{
+   if (e.seq <= 2) return;
+   if (threadIdx.x == 0)
+      for (int p = 0; p < e.npeer; p++) wait_seq_sys(e.ack + p, e.seq - 2, e.tmo, e.err);
+   __syncthreads();
 }
 // end of the producer kernel, executed by every CTA: the last one publishes the sequence number.
 // One system-scope fence per CTA (thread 0, after the CTA barrier that orders the other threads'

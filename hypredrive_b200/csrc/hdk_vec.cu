@@ -44,6 +44,7 @@ __global__ void __launch_bounds__(VT) k_scale(double a, double *x, int64_t n)
 __global__ void __launch_bounds__(VT) k_scaled_div(double *__restrict__ u, const double *__restrict__ f,
                                                    const double *__restrict__ d, double w, int64_t n, const HaloExport ex)
 {
+   export_begin_cta(ex);
    for (int64_t i = blockIdx.x * (int64_t)VT + threadIdx.x; i < n; i += (int64_t)gridDim.x * VT)
    {
       double dd = d[i];
@@ -129,6 +130,7 @@ __global__ void __launch_bounds__(VT) k_pcg_xr(double *x, double *r, const doubl
    const double      alpha = scal[S_ALPHA];
    double            acc   = 0.0;
    const int64_t     n2 = n >> 1, stride = (int64_t)gridDim.x * VT;
+   if (PREFILL) export_begin_cta(ex);
    double2          *x2 = reinterpret_cast<double2 *>(x), *r2 = reinterpret_cast<double2 *>(r);
    const double2    *p2 = reinterpret_cast<const double2 *>(p), *s2 = reinterpret_cast<const double2 *>(s);
    double2          *z2 = reinterpret_cast<double2 *>(z0);
@@ -202,6 +204,7 @@ __global__ void __launch_bounds__(VT) k_pcg_p(double *__restrict__ p, const doub
 {
    const double   beta = scal[S_BETA];
    const int64_t  n2 = n >> 1, stride = (int64_t)gridDim.x * VT;
+   export_begin_cta(ex);
    double2       *p2 = reinterpret_cast<double2 *>(p);
    const double2 *z2 = reinterpret_cast<const double2 *>(z);
    int64_t        i = blockIdx.x * (int64_t)VT + threadIdx.x;

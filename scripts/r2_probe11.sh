@@ -1,0 +1,24 @@
+#!/bin/bash
+# probe 11 (2 GPUs): quick multi-rank correctness + bench with / without folded exports
+cd /root/repo
+run() { w=$1; shift; tag=$1; shift
+  env "$@" timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node=$w --master-addr 127.0.0.1 --master-port 29611 tests/mp_gpu_check.py $ARGS > gpurun_out/r2_p11_$tag.log 2>&1
+  echo "rc=$?" >> gpurun_out/r2_p11_$tag.log; grep -h "MPCHECK\|rc=" gpurun_out/r2_p11_$tag.log | cut -c1-260; }
+ARGS="lap7 16 16 10";  run 2 sell HDK_REPLICATE_ROWS=40 HDK_SELL_MIN_ROWS=0 HDK_SELL_MIN_ROWS_DIST=0
+ARGS="lap27 8 8 6";    run 2 sell27 HDK_REPLICATE_ROWS=30 HDK_SELL_MIN_ROWS=0 HDK_SELL_MIN_ROWS_DIST=0 MPCHECK_RAGGED=1
+ARGS="convdif 16 8 6"; run 2 sellcd HDK_REPLICATE_ROWS=40 HDK_SELL_MIN_ROWS=0 HDK_SELL_MIN_ROWS_DIST=0 MPCHECK_RAGGED=1
+ARGS="lap7 40 36 20";  run 2 big HDK_REPLICATE_ROWS=2000
+for v in default noexport; do
+  E=""; [ $v = noexport ] && E="HDK_HALO_EXPORT=0"
+  env $E timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29711 bench.py --gpus 2 --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/r2_p11_bench2_$v.json 2> gpurun_out/r2_p11_bench2_$v.err
+done
+python - <<'P'
+import json
+for f in ('r2_p11_bench2_default','r2_p11_bench2_noexport'):
+    try:
+        d=json.loads(open('gpurun_out/%s.json'%f).read().strip().splitlines()[-1])
+    except Exception as e:
+        print(f,'ERR',e); continue
+    print(f, 'value %.3e ms %.2f iters %d setup %.3f'%(d['value'],d['ms_per_step'],d['iterations'],d['setup_s']), 'e2e %.3e'%d['e2e']['value'])
+    print('   ', {k:round(v['ms'],3) for k,v in d['kernels'].items()})
+P
