@@ -315,6 +315,7 @@ __device__ __forceinline__ void export_row(const HaloExport &e, int r, double v)
       const int s = e.slot[k];
       int       p = 0;
       while (p + 1 < e.npeer && s >= e.off[p + 1]) p++;
+      if (e.seq > 2) wait_seq_sys(e.ack + p, e.seq - 2, e.tmo, e.err); // the neighbour has read this half
       e.dst[p][s - e.off[p]] = v;
    }
 }

@@ -461,16 +461,7 @@ __device__ __forceinline__ void sell_body(const SpmvDev &a)
    __shared__ double s_dot[DOT ? SELL_T : 1];
    if (DOT) s_dot[threadIdx.x] = 0.0;
    bool      halo_ready = false;
-   if (OFFD) export_begin_cta(a.exp);
-   // multi-rank: even warps walk the first half of the slices upwards, odd warps the second half
-   // downwards, so the boundary slices of BOTH neighbours (first and last rows of a slab: halo waits,
-   // off-rank entries, exports) are in the first wave and their extra latency hides behind the bulk
-   // instead of forming the kernel's tail.  (The grid has an even number of warps.)
-   const int  wid  = blockIdx.x * wpb + (threadIdx.x >> 5);
-   const bool back = OFFD && (wid & 1);
-   for (int s = !OFFD ? wid : (back ? a.nslice - 1 - (wid >> 1) : (wid >> 1));
-        !OFFD ? (s < a.nslice) : (back ? (s >= ((a.nslice + 1) >> 1)) : (s < ((a.nslice + 1) >> 1)));
-        s += !OFFD ? (int)(gridDim.x * wpb) : (back ? -(int)(gridDim.x * wpb / 2) : (int)(gridDim.x * wpb / 2)))
+   for (int s = blockIdx.x * wpb + (threadIdx.x >> 5); s < a.nslice; s += gridDim.x * wpb)
    {
       const int  meta  = __ldg(a.sl_meta + (size_t)s * 32 + lane);
       const int  len   = meta >> 6;
@@ -481,7 +472,7 @@ __device__ __forceinline__ void sell_body(const SpmvDev &a)
       o.b = o.d = o.xo = o.yo = o.dv = 0.0;
       // (which operands are fetched before and which after the streaming loop is chosen by the
       // register count ptxas ends up with: 32 = 8 CTAs per SM, 33-40 = 6, 41-48 = 5)
-      constexpr bool LATE = DOT || OFFD; // fused-dot and multi-rank variants: smoother operands after the loop as well
+      constexpr bool LATE = DOT; // fused-dot variants: smoother operands after the loop as well
       if (valid)
       {
          if (SUB) o.b = a.b[r];
@@ -519,19 +510,16 @@ __device__ __forceinline__ void sell_body(const SpmvDev &a)
          c0 = n0; c1 = n1; c2 = n2; c3 = n3;
          v0 = w0; v1 = w1; v2 = w2; v3 = w3;
       }
-      if (OFFD && !halo_ready && __ballot_sync(0xffffffffu, (meta & SELL_OFFD_BIT) != 0))
-      {
-         // first slice of this warp with off-rank entries: the neighbours store the halo values into xh
-         // over NVLink and then raise their sequence flags -- ONE lane waits for them (system-scope
-         // acquire), the warp barrier orders the other lanes' reads behind it
-         if (lane == 0)
-            for (int p = 0; p < a.ipc.nflag; p++) wait_seq_sys(a.ipc.flag + p, a.ipc.seq, a.ipc.tmo, a.ipc.err);
-         __syncwarp();
-         halo_ready = true;
-      }
       if (OFFD && (meta & SELL_OFFD_BIT))
       {
-         // row with off-rank entries: continue the row in stored order with the halo values
+         // row with off-rank entries: the neighbours store the halo values into xh over NVLink and then
+         // raise their sequence flags -- wait for them here (only the first flagged row of a lane really
+         // waits), then continue the row in stored order
+         if (!halo_ready)
+         {
+            for (int p = 0; p < a.ipc.nflag; p++) wait_seq_sys(a.ipc.flag + p, a.ipc.seq, a.ipc.tmo, a.ipc.err);
+            halo_ready = true;
+         }
          for (int k = __ldg(a.orp + r), e = __ldg(a.orp + r + 1); k < e; ++k)
          {
             const double p0 = __dmul_rn(__ldg(a.oval + k), __ldcg(a.xh + __ldg(a.ocol + k)));
@@ -576,8 +564,14 @@ __device__ __forceinline__ void sell_body(const SpmvDev &a)
 // Kernel entry point.  The kernel lives on memory-level parallelism across warps, so occupancy
 // matters: 32 registers (8 CTAs per SM) for the plain variants, 40-48 with a fused dot, 48-64 with
 // the fused off-diagonal block.
+#ifdef HDK_OFFD_LB8
+// (experimental variant build: the plain multi-rank variants forced to 32 registers = 8 CTAs per SM)
+template <int MODE, bool DOT, bool OFFD>
+__global__ void __launch_bounds__(SELL_T, (OFFD && !DOT) ? 8 : 1) k_spmv_sell(SpmvDev a) { sell_body<MODE, DOT, OFFD>(a); }
+#else
 template <int MODE, bool DOT, bool OFFD>
 __global__ void __launch_bounds__(SELL_T) k_spmv_sell(SpmvDev a) { sell_body<MODE, DOT, OFFD>(a); }
+#endif
 
 // slice metadata: lanes ranked by decreasing row length (ties by row), slice width = longest row
 __global__ void k_sell_meta(const int *rowptr, int nrows, int nslice, int *meta, int *width, int *max_slice_nnz,
