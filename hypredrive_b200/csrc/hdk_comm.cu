@@ -157,6 +157,8 @@ static int ipc_setup()
       int khz = 0;
       cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, g.device);
       ipc.tmo = secs > 0.0 ? (long long)(secs * 1000.0 * (double)(khz > 0 ? khz : 1900000)) : 0;
+      if (ok && (wait_globals_set(ipc.tmo, ipc.err_d) != cudaSuccess || wait_globals_spmv(ipc.tmo, ipc.err_d) ||
+                 wait_globals_csr(ipc.tmo, ipc.err_d) || wait_globals_vec(ipc.tmo, ipc.err_d))) ok = 0;
    }
    if (ok && cudaIpcGetMemHandle(&mine, ipc.base) != cudaSuccess) { ok = 0; cudaGetLastError(); }
    // exchange the handles (and whether every rank got this far)

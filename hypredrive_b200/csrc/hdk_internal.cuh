@@ -283,9 +283,15 @@ __device__ __forceinline__ void st_release_sys_u64(unsigned long long *p, unsign
 // error flag in device memory and carries on with whatever the buffer holds -- the CUDA context stays
 // usable, the host reports HDK_ERR_COMM at the end of the operation (comm_check_error) and later
 // waits return at once.  No trap: a trap would poison the context of this rank and hang its peers.
-static __device__ __noinline__ void wait_seq_slow(const unsigned long long *p, unsigned long long want, long long tmo, int *err)
+// Budget and flag live in per-translation-unit device globals (set by wait_globals_set at communicator
+// creation), not in kernel arguments: two more arguments on the out-of-line wait cost the sliced-ELL
+// kernel 8 registers = 2 CTAs per SM.
+static __device__ long long d_wait_tmo = 0;
+static __device__ int      *d_wait_err = nullptr;
+static __device__ __noinline__ void wait_seq_slow(const unsigned long long *p, unsigned long long want)
 {
-   const long long t0 = clock64();
+   const long long t0 = clock64(), tmo = d_wait_tmo;
+   int            *err = d_wait_err;
    unsigned        spins = 0;
    while (ld_acquire_sys_u64(p) < want)
    {
@@ -298,10 +304,17 @@ static __device__ __noinline__ void wait_seq_slow(const unsigned long long *p, u
       }
    }
 }
-__device__ __forceinline__ void wait_seq_sys(const unsigned long long *p, unsigned long long want, long long tmo, int *err)
+__device__ __forceinline__ void wait_seq_sys(const unsigned long long *p, unsigned long long want, long long = 0, int * = nullptr)
 {
    if (ld_acquire_sys_u64(p) >= want) return;
-   wait_seq_slow(p, want, tmo, err); // out of line: keeps the waiting kernels' register count down
+   wait_seq_slow(p, want); // out of line: keeps the waiting kernels' register count down
+}
+// one call per translation unit that contains waiting kernels (each has its own copy of the globals)
+static inline cudaError_t wait_globals_set(long long tmo, int *err)
+{
+   cudaError_t e = cudaMemcpyToSymbol(d_wait_tmo, &tmo, sizeof(tmo));
+   if (e == cudaSuccess) e = cudaMemcpyToSymbol(d_wait_err, &err, sizeof(err));
+   return e;
 }
 // producer side of a folded halo exchange: row r of the vector just got value v
 __device__ __forceinline__ void export_row(const HaloExport &e, int r, double v)
@@ -417,6 +430,9 @@ int halo_exchange_end(const hdk_csr_s &A);
 bool halo_export_begin(const hdk_csr_s &A, HaloExport *e);
 void halo_export_cancel(const hdk_csr_s &A); // the exported vector will not be consumed after all
 int comm_check_error(); // HDK_ERR_COMM when a peer-memory wait ran out of its budget since the last call
+int wait_globals_spmv(long long tmo, int *err); // per-translation-unit setters of the wait budget / error flag
+int wait_globals_csr(long long tmo, int *err);
+int wait_globals_vec(long long tmo, int *err);
 
 // ---------------------------------------------------------------------------------------
 // device reduction helper: block sum -> partials -> last block finishes (deterministic)

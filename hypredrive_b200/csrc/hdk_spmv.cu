@@ -41,6 +41,7 @@ struct Tune
    double sell_sort     = 1;        // HDK_SELL_SORT        sort the columns of coarse operators in the slices
    double amg_keep_debug = 0;       // HDK_AMG_KEEP_DEBUG   keep S and the PMIS measures of every level (introspection)
    double replicate_rows = 262144;  // HDK_REPLICATE_ROWS   N > 1: levels with at most this many global rows form the replicated tail
+   double export_max_rows = 2000000; // HDK_EXPORT_MAX_ROWS  N > 1: operators with more rows pack their halo instead of folding the export
    double graph_rows    = 150000;   // HDK_GRAPH_ROWS       V-cycle levels with at most this many rows are replayed from a CUDA graph (0: off)
    bool   env_read      = false;
 };
@@ -52,6 +53,7 @@ static const struct { const char *key, *env; double Tune::*field; } tune_keys[] 
    {"amg_keep_debug", "HDK_AMG_KEEP_DEBUG", &Tune::amg_keep_debug},
    {"replicate_rows", "HDK_REPLICATE_ROWS", &Tune::replicate_rows},
    {"graph_rows", "HDK_GRAPH_ROWS", &Tune::graph_rows},
+   {"export_max_rows", "HDK_EXPORT_MAX_ROWS", &Tune::export_max_rows},
    {"sell_min_avg", "HDK_SELL_MIN_AVG", &Tune::sell_min_avg},  {"sell_sort", "HDK_SELL_SORT", &Tune::sell_sort}};
 static Tune &tunables()
 {
@@ -443,7 +445,8 @@ __device__ __forceinline__ double ld_x(const double *p, uint64_t pol)
 #define LDX(p) __ldg(p)
 #endif
 
-template <int MODE, bool DOT, bool OFFD>
+// EXP: the halo export of the next product is folded into this kernel (multi-rank variants only)
+template <int MODE, bool DOT, bool OFFD, bool EXP>
 __device__ __forceinline__ void sell_body(const SpmvDev &a)
 {
 #ifdef HDK_XHINT
@@ -534,11 +537,11 @@ __device__ __forceinline__ void sell_body(const SpmvDev &a)
          // y += A x: y is read only now (live across the loop it costs 10 registers = 3 CTAs per SM),
          // so the sum is y + (a_0 x_0 + a_1 x_1 + ...) -- rounding-level difference to the CSR-order sum
          if (MODE == SPMV_ADD) acc = __dadd_rn(a.y[r], acc);
-         double yn = store_out<MODE, OFFD>(a, r, row_epilogue<MODE>(a, o, acc), o.d, o.xo);
+         double yn = store_out<MODE, EXP>(a, r, row_epilogue<MODE>(a, o, acc), o.d, o.xo);
          if (DOT) s_dot[threadIdx.x] += o.dv * yn;
       }
    }
-   if (OFFD) export_finish(a.exp);
+   if (EXP) export_finish(a.exp);
    if (OFFD && a.ipc.seq)
    {
       // all reads of xh by this CTA are done; the last CTA tells the senders (buffer reuse at seq + 2)
@@ -564,14 +567,8 @@ __device__ __forceinline__ void sell_body(const SpmvDev &a)
 // Kernel entry point.  The kernel lives on memory-level parallelism across warps, so occupancy
 // matters: 32 registers (8 CTAs per SM) for the plain variants, 40-48 with a fused dot, 48-64 with
 // the fused off-diagonal block.
-#ifdef HDK_OFFD_LB8
-// (experimental variant build: the plain multi-rank variants forced to 32 registers = 8 CTAs per SM)
-template <int MODE, bool DOT, bool OFFD>
-__global__ void __launch_bounds__(SELL_T, (OFFD && !DOT) ? 8 : 1) k_spmv_sell(SpmvDev a) { sell_body<MODE, DOT, OFFD>(a); }
-#else
-template <int MODE, bool DOT, bool OFFD>
-__global__ void __launch_bounds__(SELL_T) k_spmv_sell(SpmvDev a) { sell_body<MODE, DOT, OFFD>(a); }
-#endif
+template <int MODE, bool DOT, bool OFFD, bool EXP>
+__global__ void __launch_bounds__(SELL_T) k_spmv_sell(SpmvDev a) { sell_body<MODE, DOT, OFFD, EXP>(a); }
 
 // slice metadata: lanes ranked by decreasing row length (ties by row), slice width = longest row
 __global__ void k_sell_meta(const int *rowptr, int nrows, int nslice, int *meta, int *width, int *max_slice_nnz,
@@ -642,25 +639,26 @@ __global__ void k_sell_fill(const int *rowptr, const int *col, const double *val
    }
 }
 
-template <int MODE, bool DOT, bool OFFD>
+template <int MODE, bool DOT, bool OFFD, bool EXP>
 static int launch_sell_v(const DevCSR &A, const SpmvDev &d)
 {
    static int occ = 0;
    if (!occ)
    {
-      HDK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_spmv_sell<MODE, DOT, OFFD>, SELL_T, 0));
+      HDK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_spmv_sell<MODE, DOT, OFFD, EXP>, SELL_T, 0));
       if (occ < 1) occ = 1;
    }
    int grid = cdiv(A.nslice, SELL_T / 32);
    int cap  = g.sm_count * occ;
    if (grid > cap) grid = cap;
-   k_spmv_sell<MODE, DOT, OFFD><<<grid, SELL_T, 0, g.stream>>>(d);
+   k_spmv_sell<MODE, DOT, OFFD, EXP><<<grid, SELL_T, 0, g.stream>>>(d);
    return HDK_OK;
 }
 template <int MODE, bool DOT>
 static int launch_sell(const DevCSR &A, const SpmvDev &d)
 {
-   return d.orp ? launch_sell_v<MODE, DOT, true>(A, d) : launch_sell_v<MODE, DOT, false>(A, d);
+   if (!d.orp) return launch_sell_v<MODE, DOT, false, false>(A, d);
+   return d.exp.seq ? launch_sell_v<MODE, DOT, true, true>(A, d) : launch_sell_v<MODE, DOT, true, false>(A, d);
 }
 
 // one warp per row; lanes stride the row with scalar loads (rows here are long, so each warp
@@ -783,7 +781,15 @@ int spmv_launch(const DevCSR &A, int mode, const SpmvArgs &s, const OffdFuse *of
    }
    d.exp = HaloExport();
    d.exp_y2 = s.export_y2 ? 1 : 0;
-   if (s.export_to && of) halo_export_begin(*s.export_to, &d.exp); // only the fused multi-rank kernel carries the export code
+   // Folding the export into this kernel saves the consumer's pack kernel (~8 us) but the exporting
+   // variants of SET / RESIDUAL / ADD / SET_DIV need 40 registers instead of 32 (6 instead of 8 CTAs per
+   // SM, ~+25 us on a 16 M-row operator): fold on the small levels, pack on the big ones.  The Jacobi-type
+   // variants are at 40 registers either way and always fold.  (Tunable export_max_rows.)
+   if (s.export_to && of)
+   {
+      const bool jac = (mode == SPMV_JACOBI || mode == SPMV_JACOBI_R || mode == SPMV_JACOBI2);
+      if (jac || (double)A.nrows <= tunables().export_max_rows) halo_export_begin(*s.export_to, &d.exp);
+   }
    bool dot = (s.fin != FIN_NONE && s.dotv != nullptr);
    switch (mode)
    {
@@ -958,6 +964,12 @@ void csr_free(DevCSR &A)
    dfree(A.blk_row);
    sell_free(A);
    A = DevCSR();
+}
+
+// wait budget / error flag of this translation unit's copy of the in-kernel wait globals
+int wait_globals_spmv(long long tmo, int *err)
+{
+   return wait_globals_set(tmo, err) == cudaSuccess ? HDK_OK : set_error(HDK_ERR_CUDA, "cannot set the wait budget");
 }
 
 } // namespace hdk

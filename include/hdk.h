@@ -205,7 +205,8 @@ int hdk_time_kernel(const hdk_csr *A, hdk_amg *M, int kernel, int reps, double *
 int64_t hdk_launch_count_reset(void);
 /* kernel-selection tunables for matrices analysed after the call (same names as the HDK_*
  * environment variables, lower case without the prefix): spmv_rows_mult, spmv_tgt_max, spmv_lpr,
- * sell_min_rows, sell_min_rows_dist, sell_min_avg, sell_sort, graph_rows (V-cycle levels with at most
+ * sell_min_rows, sell_min_rows_dist, sell_min_avg, sell_sort, export_max_rows (N > 1: operators with more
+ * rows pack their halo instead of folding the export into the producer), graph_rows (V-cycle levels with at most
  * this many rows are replayed from a CUDA graph; 0 = off), replicate_rows (N > 1: levels with
  * at most this many global rows are replicated on every rank), amg_keep_debug (keep the strength
  * pattern and PMIS measures of every level for hdk_amg_get_matrix(...,'S') / get_measure).

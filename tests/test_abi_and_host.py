@@ -213,13 +213,16 @@ def test_sliced_ell_kernel_register_budget():
         pytest.skip("cuobjdump not available")
     lib = os.path.join(ROOT, "hypredrive_b200", "lib", "libHYPREDRV.so")
     out = subprocess.run([cuobjdump, "--dump-resource-usage", lib], capture_output=True, text=True).stdout
-    found = re.findall(r"Function _ZN3hdk11k_spmv_sellILi(\d)ELb([01])ELb([01])EEEvNS_7SpmvDevE:\s*\n\s*REG:(\d+) STACK:(\d+)", out)
-    assert len(found) >= 36, len(found)               # 9 epilogue modes x fused dot x fused off-diagonal block
-    for mode, dot, offd, reg, stack in found:
-        # mode 7 (two-stage GS first stage) writes two vectors per row: 40 registers also when plain
-        limit = 32 if (dot == "0" and offd == "0" and mode != "7") else 40
-        assert int(reg) <= limit, (mode, dot, offd, reg)
-        assert int(stack) <= 8, (mode, dot, offd, stack)
+    found = re.findall(r"Function _ZN3hdk11k_spmv_sellILi(\d)ELb([01])ELb([01])ELb([01])EEEvNS_7SpmvDevE:\s*\n\s*REG:(\d+) STACK:(\d+)", out)
+    assert len(found) >= 54, len(found)     # 9 epilogue modes x fused dot x {one rank, multi-rank, multi-rank + folded export}
+    for mode, dot, offd, exp, reg, stack in found:
+        # 32 registers = 8 CTAs per SM: every plain variant, and the multi-rank variants of the modes without
+        # smoother operands as long as they do not fold the export (that is why big levels pack instead);
+        # mode 7 (two-stage GS first stage) writes two vectors per row: 40 also when plain
+        lean = dot == "0" and exp == "0" and mode != "7" and (offd == "0" or mode in "013468")
+        limit = 32 if lean else 40
+        assert int(reg) <= limit, (mode, dot, offd, exp, reg)
+        assert int(stack) <= 8, (mode, dot, offd, exp, stack)
 
 
 def test_bench_reference_arm_contract():
