@@ -517,8 +517,14 @@ __global__ void k_pack_ipc(const double *x, const int *idx, int n, IpcSendArgs a
       {
          __threadfence_system();
          for (int p = 0; p < a.npeer; p++) st_release_sys_u64(a.flag[p], a.seq);
+         for (int p = 0; p < a.nrflag; p++) wait_seq_sys(a.rflag + p, a.seq); // my halo of this exchange has arrived
       }
    }
+}
+// a rank that only receives in an exchange: wait for its neighbours' flags (one lane per neighbour)
+__global__ void __launch_bounds__(32) k_wait_flags(const unsigned long long *flag, int nflag, unsigned long long seq)
+{
+   if ((int)threadIdx.x < nflag) wait_seq_sys(flag + threadIdx.x, seq);
 }
 
 // one region per plan in my arena: [8 data flags | 8 ack flags | x_halo half 0 | x_halo half 1]
@@ -675,7 +681,10 @@ bool halo_export_begin(const hdk_csr_s &A, HaloExport *e)
    IpcHalo &I = const_cast<IpcHalo &>(H.ipc);
    I.seq++;
    I.preposted = true;
+   I.arrived = false;
    if (H.n_send <= 0) return true;                         // receives only: nothing to store, the sequence still advances
+   e->rflag = I.data_flag; e->nrflag = (int)H.recv_rank.size();
+   I.arrived = true;                                       // the exporting kernel's last CTA waits for my halo too
    e->dir = I.exp_dir; e->ptr = I.exp_ptr; e->slot = I.exp_slot; e->m = I.exp_m;
    e->lo_end = I.exp_lo_end; e->hi_begin = I.exp_hi_begin;
    e->npeer = (int)H.send_rank.size();
@@ -778,12 +787,29 @@ int halo_exchange_begin(const hdk_csr_s &A, const double *x)
    {
       // peer-memory path: one kernel packs, stores over NVLink and signals; the consumer waits
       IpcHalo &I = const_cast<IpcHalo &>(H.ipc);
-      if (I.preposted) { I.preposted = false; return HDK_OK; } // filled by the kernel that produced x (halo_export_begin)
+      if (I.preposted)
+      {
+         // filled by the kernel that produced x (halo_export_begin); a rank that only receives waits here
+         I.preposted = false;
+         if (!I.arrived && !H.recv_rank.empty())
+         {
+            k_wait_flags<<<1, 32, 0, g.stream>>>(I.data_flag, (int)H.recv_rank.size(), I.seq);
+            HDK_LAUNCH_CHECK();
+         }
+         I.arrived = false;
+         return HDK_OK;
+      }
       I.seq++;
+      if (H.n_send <= 0 && !H.recv_rank.empty())
+      {
+         k_wait_flags<<<1, 32, 0, g.stream>>>(I.data_flag, (int)H.recv_rank.size(), I.seq);
+         HDK_LAUNCH_CHECK();
+      }
       if (H.n_send > 0)
       {
          IpcSendArgs a;
          memset(&a, 0, sizeof(a));
+         a.rflag = I.data_flag; a.nrflag = (int)H.recv_rank.size();
          a.npeer = (int)H.send_rank.size();
          for (int p = 0; p < a.npeer; p++)
          {

@@ -207,6 +207,8 @@ struct IpcSendArgs
    unsigned           *ticket;
    long long           tmo;             // wait budget in clock64 ticks (0: wait for ever)
    int                *err;             // device flag raised when a wait ran out of budget (read by the host later)
+   const unsigned long long *rflag;     // local "data arrived" slots of MY halo, one per recv neighbour:
+   int                 nrflag;          // the last CTA waits for them, so the exchange is complete when the kernel ends
 };
 struct IpcRecvArgs
 {
@@ -238,6 +240,8 @@ struct HaloExport
    unsigned           *ticket = nullptr;
    long long           tmo = 0;
    int                *err = nullptr;
+   const unsigned long long *rflag = nullptr; // as in IpcSendArgs: my own halo's arrival flags, waited for by the last CTA
+   int                 nrflag = 0;
 };
 
 // off-diagonal block fused into the sliced-ELL kernel (peer-memory halo only): rows flagged in
@@ -265,6 +269,7 @@ struct IpcHalo
    int                *exp_dir = nullptr, *exp_ptr = nullptr, *exp_slot = nullptr;
    int                 exp_m = 0, exp_lo_end = 0, exp_hi_begin = 0;
    bool                preposted = false;  // the current sequence was filled by the producer: no pack kernel
+   bool                arrived = false;    // ... and that producer (or the pack kernel) already waited for my halo
 };
 
 #ifdef __CUDACC__
@@ -356,6 +361,9 @@ __device__ __forceinline__ void export_finish(const HaloExport &e)
       {
          __threadfence_system();
          for (int p = 0; p < e.npeer; p++) st_release_sys_u64(e.flag[p], e.seq);
+         // ... and my own halo of the same exchange must have arrived before this kernel ends: the
+         // consumer kernel then needs no system-scope synchronisation at all
+         for (int p = 0; p < e.nrflag; p++) wait_seq_sys(e.rflag + p, e.seq);
       }
    }
 }

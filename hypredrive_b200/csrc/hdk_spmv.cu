@@ -463,7 +463,6 @@ __device__ __forceinline__ void sell_body(const SpmvDev &a)
    // live across the streaming loop (the loop's register budget decides the occupancy)
    __shared__ double s_dot[DOT ? SELL_T : 1];
    if (DOT) s_dot[threadIdx.x] = 0.0;
-   bool      halo_ready = false;
    for (int s = blockIdx.x * wpb + (threadIdx.x >> 5); s < a.nslice; s += gridDim.x * wpb)
    {
       const int  meta  = __ldg(a.sl_meta + (size_t)s * 32 + lane);
@@ -475,7 +474,11 @@ __device__ __forceinline__ void sell_body(const SpmvDev &a)
       o.b = o.d = o.xo = o.yo = o.dv = 0.0;
       // (which operands are fetched before and which after the streaming loop is chosen by the
       // register count ptxas ends up with: 32 = 8 CTAs per SM, 33-40 = 6, 41-48 = 5)
+#ifdef HDK_OFFD_LATE
+      constexpr bool LATE = DOT || OFFD; // (variant build) multi-rank variants too: 32 registers for the Jacobi-type ones
+#else
       constexpr bool LATE = DOT; // fused-dot variants: smoother operands after the loop as well
+#endif
       if (valid)
       {
          if (SUB) o.b = a.b[r];
@@ -515,14 +518,10 @@ __device__ __forceinline__ void sell_body(const SpmvDev &a)
       }
       if (OFFD && (meta & SELL_OFFD_BIT))
       {
-         // row with off-rank entries: the neighbours store the halo values into xh over NVLink and then
-         // raise their sequence flags -- wait for them here (only the first flagged row of a lane really
-         // waits), then continue the row in stored order
-         if (!halo_ready)
-         {
-            for (int p = 0; p < a.ipc.nflag; p++) wait_seq_sys(a.ipc.flag + p, a.ipc.seq, a.ipc.tmo, a.ipc.err);
-            halo_ready = true;
-         }
+         // row with off-rank entries: continue the row's sum in stored order with the halo values.  The
+         // exchange is complete before this kernel starts (the pack / exporting kernel of this rank ends
+         // with the wait for the neighbours' flags), so there is no system-scope synchronisation here --
+         // in-kernel acquire loads in the first wave cost ~20 us per product.
          for (int k = __ldg(a.orp + r), e = __ldg(a.orp + r + 1); k < e; ++k)
          {
             const double p0 = __dmul_rn(__ldg(a.oval + k), __ldcg(a.xh + __ldg(a.ocol + k)));
@@ -787,7 +786,11 @@ int spmv_launch(const DevCSR &A, int mode, const SpmvArgs &s, const OffdFuse *of
    // variants are at 40 registers either way and always fold.  (Tunable export_max_rows.)
    if (s.export_to && of)
    {
+#ifdef HDK_OFFD_LATE
+      const bool jac = false; // (variant build: the Jacobi-type variants have a 32-register non-exporting form too)
+#else
       const bool jac = (mode == SPMV_JACOBI || mode == SPMV_JACOBI_R || mode == SPMV_JACOBI2);
+#endif
       if (jac || (double)A.nrows <= tunables().export_max_rows) halo_export_begin(*s.export_to, &d.exp);
    }
    bool dot = (s.fin != FIN_NONE && s.dotv != nullptr);
