@@ -423,6 +423,10 @@ def ours(args):
         solve_s, wall = float(t[0]), float(t[1])
     per_step = solve_s / args.steps
     value = n_glob * iters / per_step
+    if os.environ.get("HDK_TIMELINE") == "1":             # diagnostics: per-operation times of one more solve, to stderr
+        hdk.tune("timeline", 1)
+        one_solve()
+        hdk.tune("timeline", 0)
 
     # ---- end-to-end leg: host buffers through the C-ABI ---------------------------------
     import torch
@@ -468,6 +472,8 @@ def ours(args):
     extra_kernels = {}
     ms, by = C.c_double(), C.c_double()
     names = {0: "spmv", 1: "l1_jacobi_fused", 2: "residual", 3: "pcg_xr_update", 4: "vcycle", 5: "pcg_p_update"}
+    if world > 1:                            # what the multi-rank products add: the exchange alone, the product without it
+        names.update({7: "halo_exchange", 8: "spmv_without_exchange"})
     for kid, name in names.items():          # collective at N > 1 (halo exchange inside): every rank runs it
         hdk.check(hdk.lib().hdk_time_kernel(hA, hM, kid, 20, C.byref(ms), C.byref(by)))
         extra_kernels[name] = {"ms": ms.value, "GBps": by.value / ms.value / 1e6, "bytes": by.value}
@@ -508,7 +514,7 @@ def ours(args):
         companion = companion_parity(hdk, driver, dist, cfg, rank, world)
 
     if rank == 0:
-        if world == 1:
+        if True:                                  # (N > 1: rank 0's slabs of the distributed levels, then the replicated tail)
             for l in range(nlev):
                 r_, a_, p_ = C.c_int64(), C.c_int64(), C.c_int64()
                 hdk.check(hdk.lib().hdk_amg_level_info(hM, l, C.byref(r_), C.byref(a_), C.byref(p_)))

@@ -278,10 +278,12 @@ static int amg_cycle_impl(hdk_amg_s *M, const double *f0, double *u0, bool zero_
          if (s == 0 && zg && is_jacobi(p.relax_down))
          {
             // (the next product on this level -- another sweep or the residual -- reads this vector)
+            tl_mark(l, 5);
             if (!prefilled) HDK_TRY(vec_scaled_div(cur[(size_t)l], rhs[(size_t)l], L.l1_down, p.relax_weight, L.n, L.A));
          }
          else
          {
+            tl_mark(l, 10);
             if (s == 0 && zg) HDK_TRY(vec_fill(cur[(size_t)l], 0.0, L.n));
             HDK_TRY(relax_sweep(M, l, p.relax_down, L.l1_down, rhs[(size_t)l], cur[(size_t)l], alt[(size_t)l], FIN_NONE, nullptr, L.A));
             std::swap(cur[(size_t)l], alt[(size_t)l]);
@@ -298,9 +300,11 @@ static int amg_cycle_impl(hdk_amg_s *M, const double *f0, double *u0, bool zero_
          SpmvArgs a;
          a.x = cur[(size_t)l]; a.y = alt[(size_t)l]; a.b = rhs[(size_t)l];
          a.export_to = L.R;                                    // the restriction reads the residual next
+         tl_mark(l, 1);
          HDK_TRY(parcsr_matvec(*L.A, SPMV_RESIDUAL, a));
       }
       SpmvArgs rr;
+      tl_mark(l, 2);
       rr.x = alt[(size_t)l];
       prefilled = false;
       if (l + 1 < nl) rr.y = M->lev[(size_t)l + 1].f;
@@ -326,6 +330,7 @@ static int amg_cycle_impl(hdk_amg_s *M, const double *f0, double *u0, bool zero_
    }
    // coarsest stage
    const double *coarse_sol = nullptr; // solution feeding the prolongation of level nfine-1
+   tl_mark(ndown, 6);
    if (sub)
    {
       AmgLevel &Lk = M->lev[(size_t)kg];
@@ -360,6 +365,7 @@ static int amg_cycle_impl(hdk_amg_s *M, const double *f0, double *u0, bool zero_
    {
       AmgLevel &L = M->lev[(size_t)l];
       // u += P e_c
+      tl_mark(l, 3);
       SpmvArgs a;
       a.x = (l + 1 < nl) ? cur[(size_t)l + 1] : coarse_sol;
       a.y = cur[(size_t)l];
@@ -372,11 +378,13 @@ static int amg_cycle_impl(hdk_amg_s *M, const double *f0, double *u0, bool zero_
          int  f_   = (last && fin != FIN_NONE) ? fin : FIN_NONE;
          // reader of this sweep's result: the next sweep, or the prolongation of the level above
          const hdk_csr_s *next = (s + 1 < p.sweeps_up) ? L.A : (l > l0 ? M->lev[(size_t)l - 1].P : nullptr);
+         tl_mark(l, 4);
          HDK_TRY(relax_sweep(M, l, p.relax_up, L.l1_up, rhs[(size_t)l], cur[(size_t)l], alt[(size_t)l], f_, fin_out, next));
          std::swap(cur[(size_t)l], alt[(size_t)l]);
          if (f_ != FIN_NONE) fin_done = true;
       }
    }
+   tl_mark(l0, 0);
    if (cur[(size_t)l0] != u0) HDK_TRY(vec_copy(u0, cur[(size_t)l0], M->lev[(size_t)l0].n));
    if (fin != FIN_NONE && !fin_done) HDK_TRY(vec_dot_dev(f0, u0, M->lev[(size_t)l0].n, fin, fin_out));
    return HDK_OK;
@@ -475,6 +483,12 @@ int hdk_time_kernel(const hdk_csr *A, hdk_amg *M, int kernel, int reps, double *
                   // stage 1 reads A, u, f, d and writes r, u+r; every inner step reads L, r, d, u and writes u (and r)
                   by = 12.0 * nnz + 4.0 * (n + 1) + 40.0 * n + (type == 11 ? 1 : 2) * (12.0 * nnzL + 4.0 * (n + 1) + 32.0 * n) + (type == 12 ? 8.0 * n : 0.0);
                }
+               break;
+            case 7: rc = halo_exchange_begin(*A, x); by = 8.0 * A->halo.n_send; break; // the halo exchange alone (N > 1)
+            case 8: // the product without its exchange (N > 1: what the fused off-diagonal part costs)
+               dbg_skip_exchange(true);
+               rc = parcsr_matvec(*A, SPMV_SET, a); by = 12.0 * nnz + 4.0 * (n + 1) + 16.0 * n;
+               dbg_skip_exchange(false);
                break;
             default: rc = set_error(HDK_ERR_INVALID, "unknown kernel id %d", kernel);
          }

@@ -494,13 +494,12 @@ int allgather_i32_host(const int *mine, int cnt, std::vector<int> &all)
 
 // ---- peer-memory halo plans -------------------------------------------------------------
 // Gather the boundary values and store them into the neighbours' halo buffers (NVLink peer
-// stores); the last block to finish publishes the sequence number in every neighbour's flag.
-// A buffer half is reused every second exchange: wait until the neighbour has read seq - 2.
+// stores); the last block to finish raises this rank's sequence flag at every neighbour and waits
+// for theirs, so the exchange is complete when the kernel ends (a rank that sends nothing runs one
+// block that only does the flags).  Why no acknowledgement is needed before a buffer half is
+// reused: see export_row (hdk_internal.cuh).
 __global__ void k_pack_ipc(const double *x, const int *idx, int n, IpcSendArgs a)
 {
-   if (threadIdx.x == 0 && a.seq > 2)
-      for (int p = 0; p < a.npeer; p++) wait_seq_sys(a.ack + p, a.seq - 2, a.tmo, a.err);
-   __syncthreads();
    int i = blockIdx.x * blockDim.x + threadIdx.x;
    if (i < n)
    {
@@ -513,22 +512,20 @@ __global__ void k_pack_ipc(const double *x, const int *idx, int n, IpcSendArgs a
    {
       __threadfence_system();
       unsigned t = atomicInc(a.ticket, gridDim.x - 1);
-      if (t == gridDim.x - 1)
-      {
-         __threadfence_system();
-         for (int p = 0; p < a.npeer; p++) st_release_sys_u64(a.flag[p], a.seq);
-         for (int p = 0; p < a.nrflag; p++) wait_seq_sys(a.rflag + p, a.seq); // my halo of this exchange has arrived
-      }
+      if (t == gridDim.x - 1) exchange_complete(a.flag, a.rflag, a.nflag, a.seq);
    }
 }
-// a rank that only receives in an exchange: wait for its neighbours' flags (one lane per neighbour)
-__global__ void __launch_bounds__(32) k_wait_flags(const unsigned long long *flag, int nflag, unsigned long long seq)
-{
-   if ((int)threadIdx.x < nflag) wait_seq_sys(flag + threadIdx.x, seq);
-}
 
-// one region per plan in my arena: [8 data flags | 8 ack flags | x_halo half 0 | x_halo half 1]
+// one region per plan in my arena: [16 sequence flags | x_halo half 0 | x_halo half 1]
 static size_t ipc_half_doubles(int n_halo) { return ((size_t)n_halo + 15) & ~(size_t)15; }
+
+// neighbours of rank r in the exchange: every rank it sends to or receives from (a symmetric relation)
+static void ipc_neighbours(const std::vector<int> &all, int R, int r, std::vector<int> &out)
+{
+   out.clear();
+   for (int q = 0; q < R; q++)
+      if (q != r && (all[(size_t)r * R + q] > 0 || all[(size_t)q * R + r] > 0)) out.push_back(q);
+}
 
 static int ipc_plan_build(HaloPlan &H, const std::vector<int> &all /* all[r*R+q]: columns r wants from q */)
 {
@@ -537,7 +534,9 @@ static int ipc_plan_build(HaloPlan &H, const std::vector<int> &all /* all[r*R+q]
    if (!ipc.on) return HDK_OK;
    arena_collect(); // the host-synchronised collectives earlier in the plan build make released regions safe
    const int R = g.nranks, me = g.rank;
-   int ok = (H.send_rank.size() <= (size_t)IPC_MAXP && H.recv_rank.size() <= (size_t)IPC_MAXP) ? 1 : 0;
+   std::vector<int> nbr, theirs;
+   ipc_neighbours(all, R, me, nbr);
+   int ok = nbr.size() <= (size_t)IPC_MAXP ? 1 : 0;
    const size_t bytes = 128 + 2 * ipc_half_doubles(H.n_halo) * sizeof(double);
    int64_t off = ok ? arena_alloc(bytes) : -1;
    if (off >= 0) HDK_CUDA(cudaMemsetAsync(ipc.base + off, 0, 128, g.stream)); // flags start at sequence 0
@@ -552,35 +551,34 @@ static int ipc_plan_build(HaloPlan &H, const std::vector<int> &all /* all[r*R+q]
    }
    I.region_off = off; I.region_bytes = (bytes + 255) & ~(size_t)255;
    I.data_flag = reinterpret_cast<unsigned long long *>(ipc.base + off);
-   I.ack_flag  = I.data_flag + 8;
    I.xh[0]     = reinterpret_cast<double *>(ipc.base + off + 128);
    I.xh[1]     = I.xh[0] + ipc_half_doubles(H.n_halo);
-   // my position in every neighbour's lists, from the global want matrix
+   // where my values start in every send neighbour's halo, from the global want matrix
    for (size_t i = 0; i < H.send_rank.size(); i++)
    {
       const int D = H.send_rank[i];
-      int       roff = 0, ridx = 0, nh = 0;
+      int       roff = 0, nh = 0;
       for (int q = 0; q < R; q++)
       {
          int c = all[(size_t)D * R + q];
-         if (q < me) { roff += c; if (c > 0) ridx++; }
+         if (q < me) roff += c;
          nh += c;
       }
       char *rb = ipc.peer[(size_t)D] + offs[(size_t)D];
-      I.dst[0][i]   = reinterpret_cast<double *>(rb + 128) + roff;
-      I.dst[1][i]   = I.dst[0][i] + ipc_half_doubles(nh);
-      I.dst_flag[i] = reinterpret_cast<unsigned long long *>(rb) + ridx;
+      I.dst[0][i] = reinterpret_cast<double *>(rb + 128) + roff;
+      I.dst[1][i] = I.dst[0][i] + ipc_half_doubles(nh);
    }
-   for (size_t i = 0; i < H.recv_rank.size(); i++)
+   // my flag slot at every neighbour: my position in ITS neighbour list
+   I.nnbr = (int)nbr.size();
+   for (size_t i = 0; i < nbr.size(); i++)
    {
-      const int S = H.recv_rank[i];
-      int       sidx = 0;
-      for (int r = 0; r < me; r++) if (all[(size_t)r * R + S] > 0) sidx++;
-      char *rb = ipc.peer[(size_t)S] + offs[(size_t)S];
-      I.src_ack[i] = reinterpret_cast<unsigned long long *>(rb) + 8 + sidx;
+      const int D = nbr[i];
+      ipc_neighbours(all, R, D, theirs);
+      const int pos = (int)(std::find(theirs.begin(), theirs.end(), me) - theirs.begin());
+      I.nbr_flag[i] = reinterpret_cast<unsigned long long *>(ipc.peer[(size_t)D] + offs[(size_t)D]) + pos;
    }
-   HDK_TRY(dalloc(&I.tickets, 3));
-   HDK_CUDA(cudaMemsetAsync(I.tickets, 0, 3 * sizeof(unsigned), g.stream));
+   HDK_TRY(dalloc(&I.tickets, 2));
+   HDK_CUDA(cudaMemsetAsync(I.tickets, 0, 2 * sizeof(unsigned), g.stream));
    I.seq = 0;
    I.on  = true;
    return HDK_OK;
@@ -598,22 +596,11 @@ void halo_plan_free(HaloPlan &H)
    }
 }
 
-// arguments of the consumer of the halo (k_offd_correct): where x_halo is and what to wait for
-IpcRecvArgs halo_recv_args(const hdk_csr_s &A, const double **xh)
+// where the consumer of the halo finds it (the current buffer half)
+const double *halo_buffer(const hdk_csr_s &A)
 {
    const HaloPlan &H = A.halo;
-   IpcRecvArgs     r;
-   memset(&r, 0, sizeof(r));
-   if (!H.ipc.on) { *xh = H.x_halo; return r; }
-   const IpcHalo &I = H.ipc;
-   *xh      = I.xh[I.seq & 1];
-   r.flag   = I.data_flag;
-   r.nflag  = (int)H.recv_rank.size();
-   r.seq    = I.seq;
-   r.ticket = I.tickets + 1;
-   r.tmo = ipc.tmo; r.err = ipc.err_d;
-   for (size_t i = 0; i < H.recv_rank.size(); i++) r.ack[i] = I.src_ack[i];
-   return r;
+   return H.ipc.on ? H.ipc.xh[H.ipc.seq & 1] : H.x_halo;
 }
 
 // inverse of the send list (row -> its positions in the concatenated send buffer) for exports folded
@@ -661,7 +648,7 @@ static int ipc_export_build(HaloPlan &H, int A_rows /* rows of the vector that i
    HDK_CUDA(cudaMemcpyAsync(I.exp_ptr, ptr.data(), sizeof(int) * ((size_t)m + 1), cudaMemcpyHostToDevice, g.stream));
    HDK_CUDA(cudaMemcpyAsync(I.exp_slot, slot.data(), sizeof(int) * (size_t)H.n_send, cudaMemcpyHostToDevice, g.stream));
    HDK_CUDA(cudaStreamSynchronize(g.stream)); // the host vectors go out of scope
-   I.exp_m = m; I.exp_lo_end = lo_end; I.exp_hi_begin = hi_begin;
+   I.exp_lo_end = lo_end; I.exp_hi_begin = hi_begin;
    return HDK_OK;
 }
 
@@ -672,30 +659,43 @@ static bool export_enabled()
    return on == 1;
 }
 
+static void fill_send_args(const HaloPlan &H, IpcSendArgs &a)
+{
+   const IpcHalo &I = H.ipc;
+   memset(&a, 0, sizeof(a));
+   a.npeer = (int)H.send_rank.size();
+   for (int p = 0; p < a.npeer; p++)
+   {
+      a.dst[p] = I.dst[I.seq & 1][p];
+      a.off[p] = H.send_off[(size_t)p];
+   }
+   a.off[a.npeer] = H.n_send;
+   a.nflag = I.nnbr;
+   for (int p = 0; p < I.nnbr; p++) a.flag[p] = I.nbr_flag[p];
+   a.rflag = I.data_flag; a.seq = I.seq; a.ticket = I.tickets;
+}
+
 bool halo_export_begin(const hdk_csr_s &A, HaloExport *e)
 {
    *e = HaloExport();
    const HaloPlan &H = A.halo;
    if (g.nranks <= 1 || !H.ipc.on || !export_enabled() || H.ipc.preposted) return false;
-   if (!(H.n_send > 0 || H.n_halo > 0)) return false;    // this rank takes no part in the exchange
-   IpcHalo &I = const_cast<IpcHalo &>(H.ipc);
+   if (H.ipc.nnbr == 0 || H.n_send <= 0) return false;     // no part in the exchange / receives only: the flags are
+   IpcHalo &I = const_cast<IpcHalo &>(H.ipc);              // raised by the (empty) pack kernel before the consumer
    I.seq++;
    I.preposted = true;
-   I.arrived = false;
-   if (H.n_send <= 0) return true;                         // receives only: nothing to store, the sequence still advances
-   e->rflag = I.data_flag; e->nrflag = (int)H.recv_rank.size();
-   I.arrived = true;                                       // the exporting kernel's last CTA waits for my halo too
-   e->dir = I.exp_dir; e->ptr = I.exp_ptr; e->slot = I.exp_slot; e->m = I.exp_m;
+   e->dir = I.exp_dir; e->ptr = I.exp_ptr; e->slot = I.exp_slot; e->total = H.n_send;
    e->lo_end = I.exp_lo_end; e->hi_begin = I.exp_hi_begin;
    e->npeer = (int)H.send_rank.size();
    for (int p = 0; p < e->npeer; p++)
    {
-      e->dst[p]  = I.dst[I.seq & 1][p];
-      e->flag[p] = I.dst_flag[p];
-      e->off[p]  = H.send_off[(size_t)p];
+      e->dst[p] = I.dst[I.seq & 1][p];
+      e->off[p] = H.send_off[(size_t)p];
    }
    e->off[e->npeer] = H.n_send;
-   e->ack = I.ack_flag; e->seq = I.seq; e->ticket = I.tickets + 2; e->tmo = ipc.tmo; e->err = ipc.err_d;
+   e->nflag = I.nnbr;
+   for (int p = 0; p < I.nnbr; p++) e->flag[p] = I.nbr_flag[p];
+   e->rflag = I.data_flag; e->seq = I.seq; e->ticket = I.tickets + 1;
    return true;
 }
 
@@ -787,42 +787,12 @@ int halo_exchange_begin(const hdk_csr_s &A, const double *x)
    {
       // peer-memory path: one kernel packs, stores over NVLink and signals; the consumer waits
       IpcHalo &I = const_cast<IpcHalo &>(H.ipc);
-      if (I.preposted)
-      {
-         // filled by the kernel that produced x (halo_export_begin); a rank that only receives waits here
-         I.preposted = false;
-         if (!I.arrived && !H.recv_rank.empty())
-         {
-            k_wait_flags<<<1, 32, 0, g.stream>>>(I.data_flag, (int)H.recv_rank.size(), I.seq);
-            HDK_LAUNCH_CHECK();
-         }
-         I.arrived = false;
-         return HDK_OK;
-      }
+      if (I.preposted) { I.preposted = false; return HDK_OK; } // filled by the kernel that produced x (halo_export_begin)
       I.seq++;
-      if (H.n_send <= 0 && !H.recv_rank.empty())
-      {
-         k_wait_flags<<<1, 32, 0, g.stream>>>(I.data_flag, (int)H.recv_rank.size(), I.seq);
-         HDK_LAUNCH_CHECK();
-      }
-      if (H.n_send > 0)
-      {
-         IpcSendArgs a;
-         memset(&a, 0, sizeof(a));
-         a.rflag = I.data_flag; a.nrflag = (int)H.recv_rank.size();
-         a.npeer = (int)H.send_rank.size();
-         for (int p = 0; p < a.npeer; p++)
-         {
-            a.dst[p]  = I.dst[I.seq & 1][p];
-            a.flag[p] = I.dst_flag[p];
-            a.off[p]  = H.send_off[(size_t)p];
-         }
-         a.off[a.npeer] = H.n_send;
-         a.ack = I.ack_flag; a.seq = I.seq; a.ticket = I.tickets;
-         a.tmo = ipc.tmo; a.err = ipc.err_d;
-         k_pack_ipc<<<cdiv(H.n_send, 256), 256, 0, g.stream>>>(x, H.send_idx, H.n_send, a);
-         HDK_LAUNCH_CHECK();
-      }
+      IpcSendArgs a;
+      fill_send_args(H, a);
+      k_pack_ipc<<<H.n_send > 0 ? cdiv(H.n_send, 256) : 1, H.n_send > 0 ? 256 : 32, 0, g.stream>>>(x, H.send_idx, H.n_send, a);
+      HDK_LAUNCH_CHECK();
       return HDK_OK;
    }
    if (H.n_send > 0)

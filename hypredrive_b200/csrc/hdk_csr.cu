@@ -290,23 +290,8 @@ static int parcsr_from_device(int64_t rs, int64_t re, int64_t grows, const int64
 // ---- y = op(A) x with halo exchange: diag kernel overlaps the exchange, offd kernel follows
 __global__ void k_offd_correct(const int *rows, const int *rowptr, const int *col, const double *val, int nrows,
                                const double *xh, double *y, const double *d, double w, int mode,
-                               double alpha, IpcRecvArgs ipc, const double *dotv, const double *diag_part,
+                               double alpha, const double *dotv, const double *diag_part,
                                double *dot_out, double *partials, unsigned *ticket);
-
-// The fused variant runs at 32-40 registers like the plain one (the streaming loop is pinned to
-// no unrolling), so it is used on every level; HDK_FUSE_OFFD_MAX_ROWS / HDK_FUSE_OFFD=0 restrict it.
-static bool fuse_offd_enabled(int nrows)
-{
-   static int       on = -1;
-   static long long max_rows = 2000000000LL;
-   if (on < 0)
-   {
-      const char *e = getenv("HDK_FUSE_OFFD");
-      on = (e && atoi(e) == 0) ? 0 : 1;
-      if (getenv("HDK_FUSE_OFFD_MAX_ROWS")) max_rows = atoll(getenv("HDK_FUSE_OFFD_MAX_ROWS"));
-   }
-   return on == 1 && nrows <= max_rows;
-}
 
 // true when parcsr_matvec runs as ONE kernel (no off-rank block, or the block fused into the
 // sliced-ELL kernel): then every fused epilogue sees the complete row sum
@@ -314,15 +299,19 @@ bool parcsr_single_kernel(const hdk_csr_s &A)
 {
    bool exch = g.nranks > 1 && (A.halo.n_send > 0 || A.halo.n_halo > 0);
    if (!exch || A.offd.nnz == 0) return true;
-   return A.halo.ipc.on && A.diag.kind == 2 && A.diag.sl_offd_flags && fuse_offd_enabled(A.diag.nrows);
+   return A.diag.kind == 2 && A.diag.sl_offd_flags;
 }
+
+// (hdk_time_kernel 8: time the product without its halo exchange)
+static bool skip_exchange = false;
+void dbg_skip_exchange(bool on) { skip_exchange = on; }
 
 int parcsr_matvec(const hdk_csr_s &A, int mode, SpmvArgs a)
 {
    // p2p exchange partners must match: a rank takes part when it sends OR receives
    bool exch = g.nranks > 1 && (A.halo.n_send > 0 || A.halo.n_halo > 0);
    if (!exch) return spmv_launch(A.diag, mode, a);
-   const bool fused_offd = A.halo.ipc.on && A.diag.kind == 2 && A.diag.sl_offd_flags && A.offd.nnz > 0 && fuse_offd_enabled(A.diag.nrows);
+   const bool fused_offd = A.diag.kind == 2 && A.diag.sl_offd_flags && A.offd.nnz > 0;
    if (mode == SPMV_SET_DIV && !fused_offd && A.offd.nnz > 0)
    {
       // the second output needs the final y: plain product first, then the scaled division
@@ -333,13 +322,17 @@ int parcsr_matvec(const hdk_csr_s &A, int mode, SpmvArgs a)
    }
    if (fused_offd)
    {
-      // peer-memory halo + sliced-ELL: ONE kernel does the diag block, waits in-kernel for the
-      // neighbours' values where a row needs them, adds the off-diagonal entries and runs the
-      // fused epilogue / dot exactly as on a single rank
-      HDK_TRY(halo_exchange_begin(A, a.x));
+      // sliced-ELL with flagged boundary rows: ONE kernel does the local block, adds the off-rank entries of
+      // the flagged rows and runs the fused epilogue / dot exactly as on a single rank.  The exchange is complete before the kernel starts (peer-memory
+      // path: inside the pack / exporting kernel; NCCL path: an event).
+      if (!skip_exchange)
+      {
+         HDK_TRY(halo_exchange_begin(A, a.x));
+         HDK_TRY(halo_exchange_end(A));
+      }
       OffdFuse of;
       of.orp = A.offd.rowptr; of.ocol = A.offd.col; of.oval = A.offd.val;
-      of.ipc = halo_recv_args(A, &of.xh);
+      of.xh = halo_buffer(A);
       return spmv_launch(A.diag, mode, a, &of);
    }
    // start the exchange, run the diag block.  A fused dot <dotv, y> is linear in the off-diagonal
@@ -357,10 +350,8 @@ int parcsr_matvec(const hdk_csr_s &A, int mode, SpmvArgs a)
    if (A.offd.nnz > 0)
    {
       int           grid = cdiv(A.n_offd_rows, 128);
-      const double *xh;
-      IpcRecvArgs   ra = halo_recv_args(A, &xh);
       k_offd_correct<<<grid, 128, 0, g.stream>>>(A.offd_rows, A.offd.rowptr, A.offd.col, A.offd.val, A.n_offd_rows,
-                                                 xh, a.y, a.d, a.w, mode, a.alpha, ra, fused_dot ? a.dotv : nullptr,
+                                                 halo_buffer(A), a.y, a.d, a.w, mode, a.alpha, fused_dot ? a.dotv : nullptr,
                                                  g.dscal + S_TMP1, a.fin_out, g.partials, g.counters + 1);
       HDK_LAUNCH_CHECK();
    }
@@ -373,20 +364,13 @@ int parcsr_matvec(const hdk_csr_s &A, int mode, SpmvArgs a)
 
 __global__ void k_offd_correct(const int *rows, const int *rowptr, const int *col, const double *val, int nrows,
                                const double *xh, double *y, const double *d, double w, int mode,
-                               double alpha, IpcRecvArgs ipc, const double *dotv, const double *diag_part,
+                               double alpha, const double *dotv, const double *diag_part,
                                double *dot_out, double *partials, unsigned *ticket)
 {
    __shared__ double red[128 / 32];
    __shared__ int    lastflag;
    double            dcorr = 0.0; // dotv[r] * (change of y[r])
-   // peer-memory exchange: the neighbours' pack kernels store into xh and then raise the
-   // sequence flags; wait for them here, so the transfer overlaps the diag-block kernel
-   if (ipc.seq)
-   {
-      if (threadIdx.x == 0)
-         for (int p = 0; p < ipc.nflag; p++) wait_seq_sys(ipc.flag + p, ipc.seq, ipc.tmo, ipc.err);
-      __syncthreads();
-   }
+   // (peer-memory exchange: complete before this kernel starts, see halo_exchange_begin)
    int i = blockIdx.x * blockDim.x + threadIdx.x;
    if (i < nrows)
    {
@@ -427,20 +411,6 @@ __global__ void k_offd_correct(const int *rows, const int *rowptr, const int *co
          __syncthreads();
          sacc = block_sum<128>(sacc, red);
          if (threadIdx.x == 0) *dot_out = *diag_part + sacc;
-      }
-   }
-   if (ipc.seq)
-   {
-      // tell the senders this half of the buffer has been read (they reuse it at seq + 2)
-      __syncthreads();
-      if (threadIdx.x == 0)
-      {
-         unsigned t = atomicInc(ipc.ticket, gridDim.x - 1);
-         if (t == gridDim.x - 1)
-         {
-            __threadfence_system();
-            for (int p = 0; p < ipc.nflag; p++) st_release_sys_u64(ipc.ack[p], ipc.seq);
-         }
       }
    }
 }

@@ -199,58 +199,41 @@ constexpr int IPC_MAXP = 8; // neighbours per direction handled by the peer-memo
 struct IpcSendArgs
 {
    double             *dst[IPC_MAXP];   // remote segment of x_halo (current half) per send neighbour
-   unsigned long long *flag[IPC_MAXP];  // remote "data arrived" sequence slot
-   const unsigned long long *ack;       // local: sequence each send neighbour has finished reading
    int                 off[IPC_MAXP + 1];
-   int                 npeer;
+   int                 npeer;           // send neighbours
+   unsigned long long *flag[IPC_MAXP];  // remote "sequence reached" slot of EVERY neighbour (send or receive)
+   const unsigned long long *rflag;     // my own slots, one per neighbour: the last CTA waits for them,
+   int                 nflag;           // so the exchange is complete when the kernel ends
    unsigned long long  seq;
    unsigned           *ticket;
-   long long           tmo;             // wait budget in clock64 ticks (0: wait for ever)
-   int                *err;             // device flag raised when a wait ran out of budget (read by the host later)
-   const unsigned long long *rflag;     // local "data arrived" slots of MY halo, one per recv neighbour:
-   int                 nrflag;          // the last CTA waits for them, so the exchange is complete when the kernel ends
-};
-struct IpcRecvArgs
-{
-   const unsigned long long *flag;      // local: one slot per recv neighbour
-   int                 nflag;
-   unsigned long long  seq;             // 0: no wait (NCCL path)
-   unsigned long long *ack[IPC_MAXP];   // remote "consumed" slot per recv neighbour
-   unsigned           *ticket;
-   long long           tmo;             // as in IpcSendArgs
-   int                *err;
 };
 // Halo export folded into the PRODUCER of a vector: the kernel that writes x stores the rows its
-// neighbours need straight into their halo buffers (peer stores over NVLink) and its last CTA raises
-// the sequence flags, so the consumer's exchange costs no kernel of its own and is complete long
-// before the consumer reaches a boundary row.  dir: direct table over the rows outside the export-free
-// middle range -> index of the exported row (or -1); ptr / slot: per exported row, its positions in the
-// concatenated send list (a row may go to several neighbours).
+// neighbours need straight into their halo buffers (peer stores over NVLink); the warp whose stores
+// complete the send list raises the sequence flags and waits for this rank's own halo, so the
+// consumer's exchange costs no kernel of its own.  dir: direct table over the rows outside the
+// export-free middle range -> index of the exported row (or -1); ptr / slot: per exported row, its
+// positions in the concatenated send list (a row may go to several neighbours).
 struct HaloExport
 {
    const int          *dir = nullptr, *ptr = nullptr, *slot = nullptr;
-   int                 m = 0;              // number of exported rows (0: nothing to export)
+   int                 total = 0;          // entries of the send list: the export is complete when all are stored
    int                 lo_end = 0, hi_begin = 0; // rows in [lo_end, hi_begin) are never exported (quick reject)
    double             *dst[IPC_MAXP];
-   unsigned long long *flag[IPC_MAXP];
-   const unsigned long long *ack = nullptr;
    int                 off[IPC_MAXP + 1];
    int                 npeer = 0;
+   unsigned long long *flag[IPC_MAXP];     // as in IpcSendArgs
+   const unsigned long long *rflag = nullptr;
+   int                 nflag = 0;
    unsigned long long  seq = 0;            // 0: export off
    unsigned           *ticket = nullptr;
-   long long           tmo = 0;
-   int                *err = nullptr;
-   const unsigned long long *rflag = nullptr; // as in IpcSendArgs: my own halo's arrival flags, waited for by the last CTA
-   int                 nrflag = 0;
 };
 
-// off-diagonal block fused into the sliced-ELL kernel (peer-memory halo only): rows flagged in
-// sl_meta add their offd entries after waiting for the neighbours' sequence flags in-kernel
+// off-rank block fused into the sliced-ELL kernel: rows flagged in sl_meta continue their sum with
+// the block's entries (CSR arrays) and the values of the finished exchange (xh)
 struct OffdFuse
 {
    const int    *orp = nullptr, *ocol = nullptr;
    const double *oval = nullptr, *xh = nullptr;
-   IpcRecvArgs   ipc;
 };
 int spmv_launch(const DevCSR &A, int mode, const SpmvArgs &a, const OffdFuse *of = nullptr);
 
@@ -260,16 +243,16 @@ struct IpcHalo
    int64_t             region_off = -1;
    size_t              region_bytes = 0;
    double             *xh[2] = {nullptr, nullptr}; // local halves of x_halo
-   unsigned long long *data_flag = nullptr, *ack_flag = nullptr; // local slots
-   double             *dst[2][IPC_MAXP];
-   unsigned long long *dst_flag[IPC_MAXP], *src_ack[IPC_MAXP];
+   unsigned long long *data_flag = nullptr;         // local slots, one per neighbour (send or receive)
+   double             *dst[2][IPC_MAXP];            // per send neighbour
+   unsigned long long *nbr_flag[IPC_MAXP];          // my slot in every neighbour's region
+   int                 nnbr = 0;
    unsigned long long  seq = 0;
-   unsigned           *tickets = nullptr; // three device counters: pack, consumer ack, export
+   unsigned           *tickets = nullptr; // two device counters: pack, export
    // inverse of the send list for exports folded into the producer kernel
    int                *exp_dir = nullptr, *exp_ptr = nullptr, *exp_slot = nullptr;
-   int                 exp_m = 0, exp_lo_end = 0, exp_hi_begin = 0;
+   int                 exp_lo_end = 0, exp_hi_begin = 0;
    bool                preposted = false;  // the current sequence was filled by the producer: no pack kernel
-   bool                arrived = false;    // ... and that producer (or the pack kernel) already waited for my halo
 };
 
 #ifdef __CUDACC__
@@ -321,50 +304,57 @@ static inline cudaError_t wait_globals_set(long long tmo, int *err)
    if (e == cudaSuccess) e = cudaMemcpyToSymbol(d_wait_err, &err, sizeof(err));
    return e;
 }
-// producer side of a folded halo exchange: row r of the vector just got value v
-__device__ __forceinline__ void export_row(const HaloExport &e, int r, double v)
+// Producer side of a folded halo exchange: row r of the vector just got value v.  Returns the number
+// of send-list entries stored (summed per thread and handed to export_finish).
+// Buffer reuse needs no acknowledgement: every exchange is two-way between neighbours (a rank raises
+// its flag at EVERY neighbour, also one it sends no values to) and the kernel that starts exchange s
+// (pack or exporting producer) does not end before all neighbours' flags have reached s.  A neighbour's
+// flag s was raised after -- in its stream -- the product that read exchange s - 1, so when my exchange
+// s + 1 starts overwriting the half of s - 1, that product is finished.
+__device__ __forceinline__ int export_row(const HaloExport &e, int r, double v)
 {
-   if (e.seq == 0 || (r >= e.lo_end && r < e.hi_begin)) return;
-   // direct table over the two row ranges outside [lo_end, hi_begin): index into rows / ptr, or -1
+   if (e.seq == 0 || (r >= e.lo_end && r < e.hi_begin)) return 0;
+   // direct table over the two row ranges outside [lo_end, hi_begin): index into ptr, or -1
    const int i = e.dir[r < e.lo_end ? r : e.lo_end + (r - e.hi_begin)];
-   if (i < 0) return;
-   for (int k = e.ptr[i]; k < e.ptr[i + 1]; k++)
+   if (i < 0) return 0;
+   const int k0 = e.ptr[i], k1 = e.ptr[i + 1];
+   for (int k = k0; k < k1; k++)
    {
       const int s = e.slot[k];
       int       p = 0;
       while (p + 1 < e.npeer && s >= e.off[p + 1]) p++;
-      if (e.seq > 2) wait_seq_sys(e.ack + p, e.seq - 2, e.tmo, e.err); // the neighbour has read this half
       e.dst[p][s - e.off[p]] = v;
    }
+   return k1 - k0;
 }
-// start of the producer kernel, executed by every CTA: the neighbours must have read the buffer half
-// this sequence overwrites (their acknowledgement of sequence - 2); one acquire per CTA, not per row
-__device__ __forceinline__ void export_begin_cta(const HaloExport &e)
+// raise my flag at every neighbour, then wait until all of theirs have reached the same sequence: the
+// exchange is complete when the kernel that calls this ends, and consumers need no synchronisation.
+// (Measured against waiting in the consumer -- per boundary lane, or thread 0 of every CTA at kernel
+// start -- this is ~0.5 ms per 256^3 solve faster at N = 2: one thread polls, once, at a kernel's tail.)
+__device__ __forceinline__ void exchange_complete(unsigned long long *const *flag, const unsigned long long *rflag, int nflag,
+                                                  unsigned long long seq)
 {
-   if (e.seq <= 2) return;
-   if (threadIdx.x == 0)
-      for (int p = 0; p < e.npeer; p++) wait_seq_sys(e.ack + p, e.seq - 2, e.tmo, e.err);
-   __syncthreads();
+   __threadfence_system();
+   for (int p = 0; p < nflag; p++) st_release_sys_u64(flag[p], seq);
+   for (int p = 0; p < nflag; p++) wait_seq_sys(rflag + p, seq);
 }
-// end of the producer kernel, executed by every CTA: the last one publishes the sequence number.
-// One system-scope fence per CTA (thread 0, after the CTA barrier that orders the other threads'
-// peer stores before it) -- a fence per thread costs ~15 us at the tail of a 300 000-thread kernel.
-__device__ __forceinline__ void export_finish(const HaloExport &e)
+// End of the producer kernel, executed by every warp with all 32 lanes (cnt: what the lane's
+// export_row calls returned).  Warps that exported nothing pay one warp reduction; an exporting warp
+// orders its lanes' peer stores with ONE system-scope fence (lane 0, after the warp barrier of the
+// reduction) and adds its count to the ticket; the warp that completes the send list finishes the
+// exchange.  No CTA barrier, no per-CTA atomics.
+__device__ __forceinline__ void export_finish(const HaloExport &e, int cnt)
 {
    if (e.seq == 0) return;
-   __syncthreads();
-   if (threadIdx.x == 0)
+   const unsigned tot = __reduce_add_sync(0xffffffffu, (unsigned)cnt);
+   __syncwarp(); // (the reduction itself is no memory barrier) orders the lanes' peer stores before lane 0's fence
+   if (tot == 0 || (threadIdx.x & 31) != 0) return;
+   __threadfence_system();
+   const unsigned before = atomicAdd(e.ticket, tot);
+   if (before + tot == (unsigned)e.total)
    {
-      __threadfence_system();
-      unsigned t = atomicInc(e.ticket, gridDim.x - 1);
-      if (t == gridDim.x - 1)
-      {
-         __threadfence_system();
-         for (int p = 0; p < e.npeer; p++) st_release_sys_u64(e.flag[p], e.seq);
-         // ... and my own halo of the same exchange must have arrived before this kernel ends: the
-         // consumer kernel then needs no system-scope synchronisation at all
-         for (int p = 0; p < e.nrflag; p++) wait_seq_sys(e.rflag + p, e.seq);
-      }
+      *e.ticket = 0u; // every contribution is in: re-arm for the next exchange (kernels of one plan are stream-ordered)
+      exchange_complete(e.flag, e.rflag, e.nflag, e.seq);
    }
 }
 #endif
@@ -430,8 +420,10 @@ int allreduce_i32_dev(int *buf_d, int count);
 int alltoallv_bytes(const void *send_d, const int64_t *soff /* nranks+1 */, void *recv_d, const int64_t *roff /* nranks+1 */);
 int allgatherv_bytes(void *base_d, const int64_t *byte_offs /* nranks+1 */); // in place, compute stream
 void halo_plan_free(HaloPlan &H);
-IpcRecvArgs halo_recv_args(const hdk_csr_s &A, const double **xh); // after halo_exchange_begin
+const double *halo_buffer(const hdk_csr_s &A); // after halo_exchange_begin: where this exchange's values are
 int halo_exchange_begin(const hdk_csr_s &A, const double *x);
+void dbg_skip_exchange(bool on);
+void tl_mark(int level, int op); // diagnostics timeline (hdk_runtime.cu)
 int halo_exchange_end(const hdk_csr_s &A);
 // producer-side exchange: fills *e for the kernel that writes the vector A's next product reads and
 // marks the plan as served; false (and e->seq == 0) when the plan is not on the peer-memory path

@@ -122,6 +122,7 @@ int hdk_pcg(const hdk_csr *A, hdk_amg *M, const double *b, double *x, hdk_krylov
       // s = A p ; sdotp = <s,p> ; alpha = gamma / sdotp   (one kernel)
       SpmvArgs a;
       a.x = p; a.y = s; a.dotv = p; a.fin = local_fin(FIN_SDOTP); a.fin_out = local_out(nullptr);
+      tl_mark(0, 7);
       if ((rc = parcsr_matvec(*A, SPMV_SET, a))) goto done;
       if ((rc = finish_dot(FIN_SDOTP, nullptr))) goto done;
       // x += alpha p ; r -= alpha s ; i_prod = <r,r>       (one kernel)
@@ -132,6 +133,7 @@ int hdk_pcg(const hdk_csr *A, hdk_amg *M, const double *b, double *x, hdk_krylov
          double        zw = 1.0;
          const hdk_csr_s *zreader = nullptr;
          const bool    pf = M && amg_prefill_target(M, s, &zb, &zd, &zw, &zreader);
+         tl_mark(0, 8);
          if ((rc = pcg_update_xr(x, r, p, s, n, S, local_fin(FIN_IPROD), local_out(nullptr), pf ? zb : nullptr, zd, zw, pf ? zreader : nullptr))) goto done;
          if (pf) M->prefilled_at = 0;
       }
@@ -146,6 +148,7 @@ int hdk_pcg(const hdk_csr *A, hdk_amg *M, const double *b, double *x, hdk_krylov
       if (g.hscal[S_SDOTP] == 0.0 || i_prod != i_prod) { break; }
       if (i_prod / bi_prod < eps) { k->converged = 1; break; }
       // p = s + beta p   (the next iteration's A p reads it: its halo is filled here)
+      tl_mark(0, 9);
       if ((rc = pcg_update_p(p, s, n, S, i + 1 <= k->max_iter ? A : nullptr))) goto done;
    }
    k->iters        = i;

@@ -152,9 +152,58 @@ int hdk_copy_h2d(void *dst_d, const void *src_h, size_t bytes)
 
 } // extern "C"
 
+// ---- timeline (diagnostics): hdk_tune("timeline", 1) starts recording one CUDA event before every
+// operation of the V-cycle / PCG loop, hdk_tune("timeline", 0) prints the average time of each
+// (level, operation) segment -- launch gaps and waits included -- to stderr and stops.
+#include <map>
+#include <cstring>
+namespace hdk {
+struct TlMark { cudaEvent_t ev; int code; };
+static std::vector<TlMark> tl_marks;
+static bool                tl_on = false;
+void tl_mark(int level, int op)
+{
+   if (!tl_on) return;
+   TlMark m;
+   m.code = level * 16 + op;
+   if (cudaEventCreate(&m.ev) != cudaSuccess) return;
+   cudaEventRecord(m.ev, g.stream);
+   tl_marks.push_back(m);
+}
+static void tl_dump()
+{
+   static const char *names[16] = {"cycle-end", "residual", "restrict", "prolong", "post-sweep", "first-sweep", "tail", "pcg-spmv",
+                                   "pcg-xr", "pcg-p", "pre-sweep", "gather", "?", "?", "?", "?"};
+   if (tl_marks.empty()) return;
+   cudaEventSynchronize(tl_marks.back().ev);
+   std::map<int, std::pair<double, int>> acc;
+   for (size_t i = 0; i + 1 < tl_marks.size(); i++)
+   {
+      float ms = 0.f;
+      cudaEventElapsedTime(&ms, tl_marks[i].ev, tl_marks[i + 1].ev);
+      auto &a = acc[tl_marks[i].code];
+      a.first += ms; a.second++;
+   }
+   double tot = 0.0;
+   for (auto &kv : acc) tot += kv.second.first;
+   fprintf(stderr, "[hdk timeline rank %d] %zu marks, %.3f ms\n", g.rank, tl_marks.size(), tot);
+   for (auto &kv : acc)
+         fprintf(stderr, "[hdk timeline rank %d] level %d %-11s n=%3d avg %8.2f us total %8.3f ms\n", g.rank, kv.first >> 4,
+                 names[kv.first & 15], kv.second.second, 1e3 * kv.second.first / kv.second.second, kv.second.first);
+   for (auto &m : tl_marks) cudaEventDestroy(m.ev);
+   tl_marks.clear();
+}
+} // namespace hdk
+
 extern "C" int hdk_tune(const char *key, double value)
 {
    if (!key) return hdk::set_error(HDK_ERR_INVALID, "hdk_tune: null key");
+   if (!strcmp(key, "timeline"))
+   {
+      if (value != 0.0) hdk::tl_on = true;
+      else { hdk::tl_on = false; hdk::tl_dump(); }
+      return HDK_OK;
+   }
    return hdk::tune_set(key, value);
 }
 

@@ -41,7 +41,7 @@ struct Tune
    double sell_sort     = 1;        // HDK_SELL_SORT        sort the columns of coarse operators in the slices
    double amg_keep_debug = 0;       // HDK_AMG_KEEP_DEBUG   keep S and the PMIS measures of every level (introspection)
    double replicate_rows = 262144;  // HDK_REPLICATE_ROWS   N > 1: levels with at most this many global rows form the replicated tail
-   double export_max_rows = 2000000; // HDK_EXPORT_MAX_ROWS  N > 1: operators with more rows pack their halo instead of folding the export
+   double export_max_rows = 1e18;   // HDK_EXPORT_MAX_ROWS  N > 1: operators with more rows pack their halo instead of folding the export
    double graph_rows    = 150000;   // HDK_GRAPH_ROWS       V-cycle levels with at most this many rows are replayed from a CUDA graph (0: off)
    bool   env_read      = false;
 };
@@ -94,10 +94,12 @@ struct SpmvDev
    const int    *sl_off, *sl_meta, *sl_col;
    const double *sl_val;
    int           nslice;
-   // fused off-diagonal block (peer-memory halo): see OffdFuse
+   // fused off-rank block (N > 1, see OffdFuse): CSR arrays of the block and the halo buffer; has_halo
+   // selects the multi-rank kernel variants
    const int    *orp, *ocol;
    const double *oval, *xh;
-   IpcRecvArgs   ipc;
+   int           has_halo;
+
    // halo of the NEXT product filled by this kernel (see HaloExport); exp_y2: the exported vector is y2
    HaloExport    exp;
    int           exp_y2;
@@ -136,7 +138,7 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
 // result of the row epilogue: y for most modes, the correction w(b - Ax)/d for JACOBI2, A x for GS_STEP.
 // The row of the output that feeds the next product is also handed to the halo export.
 template <int MODE, bool EXP = false>
-__device__ __forceinline__ double store_out(const SpmvDev &a, int r, double v, double dd, double xo)
+__device__ __forceinline__ double store_out(const SpmvDev &a, int r, double v, double dd, double xo, int &nexp)
 {
    double yn = v, y2 = 0.0;
    if (MODE == SPMV_JACOBI2)
@@ -158,8 +160,15 @@ __device__ __forceinline__ double store_out(const SpmvDev &a, int r, double v, d
    }
    a.y[r] = yn;
    // (compiled only into the multi-rank sliced-ELL variants: the plain kernels keep their 32 registers)
-   if (EXP && a.exp.seq) export_row(a.exp, r, a.exp_y2 ? y2 : yn);
+   if (EXP && a.exp.seq) nexp += export_row(a.exp, r, a.exp_y2 ? y2 : yn);
    return yn;
+}
+
+template <int MODE>
+__device__ __forceinline__ double store_out(const SpmvDev &a, int r, double v, double dd, double xo)
+{
+   int none = 0;
+   return store_out<MODE, false>(a, r, v, dd, xo, none);
 }
 
 struct BlkMeta { int r0, r1, k0, k1; };
@@ -411,7 +420,7 @@ __global__ void __launch_bounds__(ST, 4) k_spmv_tma(SpmvDev a, int nblk, int cap
 // its stored order with separately rounded multiply and add.
 // ---------------------------------------------------------------------------------------
 constexpr int SELL_T = 256;
-constexpr int SELL_OFFD_BIT = 32; // sl_meta = len << 6 | offd flag << 5 | row offset in the slice
+constexpr int SELL_OFFD_BIT = 32; // sl_meta = len << 6 | row has off-rank entries << 5 | row offset in the slice
 
 template <int MODE>
 __device__ __forceinline__ double row_epilogue(const SpmvDev &a, const RowOps &o, double acc)
@@ -444,7 +453,6 @@ __device__ __forceinline__ double ld_x(const double *p, uint64_t pol)
 #else
 #define LDX(p) __ldg(p)
 #endif
-
 // EXP: the halo export of the next product is folded into this kernel (multi-rank variants only)
 template <int MODE, bool DOT, bool OFFD, bool EXP>
 __device__ __forceinline__ void sell_body(const SpmvDev &a)
@@ -463,6 +471,7 @@ __device__ __forceinline__ void sell_body(const SpmvDev &a)
    // live across the streaming loop (the loop's register budget decides the occupancy)
    __shared__ double s_dot[DOT ? SELL_T : 1];
    if (DOT) s_dot[threadIdx.x] = 0.0;
+   int nexp = 0; // send-list entries this lane stored (EXP variants)
    for (int s = blockIdx.x * wpb + (threadIdx.x >> 5); s < a.nslice; s += gridDim.x * wpb)
    {
       const int  meta  = __ldg(a.sl_meta + (size_t)s * 32 + lane);
@@ -474,11 +483,7 @@ __device__ __forceinline__ void sell_body(const SpmvDev &a)
       o.b = o.d = o.xo = o.yo = o.dv = 0.0;
       // (which operands are fetched before and which after the streaming loop is chosen by the
       // register count ptxas ends up with: 32 = 8 CTAs per SM, 33-40 = 6, 41-48 = 5)
-#ifdef HDK_OFFD_LATE
-      constexpr bool LATE = DOT || OFFD; // (variant build) multi-rank variants too: 32 registers for the Jacobi-type ones
-#else
       constexpr bool LATE = DOT; // fused-dot variants: smoother operands after the loop as well
-#endif
       if (valid)
       {
          if (SUB) o.b = a.b[r];
@@ -520,8 +525,8 @@ __device__ __forceinline__ void sell_body(const SpmvDev &a)
       {
          // row with off-rank entries: continue the row's sum in stored order with the halo values.  The
          // exchange is complete before this kernel starts (the pack / exporting kernel of this rank ends
-         // with the wait for the neighbours' flags), so there is no system-scope synchronisation here --
-         // in-kernel acquire loads in the first wave cost ~20 us per product.
+         // with the wait for the neighbours' flags) and buffer reuse is ordered by the next exchange, so
+         // this kernel has no system-scope synchronisation at all.
          for (int k = __ldg(a.orp + r), e = __ldg(a.orp + r + 1); k < e; ++k)
          {
             const double p0 = __dmul_rn(__ldg(a.oval + k), __ldcg(a.xh + __ldg(a.ocol + k)));
@@ -536,25 +541,11 @@ __device__ __forceinline__ void sell_body(const SpmvDev &a)
          // y += A x: y is read only now (live across the loop it costs 10 registers = 3 CTAs per SM),
          // so the sum is y + (a_0 x_0 + a_1 x_1 + ...) -- rounding-level difference to the CSR-order sum
          if (MODE == SPMV_ADD) acc = __dadd_rn(a.y[r], acc);
-         double yn = store_out<MODE, EXP>(a, r, row_epilogue<MODE>(a, o, acc), o.d, o.xo);
+         double yn = store_out<MODE, EXP>(a, r, row_epilogue<MODE>(a, o, acc), o.d, o.xo, nexp);
          if (DOT) s_dot[threadIdx.x] += o.dv * yn;
       }
    }
-   if (EXP) export_finish(a.exp);
-   if (OFFD && a.ipc.seq)
-   {
-      // all reads of xh by this CTA are done; the last CTA tells the senders (buffer reuse at seq + 2)
-      __syncthreads();
-      if (threadIdx.x == 0)
-      {
-         unsigned t = atomicInc(a.ipc.ticket, gridDim.x - 1);
-         if (t == gridDim.x - 1)
-         {
-            __threadfence_system();
-            for (int p = 0; p < a.ipc.nflag; p++) st_release_sys_u64(a.ipc.ack[p], a.ipc.seq);
-         }
-      }
-   }
+   if (EXP) export_finish(a.exp, nexp);
    if (DOT)
    {
       double bs = block_sum<SELL_T>(s_dot[threadIdx.x], red);
@@ -656,7 +647,7 @@ static int launch_sell_v(const DevCSR &A, const SpmvDev &d)
 template <int MODE, bool DOT>
 static int launch_sell(const DevCSR &A, const SpmvDev &d)
 {
-   if (!d.orp) return launch_sell_v<MODE, DOT, false, false>(A, d);
+   if (!d.has_halo) return launch_sell_v<MODE, DOT, false, false>(A, d);
    return d.exp.seq ? launch_sell_v<MODE, DOT, true, true>(A, d) : launch_sell_v<MODE, DOT, true, false>(A, d);
 }
 
@@ -771,28 +762,20 @@ int spmv_launch(const DevCSR &A, int mode, const SpmvArgs &s, const OffdFuse *of
    d.nrows = A.nrows; d.fin = s.fin; d.fin_out = s.fin_out;
    d.scal = g.dscal; d.partials = g.partials; d.ticket = g.counters;
    d.sl_off = A.sl_off; d.sl_meta = A.sl_meta; d.sl_col = A.sl_col; d.sl_val = A.sl_val; d.nslice = A.nslice;
-   d.orp = nullptr; d.ocol = nullptr; d.oval = nullptr; d.xh = nullptr;
-   memset(&d.ipc, 0, sizeof(d.ipc));
+   d.orp = nullptr; d.ocol = nullptr; d.oval = nullptr; d.xh = nullptr; d.has_halo = 0;
    if (of)
    {
-      if (A.kind != 2 || !A.sl_offd_flags) return set_error(HDK_ERR_INVALID, "fused off-diagonal block needs the sliced-ELL layout");
-      d.orp = of->orp; d.ocol = of->ocol; d.oval = of->oval; d.xh = of->xh; d.ipc = of->ipc;
+      if (A.kind != 2 || !A.sl_offd_flags) return set_error(HDK_ERR_INVALID, "fused off-rank block needs the sliced-ELL layout with flagged rows");
+      d.orp = of->orp; d.ocol = of->ocol; d.oval = of->oval; d.xh = of->xh;
+      d.has_halo = 1;
    }
    d.exp = HaloExport();
    d.exp_y2 = s.export_y2 ? 1 : 0;
-   // Folding the export into this kernel saves the consumer's pack kernel (~8 us) but the exporting
-   // variants of SET / RESIDUAL / ADD / SET_DIV need 40 registers instead of 32 (6 instead of 8 CTAs per
-   // SM, ~+25 us on a 16 M-row operator): fold on the small levels, pack on the big ones.  The Jacobi-type
-   // variants are at 40 registers either way and always fold.  (Tunable export_max_rows.)
-   if (s.export_to && of)
-   {
-#ifdef HDK_OFFD_LATE
-      const bool jac = false; // (variant build: the Jacobi-type variants have a 32-register non-exporting form too)
-#else
-      const bool jac = (mode == SPMV_JACOBI || mode == SPMV_JACOBI_R || mode == SPMV_JACOBI2);
-#endif
-      if (jac || (double)A.nrows <= tunables().export_max_rows) halo_export_begin(*s.export_to, &d.exp);
-   }
+   // Folding the export into this kernel saves the consumer's pack kernel (~13 us).  The exporting variants
+   // compile to the same register budget as the non-exporting multi-rank ones (32 for SET / RESIDUAL /
+   // ADD, 40 for the rest -- guarded by tests/test_abi_and_host.py), so every product folds; the tunable
+   // export_max_rows makes operators above a size pack instead (experiments).
+   if (s.export_to && of && (double)A.nrows <= tunables().export_max_rows) halo_export_begin(*s.export_to, &d.exp);
    bool dot = (s.fin != FIN_NONE && s.dotv != nullptr);
    switch (mode)
    {
@@ -857,8 +840,13 @@ static int sell_build(DevCSR &A)
    HDK_TRY(dalloc(&width, (size_t)ns + 1));
    HDK_CUDA(cudaMemsetAsync(width + ns, 0, sizeof(int), g.stream));
    HDK_CUDA(cudaMemsetAsync(dmax, 0, sizeof(int), g.stream));
-   k_sell_meta<<<cdiv(ns, 8), 256, 0, g.stream>>>(A.rowptr, A.nrows, ns, A.sl_meta, width, dmax, A.offd_rowptr);
-   A.sl_offd_flags = (A.offd_rowptr != nullptr);
+   // N > 1: rows with off-rank entries are flagged, the multi-rank kernel variants add those entries
+   // (HDK_FUSE_OFFD=0: no flags, a second kernel adds them)
+   static int fuse_on = -1;
+   if (fuse_on < 0) { const char *e = getenv("HDK_FUSE_OFFD"); fuse_on = (e && atoi(e) == 0) ? 0 : 1; }
+   const int *orp = fuse_on ? A.offd_rowptr : nullptr;
+   k_sell_meta<<<cdiv(ns, 8), 256, 0, g.stream>>>(A.rowptr, A.nrows, ns, A.sl_meta, width, dmax, orp);
+   A.sl_offd_flags = (orp != nullptr);
    HDK_LAUNCH_CHECK();
    HDK_TRY(exclusive_scan_int(width, A.sl_off, ns + 1));
    int h[2] = {0, 0};

@@ -44,15 +44,15 @@ __global__ void __launch_bounds__(VT) k_scale(double a, double *x, int64_t n)
 __global__ void __launch_bounds__(VT) k_scaled_div(double *__restrict__ u, const double *__restrict__ f,
                                                    const double *__restrict__ d, double w, int64_t n, const HaloExport ex)
 {
-   export_begin_cta(ex);
+   int nexp = 0;
    for (int64_t i = blockIdx.x * (int64_t)VT + threadIdx.x; i < n; i += (int64_t)gridDim.x * VT)
    {
       double dd = d[i];
       double v  = (dd != 0.0) ? __ddiv_rn(__dmul_rn(w, f[i]), dd) : 0.0;
       u[i]      = v;
-      if (ex.seq) export_row(ex, (int)i, v);
+      if (ex.seq) nexp += export_row(ex, (int)i, v);
    }
-   export_finish(ex);
+   export_finish(ex, nexp);
 }
 
 // kind: 0 dot(x,y), 1 sum|x|, 2 max|x| (max uses the same tree with fmax)
@@ -130,7 +130,7 @@ __global__ void __launch_bounds__(VT) k_pcg_xr(double *x, double *r, const doubl
    const double      alpha = scal[S_ALPHA];
    double            acc   = 0.0;
    const int64_t     n2 = n >> 1, stride = (int64_t)gridDim.x * VT;
-   if (PREFILL) export_begin_cta(ex);
+   int nexp = 0;
    double2          *x2 = reinterpret_cast<double2 *>(x), *r2 = reinterpret_cast<double2 *>(r);
    const double2    *p2 = reinterpret_cast<const double2 *>(p), *s2 = reinterpret_cast<const double2 *>(s);
    double2          *z2 = reinterpret_cast<double2 *>(z0);
@@ -152,7 +152,7 @@ __global__ void __launch_bounds__(VT) k_pcg_xr(double *x, double *r, const doubl
          zo.x = (di.x != 0.0) ? __ddiv_rn(__dmul_rn(zw, ro.x), di.x) : 0.0;
          zo.y = (di.y != 0.0) ? __ddiv_rn(__dmul_rn(zw, ro.y), di.y) : 0.0;
          z2[i] = zo;
-         if (ex.seq) { export_row(ex, (int)(2 * i), zo.x); export_row(ex, (int)(2 * i + 1), zo.y); }
+         if (ex.seq) { nexp += export_row(ex, (int)(2 * i), zo.x); nexp += export_row(ex, (int)(2 * i + 1), zo.y); }
       }
       acc += ro.x * ro.x; acc += ro.y * ro.y;
       xo.x = __dadd_rn(xj.x, __dmul_rn(alpha, pj.x)); xo.y = __dadd_rn(xj.y, __dmul_rn(alpha, pj.y));
@@ -163,7 +163,7 @@ __global__ void __launch_bounds__(VT) k_pcg_xr(double *x, double *r, const doubl
          zo.x = (dj.x != 0.0) ? __ddiv_rn(__dmul_rn(zw, ro.x), dj.x) : 0.0;
          zo.y = (dj.y != 0.0) ? __ddiv_rn(__dmul_rn(zw, ro.y), dj.y) : 0.0;
          z2[j] = zo;
-         if (ex.seq) { export_row(ex, (int)(2 * j), zo.x); export_row(ex, (int)(2 * j + 1), zo.y); }
+         if (ex.seq) { nexp += export_row(ex, (int)(2 * j), zo.x); nexp += export_row(ex, (int)(2 * j + 1), zo.y); }
       }
       acc += ro.x * ro.x; acc += ro.y * ro.y;
    }
@@ -181,7 +181,7 @@ __global__ void __launch_bounds__(VT) k_pcg_xr(double *x, double *r, const doubl
          zo.x = (di.x != 0.0) ? __ddiv_rn(__dmul_rn(zw, ro.x), di.x) : 0.0;
          zo.y = (di.y != 0.0) ? __ddiv_rn(__dmul_rn(zw, ro.y), di.y) : 0.0;
          z2[i] = zo;
-         if (ex.seq) { export_row(ex, (int)(2 * i), zo.x); export_row(ex, (int)(2 * i + 1), zo.y); }
+         if (ex.seq) { nexp += export_row(ex, (int)(2 * i), zo.x); nexp += export_row(ex, (int)(2 * i + 1), zo.y); }
       }
       acc += ro.x * ro.x; acc += ro.y * ro.y;
    }
@@ -190,9 +190,9 @@ __global__ void __launch_bounds__(VT) k_pcg_xr(double *x, double *r, const doubl
       const int64_t k  = n - 1;
       const double  dk = PREFILL ? zd[k] : 0.0;
       acc += pcg_xr_row<PREFILL>(alpha, x[k], p[k], r[k], s[k], dk, zw, x, r, z0, k);
-      if (PREFILL && ex.seq) export_row(ex, (int)k, z0[k]);
+      if (PREFILL && ex.seq) nexp += export_row(ex, (int)k, z0[k]);
    }
-   if (PREFILL) export_finish(ex);
+   if (PREFILL) export_finish(ex, nexp);
    double bs = block_sum<VT>(acc, sm);
    __syncthreads();
    grid_finish<VT>(bs, partials, ticket, fin, fin_out, scal, sm, &flag);
@@ -204,7 +204,7 @@ __global__ void __launch_bounds__(VT) k_pcg_p(double *__restrict__ p, const doub
 {
    const double   beta = scal[S_BETA];
    const int64_t  n2 = n >> 1, stride = (int64_t)gridDim.x * VT;
-   export_begin_cta(ex);
+   int nexp = 0;
    double2       *p2 = reinterpret_cast<double2 *>(p);
    const double2 *z2 = reinterpret_cast<const double2 *>(z);
    int64_t        i = blockIdx.x * (int64_t)VT + threadIdx.x;
@@ -217,8 +217,8 @@ __global__ void __launch_bounds__(VT) k_pcg_p(double *__restrict__ p, const doub
       p2[i] = qi; p2[j] = qj;
       if (ex.seq)
       {
-         export_row(ex, (int)(2 * i), qi.x); export_row(ex, (int)(2 * i + 1), qi.y);
-         export_row(ex, (int)(2 * j), qj.x); export_row(ex, (int)(2 * j + 1), qj.y);
+         nexp += export_row(ex, (int)(2 * i), qi.x); nexp += export_row(ex, (int)(2 * i + 1), qi.y);
+         nexp += export_row(ex, (int)(2 * j), qj.x); nexp += export_row(ex, (int)(2 * j + 1), qj.y);
       }
    }
    if (i < n2)
@@ -226,15 +226,15 @@ __global__ void __launch_bounds__(VT) k_pcg_p(double *__restrict__ p, const doub
       const double2 pi = p2[i], zi = z2[i];
       const double2 qi = make_double2(__dadd_rn(zi.x, __dmul_rn(beta, pi.x)), __dadd_rn(zi.y, __dmul_rn(beta, pi.y)));
       p2[i] = qi;
-      if (ex.seq) { export_row(ex, (int)(2 * i), qi.x); export_row(ex, (int)(2 * i + 1), qi.y); }
+      if (ex.seq) { nexp += export_row(ex, (int)(2 * i), qi.x); nexp += export_row(ex, (int)(2 * i + 1), qi.y); }
    }
    if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0)
    {
       const double q = __dadd_rn(z[n - 1], __dmul_rn(beta, p[n - 1]));
       p[n - 1] = q;
-      if (ex.seq) export_row(ex, (int)(n - 1), q);
+      if (ex.seq) nexp += export_row(ex, (int)(n - 1), q);
    }
-   export_finish(ex);
+   export_finish(ex, nexp);
 }
 
 // scalar forms for operands that are not 16-byte aligned (sub-vectors at odd offsets)
