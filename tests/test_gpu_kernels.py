@@ -354,3 +354,22 @@ def test_random_vector_matches_hypre_stream(gpu):
     ds = gpu.DVec(1000)
     gpu.check(gpu.lib().hdk_vec_random(ds.p, 1000, 5000, 2023))
     assert np.array_equal(ds.get(), ref[5000:6000])
+
+
+def test_timeline_diagnostics_do_not_change_the_solve(gpu, capfd):
+    """hdk_tune("timeline", 1/0) brackets a solve with CUDA events per operation and prints the
+    per-(level, operation) averages to stderr; the solve itself is the same."""
+    A, b = O.gen("lap7", 12, 12, 12)
+    n = A.shape[0]
+    dA = gpu.DCsr.from_scipy(A)
+    M = gpu.DAmg(dA)
+    db, dx = gpu.DVec(n, b), gpu.DVec(n)
+    ref = gpu.pcg(dA, db, dx, M)
+    x0 = dx.get().copy()
+    gpu.tune("timeline", 1)
+    dx.set(np.zeros(n))
+    info = gpu.pcg(dA, db, dx, M)
+    gpu.tune("timeline", 0)
+    err = capfd.readouterr().err
+    assert info["iters"] == ref["iters"] and np.array_equal(dx.get(), x0)
+    assert "hdk timeline" in err and "pcg-spmv" in err and "residual" in err

@@ -84,11 +84,14 @@ def test_row_distributed_setup_matches_oracle(gpu, world, kind, dims, rep, ragge
     _row_distributed_case(world, kind, dims, rep, ragged, {})
 
 
-@pytest.mark.parametrize("knob", ["HDK_RAP_SINGLE", "HDK_INTERP_SINGLE", "HDK_HALO_EXPORT", "HDK_MAILBOX", "HDK_GRAPH_ROWS"])
+@pytest.mark.parametrize("knob", ["HDK_RAP_SINGLE", "HDK_INTERP_SINGLE", "HDK_HALO_EXPORT", "HDK_MAILBOX", "HDK_GRAPH_ROWS",
+                                  "HDK_FUSE_OFFD", "HDK_EXPORT_MAX_ROWS=100"])
 def test_fallback_paths_match_oracle(gpu, knob):
-    """Every default-on optimisation switched off in turn (count + fill Galerkin product, pack kernels
-    instead of folded halo exports, NCCL all-reduce instead of the mailbox, no CUDA graph): same bits."""
-    extra = {knob: "0", "HDK_SELL_MIN_ROWS": "0", "HDK_SELL_MIN_ROWS_DIST": "0"}
+    """Every default-on optimisation switched off in turn (count + fill Galerkin product and interpolation,
+    pack kernels instead of folded halo exports, NCCL all-reduce instead of the mailbox, no CUDA graph,
+    off-rank block in a kernel of its own, big operators packing while small ones fold): same bits."""
+    name, _, value = knob.partition("=")
+    extra = {name: value or "0", "HDK_SELL_MIN_ROWS": "0", "HDK_SELL_MIN_ROWS_DIST": "0"}
     if gpu.device_count() < 2:
         extra["MPCHECK_SHARED_IPC"] = "1"        # keep the peer-memory path on (two processes, one GPU)
     _row_distributed_case(2, "lap7", ("16", "16", "10"), "40", "0", extra)
