@@ -88,7 +88,8 @@ SOLVER_DESC = {"pcg": "BoomerAMG(PMIS, ext+i, max_nnz_row 4, l1-Jacobi, GE coars
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of the fine-level residual SpMV at the
 # headline workload (256^3 7-point rows per GPU), from the `ncu --set full` capture summarised
 # under profiles/ (see profiles/README.md); None when no capture exists for the selected kernel
-NCU_TRAFFIC_BYTES = {"lap7_256": {"k_spmv_sell": 1.7437e9 + 0.1171e9, "k_spmv_tma": 1.7404e9 + 0.1303e9}}
+NCU_TRAFFIC_BYTES = {"lap7_256": {"k_spmv_sell": 1.7438e9 + 0.1177e9,   # profiles/r02_spmv_sell_ncu_full.csv, first launch
+                                   "k_spmv_tma": 1.7404e9 + 0.1303e9}}
 
 
 def measured_peaks():

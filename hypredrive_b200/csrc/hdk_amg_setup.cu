@@ -668,6 +668,115 @@ __global__ void k_interp_fill(const int *arp, const int *acol, const double *ava
    for (int k = 0; k < len; k++) { pcol[p0 + k] = f2c[lc[k]]; pval[p0 + k] = lv[k]; }
 }
 
+// ---- one thread per row, C-hat in thread-local arrays (short rows: the stencil levels) -----------
+// Single pass like k_interp_warp<true, true>: discovery, weights and truncation of a row in one go, the
+// result in slot i * max_elmts of the staging buffer, cnt / rowlen / slow set for the later passes.
+// C-hat of a 7-point row has at most ~20 members, so a linear search over a local array replaces the
+// hash table in global scratch (round 2 before: 8.6 GB of tables for 256^3, 10.7 GB of DRAM traffic
+// and a counting pass).  Slots are assigned in discovery order, exactly like the tables' indices, so
+// every sum is accumulated in the same order.  Rows that do not fit the arrays are flagged slow.
+constexpr int IS_CAP = 48; // |C-hat| handled here
+constexpr int IS_F   = 24; // strong F neighbours handled here
+__device__ __forceinline__ int is_find(const int *key, int n, int k)
+{
+   for (int j = 0; j < n; j++)
+      if (key[j] == k) return j;
+   return -1;
+}
+__global__ void __launch_bounds__(128) k_interp_small(const int *arp, const int *acol, const double *aval, const int *srp,
+                                                      const int *scol, const int *cf, const int *f2c, int row_lo, int row_hi,
+                                                      int max_elmts, int *cnt, int *rowlen, int *slow, int *scol_out, double *sval_out)
+{
+   const int i = row_lo + blockIdx.x * blockDim.x + threadIdx.x;
+   if (i >= row_hi) return;
+   const int       ci = cf[i];
+   const long long p0 = (long long)i * max_elmts;
+   if (ci > 0) { cnt[i] = 1; rowlen[i] = 1; slow[i] = 0; scol_out[p0] = f2c[i]; sval_out[p0] = 1.0; return; }
+   if (ci == SF_PT) { cnt[i] = 0; rowlen[i] = 0; slow[i] = 0; return; }
+   int    lc[IS_CAP], fk[IS_F];
+   double lv[IS_CAP];
+   int    nC = 0, nF = 0;
+   bool   overflow = false;
+   // discovery of C-hat_i in hypre's order
+   for (int k = srp[i]; k < srp[i + 1] && !overflow; k++)
+   {
+      const int i1 = scol[k], c1 = cf[i1];
+      if (c1 > 0)
+      {
+         if (is_find(lc, nC, i1) < 0) { if (nC < IS_CAP) { lc[nC] = i1; lv[nC] = 0.0; nC++; } else overflow = true; }
+      }
+      else if (c1 != SF_PT)
+      {
+         if (nF < IS_F) fk[nF++] = i1; else overflow = true;
+         for (int kk = srp[i1]; kk < srp[i1 + 1] && !overflow; kk++)
+         {
+            const int k1 = scol[kk];
+            if (cf[k1] > 0 && is_find(lc, nC, k1) < 0) { if (nC < IS_CAP) { lc[nC] = k1; lv[nC] = 0.0; nC++; } else overflow = true; }
+         }
+      }
+   }
+   if (overflow) { cnt[i] = 0; rowlen[i] = 0; slow[i] = 1; return; } // (the table-based path does this row)
+   cnt[i] = nC; rowlen[i] = (nC > max_elmts) ? max_elmts : nC; slow[i] = 0;
+   // weights: the row of A in stored order
+   double diagonal = aval[arp[i]];
+   for (int jj = arp[i] + 1; jj < arp[i + 1]; jj++)
+   {
+      const int    i1 = acol[jj];
+      const double a  = aval[jj];
+      const int    m  = is_find(lc, nC, i1);
+      if (m >= 0) lv[m] = __dadd_rn(lv[m], a);
+      else if (is_find(fk, nF, i1) >= 0)
+      {
+         double       sum = 0.0;
+         const int    b1 = arp[i1] + 1, e1 = arp[i1 + 1];
+         const double sgn = aval[b1 - 1] < 0 ? -1.0 : 1.0;
+         for (int j1 = b1; j1 < e1; j1++)
+         {
+            const int    i2 = acol[j1];
+            const double v  = aval[j1];
+            if (sgn * v < 0 && (i2 == i || is_find(lc, nC, i2) >= 0)) sum = __dadd_rn(sum, v);
+         }
+         if (sum != 0.0)
+         {
+            const double distribute = __ddiv_rn(a, sum);
+            for (int j1 = b1; j1 < e1; j1++)
+            {
+               const int    i2 = acol[j1];
+               const double v  = aval[j1];
+               if (sgn * v < 0)
+               {
+                  const int m2 = is_find(lc, nC, i2);
+                  if (m2 >= 0) lv[m2] = __dadd_rn(lv[m2], __dmul_rn(distribute, v));
+                  if (i2 == i) diagonal = __dadd_rn(diagonal, __dmul_rn(distribute, v));
+               }
+            }
+         }
+         else diagonal = __dadd_rn(diagonal, a);
+      }
+      else if (cf[i1] != SF_PT) diagonal = __dadd_rn(diagonal, a);
+   }
+   if (diagonal != 0.0)
+   {
+      const double nd = -diagonal;
+      for (int k = 0; k < nC; k++) lv[k] = __ddiv_rn(lv[k], nd);
+   }
+   int len = nC;
+   if (nC > max_elmts)
+   {
+      double row_sum = 0.0, scale = 0.0;
+      for (int k = 0; k < nC; k++) row_sum = __dadd_rn(row_sum, lv[k]);
+      qsort2abs_dev(lc, lv, nC, max_elmts);
+      for (int k = 0; k < max_elmts; k++) scale = __dadd_rn(scale, lv[k]);
+      if (scale != 0.0 && scale != row_sum)
+      {
+         scale = __ddiv_rn(row_sum, scale);
+         for (int k = 0; k < max_elmts; k++) lv[k] = __dmul_rn(lv[k], scale);
+      }
+      len = max_elmts;
+   }
+   for (int k = 0; k < len; k++) { scol_out[p0 + k] = f2c[lc[k]]; sval_out[p0 + k] = lv[k]; }
+}
+
 // ---- warp-per-row extended+i interpolation (shared-memory hash + candidate list) ----------
 // Same sequence of operations as the one-thread version (and the oracle): C-hat is discovered
 // in hypre's order (chunks of 32 candidates, slots assigned in lane order), the weight loop
@@ -1029,20 +1138,28 @@ int build_interp(const DevCSR &A, const DevCSR &S, int *cf, const int *f2c, int 
       HDK_CUDA(cudaMemsetAsync(cnt, 0, sizeof(int) * ((size_t)n + 1), g.stream));
       HDK_CUDA(cudaMemsetAsync(rowlen, 0, sizeof(int) * ((size_t)n + 1), g.stream));
    }
-   // Single-pass interpolation (rows of at most max_elmts entries, warp path): discovery and weights in
-   // ONE launch into a fixed-stride staging buffer, row lengths from the same launch; the counting pass
-   // below is only needed when rows are unbounded (no truncation) or go one thread per row.
+   // Single-pass interpolation (rows of at most max_elmts entries): discovery and weights in ONE launch
+   // into a fixed-stride staging buffer, row lengths from the same launch -- one warp per row with a
+   // shared-memory table, or one thread per row with thread-local arrays on the stencil levels.  The
+   // counting pass below is only needed when rows are unbounded (no truncation) or for flagged rows.
    static int interp_single = -1;
    if (interp_single < 0) { const char *e = getenv("HDK_INTERP_SINGLE"); interp_single = (e && atoi(e) == 0) ? 0 : 1; }
-   const bool staged = interp_single == 1 && !force_slow && max_elmts > 0 && (long long)n * max_elmts < 2000000000LL;
+   const bool staged = interp_single == 1 && max_elmts > 0 && (long long)n * max_elmts < 2000000000LL;
    int    *stg_col = nullptr;
    double *stg_val = nullptr;
    if (staged)
    {
       HDK_TRY(dalloc(&stg_col, (size_t)n * max_elmts + 8));
       HDK_TRY(dalloc(&stg_val, (size_t)n * max_elmts + 8));
-      k_interp_warp<true, true><<<cdiv(hi - lo, IW_WARPS), 32 * IW_WARPS, 0, g.stream>>>(A.rowptr, A.col, A.val, S.rowptr, S.col, cf, f2c, hi,
-                                                                                         max_elmts, cnt, rowlen, slow, nullptr, stg_col, stg_val, 0, lo);
+      if (force_slow) // short rows: one thread per row with thread-local tables
+      {
+         if (hi > lo)
+            k_interp_small<<<cdiv(hi - lo, 128), 128, 0, g.stream>>>(A.rowptr, A.col, A.val, S.rowptr, S.col, cf, f2c, lo, hi, max_elmts,
+                                                                     cnt, rowlen, slow, stg_col, stg_val);
+      }
+      else
+         k_interp_warp<true, true><<<cdiv(hi - lo, IW_WARPS), 32 * IW_WARPS, 0, g.stream>>>(A.rowptr, A.col, A.val, S.rowptr, S.col, cf, f2c, hi,
+                                                                                            max_elmts, cnt, rowlen, slow, nullptr, stg_col, stg_val, 0, lo);
       HDK_LAUNCH_CHECK();
    }
    else
