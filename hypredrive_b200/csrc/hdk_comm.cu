@@ -95,7 +95,7 @@ struct IpcState
    bool                on = false;
    bool                mail_on = false;
    unsigned long long  mail_seq = 0;
-   long long           tmo = 0;              // wait budget of the in-kernel waits (clock64 ticks)
+   long long           tmo = 0;              // wait budget of the flag waits (clock64 ticks)
    int                *err_d = nullptr;      // device word raised by a kernel whose wait ran out (polled from
                                              // L2 by the waiting threads, read by the host at the end of a solve)
    char               *base = nullptr;

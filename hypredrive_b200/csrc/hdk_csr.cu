@@ -518,7 +518,7 @@ __global__ void k_stencil_fill(int kind, int nx, int ny, int nz, double c0, doub
    }
 }
 
-// wait budget / error flag of this translation unit's copy of the in-kernel wait globals
+// wait budget / error flag of this translation unit's copy of the flag-wait globals
 int wait_globals_csr(long long tmo, int *err)
 {
    return wait_globals_set(tmo, err) == cudaSuccess ? HDK_OK : set_error(HDK_ERR_CUDA, "cannot set the wait budget");

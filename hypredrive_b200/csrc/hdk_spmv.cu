@@ -36,7 +36,7 @@ struct Tune
    double tgt_max       = 3072;     // HDK_SPMV_TGT_MAX     non-zeros per stream-kernel block (cap)
    double lpr           = 0;        // HDK_SPMV_LPR         force lanes per row (0 = by row length)
    double sell_min_rows = 200000;   // HDK_SELL_MIN_ROWS    sliced-ELL for matrices with at least this many rows
-   double sell_min_rows_dist = 30000;  // HDK_SELL_MIN_ROWS_DIST  the same for slabs with off-rank entries (fused halo wait)
+   double sell_min_rows_dist = 30000;  // HDK_SELL_MIN_ROWS_DIST  the same for slabs with off-rank entries (fused off-rank block)
    double sell_min_avg  = 0.0;      // HDK_SELL_MIN_AVG     ... and more than this many non-zeros per row
    double sell_sort     = 1;        // HDK_SELL_SORT        sort the columns of coarse operators in the slices
    double amg_keep_debug = 0;       // HDK_AMG_KEEP_DEBUG   keep S and the PMIS measures of every level (introspection)
@@ -957,7 +957,7 @@ void csr_free(DevCSR &A)
    A = DevCSR();
 }
 
-// wait budget / error flag of this translation unit's copy of the in-kernel wait globals
+// wait budget / error flag of this translation unit's copy of the flag-wait globals
 int wait_globals_spmv(long long tmo, int *err)
 {
    return wait_globals_set(tmo, err) == cudaSuccess ? HDK_OK : set_error(HDK_ERR_CUDA, "cannot set the wait budget");

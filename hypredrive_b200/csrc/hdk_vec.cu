@@ -406,7 +406,7 @@ int vec_dot_host(const double *x, const double *y, int64_t n, double *out_h)
    return HDK_OK;
 }
 
-// wait budget / error flag of this translation unit's copy of the in-kernel wait globals
+// wait budget / error flag of this translation unit's copy of the flag-wait globals
 int wait_globals_vec(long long tmo, int *err)
 {
    return wait_globals_set(tmo, err) == cudaSuccess ? HDK_OK : set_error(HDK_ERR_CUDA, "cannot set the wait budget");

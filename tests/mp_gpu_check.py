@@ -27,7 +27,7 @@ def main():
     if shared:
         # fewer GPUs than ranks: the ranks share cuda:0.  NCCL refuses two ranks on one device of one
         # host, so every rank reports its own host id and the ranks talk through NCCL's socket
-        # transport on the loopback interface.  The peer-memory halo path (in-kernel waits on another
+        # transport on the loopback interface.  The peer-memory halo path (kernels waiting on another
         # process of the same GPU) is switched off unless MPCHECK_SHARED_IPC=1.
         local = local % max(torch.cuda.device_count(), 1)
         os.environ["NCCL_HOSTID"] = f"hdk-one-gpu-rank{rank}"

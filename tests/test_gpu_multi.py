@@ -35,8 +35,8 @@ def _run(world, args, env_extra=None):
     ("lap7", ("12", "11", "6"), "40", "off"),
     # NCCL send/recv halo exchange instead of the peer-memory (CUDA IPC) path
     ("lap7", ("12", "11", "6"), "40", "nccl"),
-    # sliced-ELL kernel on every level: off-diagonal block fused into the SpMV kernel (in-kernel
-    # wait on the neighbours' flags), and the same layout with the separate correction kernel
+    # sliced-ELL kernel on every level: off-rank block fused into the SpMV kernel, and the same layout
+    # with the separate correction kernel
     ("lap7", ("16", "16", "10"), "40", "sell-fused"), ("lap27", ("8", "8", "6"), "30", "sell-fused"),
     ("convdif", ("16", "8", "6"), "40", "sell-fused"), ("lap7", ("16", "16", "10"), "40", "sell-unfused"),
     ("lap7", ("12", "11", "6"), "40", "sell-nccl"),
