@@ -163,7 +163,7 @@ static std::vector<TlMark> tl_marks;
 static bool                tl_on = false;
 void tl_mark(int level, int op)
 {
-   if (!tl_on) return;
+   if (!tl_on || tl_marks.size() >= 1000000) return; // (a forgotten timeline does not grow without bound)
    TlMark m;
    m.code = level * 16 + op;
    if (cudaEventCreate(&m.ev) != cudaSuccess) return;
