@@ -4,13 +4,16 @@ binaries travel to the GPU box under oracle/_ref/):
   * examples/src/C_laplacian/laplacian.c  -- `laplacian -n 10 10 10`: the STATISTICS table must
     have the layout of the reference's golden output (examples/refOutput/laplacian.txt,
     transcribed into tests/golden/laplacian_layout.json) with the same initial residual norm;
-    the iteration count is the GPU-default chain's (PMIS + l1-Jacobi), checked against the oracle.
+    the iteration count is the GPU-default chain's (PMIS + l1-Jacobi), checked against the oracle;
+    also as two ranks (`-P 1 1 2`, communicator from the launcher environment).
   * tests/test_setmatrix_from_csr.c       -- the reference's unit test of the CSR ingest path runs
     green (its own assertions: error bits, known answers, offset slabs)."""
 import json
 import os
 import re
 import subprocess
+
+import numpy as np
 
 import pytest
 
@@ -56,3 +59,41 @@ def test_reference_unit_test_of_the_csr_ingest_path(gpu):
     exe = _need("test_setmatrix_from_csr")
     r = subprocess.run([exe], capture_output=True, text=True, timeout=600, cwd=ROOT)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+
+
+def test_reference_laplacian_driver_as_two_ranks(gpu, tmp_path):
+    """The same unmodified example as TWO processes (its own `-P 1 1 2` z-split and MPI calls on the
+    `include/mpi.h` shim): the communicator comes from the launcher environment
+    (`hdk_comm_init_from_env`, rank 0 publishes the NCCL id in a file), the hierarchy is set up
+    row-distributed, and the printed iteration count / residual are the oracle's for the whole grid."""
+    from oracle import oracle as O
+    exe = _need("laplacian")
+    shared = gpu.device_count() < 2
+    procs = []
+    for r in range(2):
+        env = dict(os.environ, RANK=str(r), WORLD_SIZE="2", LOCAL_RANK=str(r), MASTER_ADDR="127.0.0.1", MASTER_PORT="29777",
+                   HDK_NCCL_ID_FILE=str(tmp_path / "nccl_id"), NCCL_SOCKET_IFNAME="lo", NCCL_IB_DISABLE="1")
+        if shared:      # both ranks on the one GPU: NCCL needs distinct host ids, no peer-memory halo between them
+            env.update(NCCL_HOSTID=f"hdk-ref-rank{r}", HDK_HALO_IPC="0")
+        procs.append(subprocess.Popen([exe, "-n", "10", "10", "20", "-P", "1", "1", "2"], stdout=subprocess.PIPE,
+                                      stderr=subprocess.STDOUT, text=True, env=env, cwd=ROOT))
+    outs = []
+    for p in procs:
+        try:
+            out, _ = p.communicate(timeout=300)
+        except subprocess.TimeoutExpired:
+            for q in procs:
+                q.kill()
+            raise
+        outs.append(out)
+    assert all(p.returncode == 0 for p in procs), outs[0][-2000:] + outs[1][-2000:]
+    out = outs[0].splitlines()
+    assert "Processor topology:   1 x 1 x 2" in out
+    rows = [l for l in out[out.index("STATISTICS SUMMARY:") + 6:] if l.startswith("|")]
+    assert len(rows) == 5 and not any(l.startswith("|") for l in outs[1].splitlines())   # rank 0 prints the table
+    A, b = O.gen("lap7", 10, 10, 20)
+    _, info = O.pcg(A, b, M=O.Hierarchy(A, O.default_params(True)), rel_tol=1e-6)
+    for row in rows:
+        cells = [c.strip() for c in row.split("|")[1:-1]]
+        assert int(cells[6]) == info["iters"]
+        assert cells[4] == "%.2e" % np.linalg.norm(b) and cells[5] == "%.2e" % info["rel_res_norm"]
