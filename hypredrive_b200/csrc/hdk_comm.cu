@@ -4,6 +4,8 @@
 // src/HYPREDRV.c:1014-1043, src/internal/runtime.c:118-133).  NCCL is bound at run time with
 // dlopen so that a process that already carries torch's libnccl shares that copy.
 #include "hdk_internal.cuh"
+#include <sys/stat.h>
+#include <time.h>
 #include <dlfcn.h>
 #include <time.h>
 #include <algorithm>
@@ -876,10 +878,14 @@ int hdk_comm_init_from_env(void)
    }
    else
    {
-      bool got = false;
+      // a file left behind by a run that died before rank 0 removed it must not be taken for this run's:
+      // only files written at most two minutes before this rank got here count
+      const time_t t_entry = time(nullptr);
+      bool         got = false;
       for (int tries = 0; tries < 1200 && !got; tries++) // up to 2 minutes
       {
-         FILE *fp = fopen(path, "rb");
+         struct stat st;
+         FILE       *fp = (stat(path, &st) == 0 && st.st_mtime + 120 >= t_entry) ? fopen(path, "rb") : nullptr;
          if (fp) { got = fread(id, 1, 128, fp) == 128; fclose(fp); }
          if (!got) { struct timespec ts = {0, 100000000L}; nanosleep(&ts, nullptr); }
       }
